@@ -1,0 +1,242 @@
+/*
+ * omfs_b200.h — C-ABI of the B200-native surgery-render hot path.
+ *
+ * The reference (cwlachap/OMFS-4D-Video-Gen) has no FFI / operator table for this path: it
+ * reaches its renderer by spawning a process
+ * (02_Visual_Engine/render_surgery.py:289-315, `render_with_gaussians`).  The entry points
+ * below are what an in-process binding at that replacement point needs; each comment names
+ * the reference interface (file:line) or the un-vendored upstream unit
+ * it stands in for.  INTEGRATION.md shows the ctypes stub a maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross the boundary;
+ *   - every function returns 0 on success, a negative omfs_status otherwise, and never
+ *     throws; omfs_last_error() gives the message of the last failure on this thread;
+ *   - "d_" arguments are device pointers, "h_" host pointers; stream is a cudaStream_t
+ *     passed as void* (NULL = default stream);
+ *   - level-1 functions (kernels) never allocate: scratch comes from the caller
+ *     (omfs_binning_workspace_bytes); level-2 (omfs_session_*) owns its device buffers
+ *     between create and destroy;
+ *   - all float data is IEEE binary32, images are [S,3,H,W] planar float or [S,H,W,3] uint8.
+ */
+#ifndef OMFS_B200_H
+#define OMFS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define OMFS_ABI_VERSION 1
+#define OMFS_TILE 16          /* compositing tile edge, pixels */
+#define OMFS_FF_STRIDE 20     /* floats per face-frame record */
+#define OMFS_CAM_FLOATS 40    /* floats per camera record (cameras.py: Camera.pack) */
+#define OMFS_N_JOINTS 5
+#define OMFS_N_POSE_FEAT 36
+
+typedef enum omfs_status {
+    OMFS_OK = 0,
+    OMFS_ERR_INVALID = -1,     /* bad argument */
+    OMFS_ERR_CUDA = -2,        /* a CUDA call failed; see omfs_last_error() */
+    OMFS_ERR_CAPACITY = -3,    /* tile-pair list overflowed the caller's capacity */
+    OMFS_ERR_UNSUPPORTED = -4, /* no sm_100 device / feature missing */
+    OMFS_ERR_NOMEM = -5
+} omfs_status;
+
+const char* omfs_last_error(void);
+int omfs_abi_version(void);
+/* 0 when device `dev` is an sm_100 part this library can run on. */
+int omfs_device_check(int dev);
+
+/* ------------------------------------------------------------------------------------------
+ * Level 1 — one call per pipeline stage, device pointers in and out.
+ * ---------------------------------------------------------------------------------------- */
+
+/* U1+U2 operand prep (the in-tree anchor is SimpleFLAME.forward,
+ * 02_Visual_Engine/flame_fitter.py:154-175).  Per frame: Rodrigues of the 5 joint rotations
+ * -> d_rmats[T,5,9]; coefficient row [expr | pose features | 0] split into tf32 hi/lo and laid
+ * out as the GEMM's A operand d_acoef[T,3*kpad] = [hi | hi | lo].  kpad = round_up(n_expr+36, 8). */
+int omfs_flame_pose_prep(int T, int n_expr, int kpad,
+                         const float* d_expr, const float* d_rotation, const float* d_neck,
+                         const float* d_jaw, const float* d_eyes,
+                         float* d_acoef, float* d_rmats, void* stream);
+
+/* U1+U2 contraction: d_vp[T,npad] = d_base[npad] + A[T,3*kpad] . Bt[npad,3*kpad]^T.
+ * Columns 0..3V-1 are posed-template vertices before skinning, 3V..3V+14 the 5 joints.
+ * impl 0 = tcgen05/TMA tensor-core kernel (tf32x3), 1 = fp32 CUDA-core kernel (same operands;
+ * kept as the cross-check and for T < 16). */
+int omfs_flame_blend_gemm(int T, int kpad, int npad,
+                          const float* d_acoef, const float* d_bt, const float* d_base,
+                          float* d_vp, int impl, void* stream);
+
+/* U3: linear-blend skinning.  d_verts[T,V,3] = sum_j W[v,j] A_j(t) [v_posed;1] + transl[t];
+ * the kinematic chain A_j(t) is rebuilt per block from d_rmats and the joint columns of d_vp.
+ * d_dyn (optional, [T,V,3]) is the per-frame dynamic offset; d_jdyn (optional, [T,15]) its
+ * joint contribution. */
+int omfs_flame_lbs(int T, int V, int npad,
+                   const float* d_vp, const float* d_rmats, const float* d_weights /*[V,5]*/,
+                   const float* d_transl /*[T,3]*/, const float* d_dyn, const float* d_jdyn,
+                   float* d_verts, void* stream);
+
+/* J_reg . dyn[t] -> d_jdyn[T,15] (only needed when dynamic offsets are non-zero). */
+int omfs_flame_joint_dyn(int T, int V, const float* d_jreg /*[5,V]*/, const float* d_dyn, float* d_jdyn,
+                         void* stream);
+
+/* U4: per-face centre, orthonormal frame, isotropic scale, unit quaternion.
+ * d_ff[T,F,20] = [cx cy cz s | qw qx qy qz | R row0,0 | R row1,0 | R row2,0]. */
+int omfs_face_frames(int T, int V, int F, const float* d_verts, const int32_t* d_faces, float* d_ff,
+                     void* stream);
+
+/* U5+U6 fused: parent-triangle transform of every Gaussian, then cull / project / EWA / SH.
+ * One segment = one (frame, camera) pair; d_seg_frame[S] gives the frame of each segment and
+ * d_cams[S,40] its camera.  Outputs are [S,N,4] float4 streams plus d_tiles_touched[S,N]:
+ *   P0 = (px, py, depth, radius as int32 bits)  P1 = (ca, cb, cc, lo)  P2 = (r, g, b, 0). */
+int omfs_bind_preprocess(int S, int N, int F, int width, int height,
+                         const float* d_ff, const int32_t* d_seg_frame, const float* d_cams,
+                         const float* d_xyzb, const float* d_scale_lo, const float* d_rot, const float* d_sh,
+                         float* d_P0, float* d_P1, float* d_P2, uint32_t* d_tiles_touched, void* stream);
+
+/* U7+U8+U9: inclusive scan of tiles_touched, key emission ((seg*tiles+tile)<<32 | depth bits,
+ * value = Gaussian index in its segment), onesweep LSD radix sort on the low sort_bits bits,
+ * tile ranges.  capacity = max tile pairs the key/value buffers hold.  The sorted pairs end up
+ * in d_keys[out]/d_vals[out] where *h_out_buffer_index (0 or 1) is returned immediately (it only
+ * depends on sort_bits).  d_num_pairs (uint32 on device) receives the pair count; if it exceeds
+ * capacity the batch is truncated and d_status_flag (int on device) is set to 1. */
+size_t omfs_binning_workspace_bytes(int S, int N, int width, int height, size_t capacity);
+int omfs_binning(int S, int N, int width, int height, size_t capacity,
+                 const float* d_P0, const uint32_t* d_tiles_touched,
+                 uint32_t* d_offsets, uint64_t* d_keys0, uint64_t* d_keys1, uint32_t* d_vals0, uint32_t* d_vals1,
+                 uint32_t* d_ranges /*[S*tiles,2]*/, uint32_t* d_num_pairs, int* d_status_flag,
+                 void* d_workspace, size_t workspace_bytes, int* h_out_buffer_index, void* stream);
+
+/* U10: front-to-back alpha compositing, one 16x16 tile per CTA.  d_image[S,3,H,W];
+ * d_image_u8 (optional) [S,H,W,3] gets the save_image quantisation in the same kernel. */
+int omfs_composite(int S, int N, int width, int height,
+                   const float* d_P0, const float* d_P1, const float* d_P2,
+                   const uint32_t* d_sorted_vals, const uint32_t* d_ranges, const float* bg3,
+                   float* d_image, uint8_t* d_image_u8, void* stream);
+
+/* R5/R6 (01_Clinical_Engine/surgical_sim.py:25-47, 180-204, 262-329): half-space masks and the
+ * rigid move of the two mobile segments, on an arbitrary point set, in float64.
+ *   planes[3][8]  = {nx,ny,nz, ox,oy,oz, 0,0} for Le Fort, BSSO-L, BSSO-R (normals from
+ *                   _angle_to_normal, evaluated on the host in float64);
+ *   moves[2][12]  = row-major 3x3 rotation then translation, for maxilla and mandible
+ *                   (rotation about the segment's bounding-box centre, as PyVista's
+ *                   `mesh.center` is, surgical_sim.py:300,312);
+ *   d_jaw_weight  optional [P]: points with weight > 0.5 belong to the mandible side
+ *                   (NULL: `mandible_first` points by index belong to it);
+ *   d_mask[P]     bit0 (p-o).n<=0 for Le Fort, bit1 (p-o).n>0 for BSSO-L, bit2 (p-o).n<=0 for
+ *                 BSSO-R, bit3 = mobile maxilla, bit4 = distal mandible;
+ *   d_out[P,3]    moved points (float32), d_bbox[2][6] the two segment bounding boxes. */
+int omfs_displace_points(int P, const float* d_points, const double* h_planes, const double* h_moves,
+                         const float* d_jaw_weight, int mandible_first,
+                         uint8_t* d_mask, float* d_out, float* d_bbox /*[12]*/, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Level 2 — a render session: model + avatar resident in HBM, frames streamed in batches.
+ * This is the call that replaces the body of render_with_gaussians
+ * (02_Visual_Engine/render_surgery.py:245-362).
+ * ---------------------------------------------------------------------------------------- */
+typedef struct omfs_session omfs_session;
+
+typedef struct omfs_model_desc {
+    int32_t n_verts, n_faces, n_expr, n_gauss;
+    const float* v_template;   /* [V,3] */
+    const float* shapedirs;    /* [300+n_expr, 3V] row k = direction k */
+    const float* posedirs;     /* [36, 3V] */
+    const float* j_regressor;  /* [5,V] */
+    const float* lbs_weights;  /* [V,5] */
+    const int32_t* faces;      /* [F,3] */
+    /* baked avatar (avatar.py: bake_avatar) */
+    const float* xyzb;         /* [N,4] */
+    const float* scale_lo;     /* [N,4] */
+    const float* rot;          /* [N,4] */
+    const float* sh;           /* [12,N,4] */
+} omfs_model_desc;
+
+typedef struct omfs_session_config {
+    int32_t width, height;
+    int32_t max_batch;          /* segments (frame x view) per launch group */
+    int32_t device;
+    int32_t gemm_impl;          /* 0 tensor core, 1 CUDA core */
+    int32_t use_graph;          /* replay each batch as a CUDA graph */
+    uint64_t pair_capacity;     /* tile pairs per batch; 0 = 24 * max_batch * n_gauss / 4 */
+    float bg[3];
+} omfs_session_config;
+
+int omfs_session_create(const omfs_model_desc* model, const omfs_session_config* cfg, omfs_session** out);
+void omfs_session_destroy(omfs_session* s);
+
+/* Per-subject fold: base = v_template + shapedirs[:300].shape + static_offset (+ plan_offset),
+ * joint base = J_reg . base.  Host pointers; plan_offset may be NULL. */
+int omfs_session_set_subject(omfs_session* s, const float* h_shape300, const float* h_static_offset,
+                             const float* h_plan_offset);
+
+typedef struct omfs_frames_desc {
+    int32_t n_frames;           /* T */
+    int32_t n_views;            /* cameras per frame; segments = T * n_views, view-minor */
+    const float* expr;          /* [T,n_expr] */
+    const float* rotation;      /* [T,3] */
+    const float* neck_pose;     /* [T,3] */
+    const float* jaw_pose;      /* [T,3] */
+    const float* eyes_pose;     /* [T,6] */
+    const float* translation;   /* [T,3] */
+    const float* dynamic_offset;/* [T,V,3] or NULL */
+    const float* cams;          /* [n_views,40] */
+} omfs_frames_desc;
+
+/* Host in, host out: parameters are copied host->device, frames come back as uint8 [S,H,W,3]
+ * (h_out_u8) and/or float [S,3,H,W] (h_out_f32); either may be NULL.  Pinned host memory
+ * makes the copies asynchronous.  Blocks until the frames are in host memory. */
+int omfs_session_render_host(omfs_session* s, const omfs_frames_desc* frames,
+                             uint8_t* h_out_u8, float* h_out_f32);
+
+/* Device in, device out (inputs already resident; same field meaning, device pointers).
+ * d_out_u8 / d_out_f32 may be NULL.  Asynchronous on `stream`. */
+int omfs_session_render_device(omfs_session* s, const omfs_frames_desc* d_frames,
+                               uint8_t* d_out_u8, float* d_out_f32, void* stream);
+
+/* Counters of the last render call: [0] tile pairs, [1] kernel launches, [2] batches,
+ * [3] overflow flag. */
+int omfs_session_stats(omfs_session* s, uint64_t* out4);
+
+/* Debug taps for the parity tests: pointers into the session's buffers for the LAST batch
+ * rendered (valid until the next call).  Names: "verts" "ff" "P0" "P1" "P2" "tiles_touched"
+ * "offsets" "keys_unsorted" "vals_unsorted" "keys" "vals" "ranges" "image" "vp" "acoef". */
+int omfs_session_tap(omfs_session* s, const char* name, void** d_ptr, size_t* bytes);
+
+/* Waits for the session's streams; returns OMFS_ERR_CAPACITY if any batch overflowed. */
+int omfs_session_sync(omfs_session* s);
+void* omfs_session_stream(omfs_session* s);
+/* out8 = V, F, n_expr, N, kpad, npad, tiles, segments of the last batch */
+int omfs_session_dims(omfs_session* s, int32_t* out8);
+
+/* ------------------------------------------------------------------------------------------
+ * Helpers for callers without a CUDA runtime of their own (ctypes, cgo, JNI ...).
+ * ---------------------------------------------------------------------------------------- */
+int omfs_host_alloc(void** p, size_t bytes);   /* page-locked host memory */
+int omfs_host_free(void* p);
+int omfs_device_alloc(void** p, size_t bytes);
+int omfs_device_free(void* p);
+int omfs_memcpy_h2d(void* d_dst, const void* h_src, size_t bytes);
+int omfs_memcpy_d2h(void* h_dst, const void* d_src, size_t bytes); /* synchronises the device first */
+int omfs_device_sync(void);
+unsigned long long omfs_launch_count(void);    /* kernels launched by this library so far */
+
+/* Level-1 extras used by the parity tests and by omfs_session_set_subject. */
+int omfs_flame_fold_subject(int V, int n_shape, int npad, const float* d_template, const float* d_shapedirs,
+                            const float* d_shape, const float* d_static, const float* d_plan, const float* d_jreg,
+                            float* d_base, void* stream);
+int omfs_scan_emit(int S, int N, int width, int height, size_t capacity, const float* d_P0,
+                   const uint32_t* d_tiles_touched, uint32_t* d_offsets, uint64_t* d_keys, uint32_t* d_vals,
+                   uint32_t* d_num_pairs, int* d_status_flag, void* d_workspace, size_t workspace_bytes,
+                   void* stream);
+int omfs_binning_sort_bits(int S, int width, int height);
+int omfs_to_uint8(int S, int width, int height, const float* d_image, uint8_t* d_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* OMFS_B200_H */

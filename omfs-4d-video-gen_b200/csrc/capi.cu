@@ -1,0 +1,553 @@
+// capi.cu — error plumbing, device check and the level-2 render session of include/omfs_b200.h.
+//
+// The session is the in-process replacement for the body of the reference's
+// render_with_gaussians (02_Visual_Engine/render_surgery.py:245-362): model and avatar are
+// uploaded once and stay resident in HBM; frames are processed in batches of `max_batch`
+// segments (frame x view), every stage of a batch being ONE launch over all its segments.
+// FLAME evaluation (pose prep, tensor-core blendshape GEMM, skinning) runs over larger frame
+// chunks so that the GEMM sees M >= 128 rows whenever the clip is long enough.
+// Finished frames leave through a second stream (double-buffered images) so the device->host
+// copy of batch i overlaps the kernels of batch i+1.
+#include <stdarg.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "common.cuh"
+
+namespace omfs {
+
+static thread_local char g_err[1024] = "";
+unsigned long long g_launches = 0;
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+    set_error("CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e), file, line, what);
+    return OMFS_ERR_CUDA;
+}
+
+}  // namespace omfs
+
+using namespace omfs;
+
+extern "C" int omfs_flame_fold_subject(int V, int n_shape, int npad, const float* d_template,
+                                       const float* d_shapedirs, const float* d_shape, const float* d_static,
+                                       const float* d_plan, const float* d_jreg, float* d_base, void* stream);
+extern "C" int omfs_to_uint8(int S, int width, int height, const float* d_image, uint8_t* d_out, void* stream);
+
+extern "C" const char* omfs_last_error(void) { return g_err; }
+extern "C" int omfs_abi_version(void) { return OMFS_ABI_VERSION; }
+extern "C" unsigned long long omfs_launch_count(void) { return g_launches; }
+
+extern "C" int omfs_device_check(int dev) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || dev < 0 || dev >= count) {
+        set_error("no CUDA device %d (count=%d, %s)", dev, count, cudaGetErrorString(e));
+        return OMFS_ERR_UNSUPPORTED;
+    }
+    cudaDeviceProp p;
+    OMFS_CUDA(cudaGetDeviceProperties(&p, dev));
+    if (p.major != 10) {
+        set_error("device %d is sm_%d%d; this library is built for sm_100a (B200) only", dev, p.major, p.minor);
+        return OMFS_ERR_UNSUPPORTED;
+    }
+    return OMFS_OK;
+}
+
+extern "C" int omfs_host_alloc(void** p, size_t bytes) {
+    OMFS_REQUIRE(p != nullptr, "null pointer");
+    OMFS_CUDA(cudaMallocHost(p, bytes));
+    return OMFS_OK;
+}
+extern "C" int omfs_host_free(void* p) {
+    OMFS_CUDA(cudaFreeHost(p));
+    return OMFS_OK;
+}
+extern "C" int omfs_device_alloc(void** p, size_t bytes) {
+    OMFS_REQUIRE(p != nullptr, "null pointer");
+    OMFS_CUDA(cudaMalloc(p, bytes));
+    return OMFS_OK;
+}
+extern "C" int omfs_device_free(void* p) {
+    OMFS_CUDA(cudaFree(p));
+    return OMFS_OK;
+}
+extern "C" int omfs_memcpy_h2d(void* d_dst, const void* h_src, size_t bytes) {
+    OMFS_CUDA(cudaMemcpy(d_dst, h_src, bytes, cudaMemcpyHostToDevice));
+    return OMFS_OK;
+}
+extern "C" int omfs_memcpy_d2h(void* h_dst, const void* d_src, size_t bytes) {
+    OMFS_CUDA(cudaDeviceSynchronize());
+    OMFS_CUDA(cudaMemcpy(h_dst, d_src, bytes, cudaMemcpyDeviceToHost));
+    return OMFS_OK;
+}
+extern "C" int omfs_device_sync(void) {
+    OMFS_CUDA(cudaDeviceSynchronize());
+    return OMFS_OK;
+}
+
+// --------------------------------------------------------------------------------------------
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    int ensure(size_t need) {
+        if (need <= bytes) return OMFS_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+        const size_t want = need + need / 4;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            p = nullptr;
+            set_error("cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+            return OMFS_ERR_NOMEM;
+        }
+        bytes = want;
+        return OMFS_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
+    template <typename T>
+    T* as() const {
+        return reinterpret_cast<T*>(p);
+    }
+};
+
+struct omfs_session {
+    omfs_session_config cfg{};
+    int V = 0, F = 0, n_expr = 0, N = 0, kpad = 0, npad = 0, tiles = 0;
+    size_t capacity = 0;
+    int geo_chunk = 512;  // frames per FLAME launch group
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t ev_done[2]{}, ev_copied[2]{};
+    bool subject_set = false;
+    // model (resident)
+    DevBuf template_, shapedirs, bt, jreg, weights, faces, xyzb, scale_lo, rot, sh, base;
+    // subject staging
+    DevBuf shape, static_off, plan_off;
+    // per call
+    DevBuf expr, rotation, neck, jaw, eyes, transl, dyn, jdyn, cams, seg_frame;
+    // per geometry chunk
+    DevBuf acoef, rmats, vp, verts;
+    // per batch
+    DevBuf ff, P0, P1, P2, tt, offsets, keys0, keys1, vals0, vals1, ranges, counters, ws, image[2], image_u8[2];
+    size_t ws_bytes = 0;
+    int last_sorted_buffer = 0, last_image_buffer = 0, last_batch_segments = 0;
+    uint64_t stats[4]{};
+};
+
+static int upload(DevBuf& b, const void* h, size_t bytes, cudaStream_t st) {
+    int rc = b.ensure(bytes);
+    if (rc) return rc;
+    OMFS_CUDA(cudaMemcpyAsync(b.p, h, bytes, cudaMemcpyHostToDevice, st));
+    return OMFS_OK;
+}
+
+static inline float tf32_hi_host(float x) {
+    uint32_t u;
+    memcpy(&u, &x, 4);
+    u &= 0xffffe000u;
+    float r;
+    memcpy(&r, &u, 4);
+    return r;
+}
+
+extern "C" void omfs_session_destroy(omfs_session* s) {
+    if (!s) return;
+    cudaSetDevice(s->cfg.device);
+    if (s->stream) cudaStreamSynchronize(s->stream);
+    if (s->copy_stream) cudaStreamSynchronize(s->copy_stream);
+    DevBuf* all[] = {&s->template_, &s->shapedirs, &s->bt, &s->jreg, &s->weights, &s->faces, &s->xyzb,
+                     &s->scale_lo, &s->rot, &s->sh, &s->base, &s->shape, &s->static_off, &s->plan_off,
+                     &s->expr, &s->rotation, &s->neck, &s->jaw, &s->eyes, &s->transl, &s->dyn, &s->jdyn,
+                     &s->cams, &s->seg_frame, &s->acoef, &s->rmats, &s->vp, &s->verts, &s->ff, &s->P0, &s->P1,
+                     &s->P2, &s->tt, &s->offsets, &s->keys0, &s->keys1, &s->vals0, &s->vals1, &s->ranges,
+                     &s->counters, &s->ws, &s->image[0], &s->image[1], &s->image_u8[0], &s->image_u8[1]};
+    for (DevBuf* b : all) b->release();
+    for (int i = 0; i < 2; i++) {
+        if (s->ev_done[i]) cudaEventDestroy(s->ev_done[i]);
+        if (s->ev_copied[i]) cudaEventDestroy(s->ev_copied[i]);
+    }
+    if (s->stream) cudaStreamDestroy(s->stream);
+    if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
+    delete s;
+}
+
+extern "C" int omfs_session_create(const omfs_model_desc* m, const omfs_session_config* cfg, omfs_session** out) {
+    OMFS_REQUIRE(m && cfg && out, "null argument");
+    OMFS_REQUIRE(m->n_verts > 0 && m->n_faces > 0 && m->n_gauss > 0 && m->n_expr >= 0 && m->n_expr <= 400,
+                 "bad model sizes");
+    OMFS_REQUIRE(m->v_template && m->shapedirs && m->posedirs && m->j_regressor && m->lbs_weights && m->faces &&
+                     m->xyzb && m->scale_lo && m->rot && m->sh,
+                 "null model array");
+    OMFS_REQUIRE(cfg->width > 0 && cfg->height > 0 && cfg->max_batch > 0 && cfg->max_batch <= 65535, "bad config");
+    int rc = omfs_device_check(cfg->device);
+    if (rc) return rc;
+    OMFS_CUDA(cudaSetDevice(cfg->device));
+    omfs_session* s = new omfs_session();
+    s->cfg = *cfg;
+    s->V = m->n_verts;
+    s->F = m->n_faces;
+    s->n_expr = m->n_expr;
+    s->N = m->n_gauss;
+    s->kpad = ((m->n_expr + OMFS_N_POSE_FEAT) + 7) / 8 * 8;
+    s->npad = ((3 * s->V + 15) + 127) / 128 * 128;
+    s->tiles = ((cfg->width + kTile - 1) / kTile) * ((cfg->height + kTile - 1) / kTile);
+    s->capacity = cfg->pair_capacity ? (size_t)cfg->pair_capacity : (size_t)6 * cfg->max_batch * (size_t)s->N;
+    if (s->capacity >= (1ull << 30)) s->capacity = (1ull << 30) - 1;
+    const int V = s->V, V3 = 3 * V, N = s->N;
+#define TRY(x)                       \
+    do {                             \
+        rc = (x);                    \
+        if (rc) {                    \
+            omfs_session_destroy(s); \
+            return rc;               \
+        }                            \
+    } while (0)
+#define TRY_CUDA(x)                                                \
+    do {                                                           \
+        cudaError_t _e = (x);                                      \
+        if (_e != cudaSuccess) {                                   \
+            rc = omfs::cuda_fail(_e, #x, __FILE__, __LINE__);      \
+            omfs_session_destroy(s);                               \
+            return rc;                                             \
+        }                                                          \
+    } while (0)
+    TRY_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    TRY_CUDA(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; i++) {
+        TRY_CUDA(cudaEventCreateWithFlags(&s->ev_done[i], cudaEventDisableTiming));
+        TRY_CUDA(cudaEventCreateWithFlags(&s->ev_copied[i], cudaEventDisableTiming));
+    }
+    cudaStream_t st = s->stream;
+    TRY(upload(s->template_, m->v_template, sizeof(float) * V3, st));
+    TRY(upload(s->shapedirs, m->shapedirs, sizeof(float) * (size_t)300 * V3, st));
+    TRY(upload(s->jreg, m->j_regressor, sizeof(float) * 5 * V, st));
+    TRY(upload(s->weights, m->lbs_weights, sizeof(float) * 5 * V, st));
+    TRY(upload(s->faces, m->faces, sizeof(int32_t) * 3 * s->F, st));
+    TRY(upload(s->xyzb, m->xyzb, sizeof(float) * 4 * (size_t)N, st));
+    TRY(upload(s->scale_lo, m->scale_lo, sizeof(float) * 4 * (size_t)N, st));
+    TRY(upload(s->rot, m->rot, sizeof(float) * 4 * (size_t)N, st));
+    TRY(upload(s->sh, m->sh, sizeof(float) * 48 * (size_t)N, st));
+    TRY(s->base.ensure(sizeof(float) * s->npad));
+
+    // B' = [Bh | Bl | Bh] per output column, K-major.  Rows of B: n_expr expression directions, 36
+    // pose correctives; columns: 3V vertex coordinates then the 15 regressed joint coordinates.
+    {
+        const int kpad = s->kpad, K3 = 3 * kpad, npad = s->npad, ne = s->n_expr;
+        std::vector<float> bt((size_t)npad * K3, 0.f);
+        const float* exprdirs = m->shapedirs + (size_t)300 * V3;
+        for (int n = 0; n < V3; n++) {
+            float* row = bt.data() + (size_t)n * K3;
+            for (int k = 0; k < ne + OMFS_N_POSE_FEAT; k++) {
+                const float b = (k < ne) ? exprdirs[(size_t)k * V3 + n] : m->posedirs[(size_t)(k - ne) * V3 + n];
+                const float hi = tf32_hi_host(b), lo = tf32_hi_host(b - hi);
+                row[k] = hi;
+                row[kpad + k] = lo;
+                row[2 * kpad + k] = hi;
+            }
+        }
+        for (int j = 0; j < 5; j++)
+            for (int c = 0; c < 3; c++) {
+                float* row = bt.data() + (size_t)(V3 + j * 3 + c) * K3;
+                for (int k = 0; k < ne; k++) {
+                    double a = 0.0;
+                    const float* d = exprdirs + (size_t)k * V3;
+                    const float* jr = m->j_regressor + (size_t)j * V;
+                    for (int v = 0; v < V; v++) a += (double)jr[v] * (double)d[v * 3 + c];
+                    const float b = (float)a;
+                    const float hi = tf32_hi_host(b), lo = tf32_hi_host(b - hi);
+                    row[k] = hi;
+                    row[kpad + k] = lo;
+                    row[2 * kpad + k] = hi;
+                }
+            }
+        TRY(s->bt.ensure(sizeof(float) * bt.size()));
+        TRY_CUDA(cudaMemcpy(s->bt.p, bt.data(), sizeof(float) * bt.size(), cudaMemcpyHostToDevice));
+    }
+
+    // per-batch buffers
+    const size_t Sb = (size_t)cfg->max_batch;
+    const size_t hw = (size_t)cfg->width * cfg->height;
+    TRY(s->ff.ensure(sizeof(float) * kFF * Sb * s->F));
+    TRY(s->P0.ensure(sizeof(float) * 4 * Sb * N));
+    TRY(s->P1.ensure(sizeof(float) * 4 * Sb * N));
+    TRY(s->P2.ensure(sizeof(float) * 4 * Sb * N));
+    TRY(s->tt.ensure(sizeof(uint32_t) * Sb * N));
+    TRY(s->offsets.ensure(sizeof(uint32_t) * Sb * N));
+    TRY(s->keys0.ensure(sizeof(uint64_t) * s->capacity));
+    TRY(s->keys1.ensure(sizeof(uint64_t) * s->capacity));
+    TRY(s->vals0.ensure(sizeof(uint32_t) * s->capacity));
+    TRY(s->vals1.ensure(sizeof(uint32_t) * s->capacity));
+    TRY(s->ranges.ensure(sizeof(uint32_t) * 2 * Sb * s->tiles));
+    TRY(s->counters.ensure(256));
+    TRY_CUDA(cudaMemsetAsync(s->counters.p, 0, 256, st));
+    s->ws_bytes = omfs_binning_workspace_bytes((int)Sb, N, cfg->width, cfg->height, s->capacity);
+    TRY(s->ws.ensure(s->ws_bytes));
+    for (int i = 0; i < 2; i++) {
+        TRY(s->image[i].ensure(sizeof(float) * 3 * Sb * hw));
+        TRY(s->image_u8[i].ensure(3 * Sb * hw));
+    }
+    TRY_CUDA(cudaStreamSynchronize(st));
+#undef TRY
+#undef TRY_CUDA
+    *out = s;
+    return OMFS_OK;
+}
+
+extern "C" int omfs_session_set_subject(omfs_session* s, const float* h_shape300, const float* h_static_offset,
+                                        const float* h_plan_offset) {
+    OMFS_REQUIRE(s && h_shape300, "null argument");
+    OMFS_CUDA(cudaSetDevice(s->cfg.device));
+    const int V3 = 3 * s->V;
+    int rc = upload(s->shape, h_shape300, sizeof(float) * 300, s->stream);
+    if (rc) return rc;
+    if (h_static_offset) {
+        rc = upload(s->static_off, h_static_offset, sizeof(float) * V3, s->stream);
+        if (rc) return rc;
+    }
+    if (h_plan_offset) {
+        rc = upload(s->plan_off, h_plan_offset, sizeof(float) * V3, s->stream);
+        if (rc) return rc;
+    }
+    rc = omfs_flame_fold_subject(s->V, 300, s->npad, s->template_.as<float>(), s->shapedirs.as<float>(),
+                                 s->shape.as<float>(), h_static_offset ? s->static_off.as<float>() : nullptr,
+                                 h_plan_offset ? s->plan_off.as<float>() : nullptr, s->jreg.as<float>(),
+                                 s->base.as<float>(), s->stream);
+    if (rc) return rc;
+    OMFS_CUDA(cudaStreamSynchronize(s->stream));
+    s->subject_set = true;
+    return OMFS_OK;
+}
+
+// Core loop.  All `p_*` pointers are DEVICE pointers valid on s->stream.
+static int render_core(omfs_session* s, int T, int n_views, const float* p_expr, const float* p_rot,
+                       const float* p_neck, const float* p_jaw, const float* p_eyes, const float* p_transl,
+                       const float* p_dyn, const float* p_cams, uint8_t* out_u8, float* out_f32, bool out_on_host,
+                       cudaStream_t st) {
+    const int V = s->V, F = s->F, N = s->N, W = s->cfg.width, H = s->cfg.height;
+    const size_t hw = (size_t)W * H;
+    const unsigned long long launches0 = g_launches;
+    s->stats[0] = s->stats[2] = s->stats[3] = 0;
+    int rc;
+    const int fpb = std::max(1, s->cfg.max_batch / n_views);  // frames per render batch
+    const int geo = std::max(fpb, s->geo_chunk / fpb * fpb);   // frames per FLAME chunk (multiple of fpb)
+    if ((rc = s->acoef.ensure(sizeof(float) * 3 * s->kpad * (size_t)geo))) return rc;
+    if ((rc = s->rmats.ensure(sizeof(float) * 45 * (size_t)geo))) return rc;
+    if ((rc = s->vp.ensure(sizeof(float) * (size_t)s->npad * geo))) return rc;
+    if ((rc = s->verts.ensure(sizeof(float) * 3 * (size_t)V * geo))) return rc;
+    if (p_dyn && (rc = s->jdyn.ensure(sizeof(float) * 15 * (size_t)geo))) return rc;
+    // segment tables for one full batch: seg -> local frame, seg -> camera
+    {
+        const int Sb = fpb * n_views;
+        std::vector<int32_t> sf(Sb);
+        for (int i = 0; i < Sb; i++) sf[i] = i / n_views;
+        if ((rc = s->seg_frame.ensure(sizeof(int32_t) * Sb))) return rc;
+        OMFS_CUDA(cudaMemcpyAsync(s->seg_frame.p, sf.data(), sizeof(int32_t) * Sb, cudaMemcpyHostToDevice, st));
+        OMFS_CUDA(cudaStreamSynchronize(st));  // sf is a stack-lifetime vector
+        // cameras tiled per frame of the batch
+        if ((rc = s->cams.ensure(sizeof(float) * kCam * Sb))) return rc;
+        for (int f = 0; f < fpb; f++)
+            OMFS_CUDA(cudaMemcpyAsync(s->cams.as<float>() + (size_t)f * n_views * kCam, p_cams,
+                                      sizeof(float) * kCam * n_views, cudaMemcpyDeviceToDevice, st));
+    }
+    uint32_t* d_num_pairs = s->counters.as<uint32_t>();
+    int* d_flag = s->counters.as<int>() + 1;
+    OMFS_CUDA(cudaMemsetAsync(s->counters.p, 0, 256, st));
+    uint64_t* d_pair_total = reinterpret_cast<uint64_t*>(s->counters.as<unsigned char>() + 16);
+    (void)d_pair_total;
+
+    int batch_index = 0;
+    for (int g0 = 0; g0 < T; g0 += geo) {
+        const int gT = std::min(geo, T - g0);
+        // ---- FLAME: operand prep, blendshape GEMM (tensor cores), skinning
+        if ((rc = omfs_flame_pose_prep(gT, s->n_expr, s->kpad, p_expr + (size_t)g0 * s->n_expr, p_rot + (size_t)g0 * 3,
+                                       p_neck + (size_t)g0 * 3, p_jaw + (size_t)g0 * 3, p_eyes + (size_t)g0 * 6,
+                                       s->acoef.as<float>(), s->rmats.as<float>(), st)))
+            return rc;
+        const int impl = (s->cfg.gemm_impl == 0) ? 0 : 1;
+        if ((rc = omfs_flame_blend_gemm(gT, s->kpad, s->npad, s->acoef.as<float>(), s->bt.as<float>(),
+                                        s->base.as<float>(), s->vp.as<float>(), impl, st)))
+            return rc;
+        const float* dyn_g = p_dyn ? p_dyn + (size_t)g0 * V * 3 : nullptr;
+        if (dyn_g && (rc = omfs_flame_joint_dyn(gT, V, s->jreg.as<float>(), dyn_g, s->jdyn.as<float>(), st)))
+            return rc;
+        if ((rc = omfs_flame_lbs(gT, V, s->npad, s->vp.as<float>(), s->rmats.as<float>(), s->weights.as<float>(),
+                                 p_transl + (size_t)g0 * 3, dyn_g, dyn_g ? s->jdyn.as<float>() : nullptr,
+                                 s->verts.as<float>(), st)))
+            return rc;
+        // ---- render batches inside the chunk
+        for (int b0 = 0; b0 < gT; b0 += fpb) {
+            const int bT = std::min(fpb, gT - b0);
+            const int S = bT * n_views;
+            const int ib = batch_index & 1;
+            if ((rc = omfs_face_frames(bT, V, F, s->verts.as<float>() + (size_t)b0 * V * 3, s->faces.as<int32_t>(),
+                                       s->ff.as<float>(), st)))
+                return rc;
+            if ((rc = omfs_bind_preprocess(S, N, F, W, H, s->ff.as<float>(), s->seg_frame.as<int32_t>(),
+                                           s->cams.as<float>(), s->xyzb.as<float>(), s->scale_lo.as<float>(),
+                                           s->rot.as<float>(), s->sh.as<float>(), s->P0.as<float>(),
+                                           s->P1.as<float>(), s->P2.as<float>(), s->tt.as<uint32_t>(), st)))
+                return rc;
+            int sorted = 0;
+            if ((rc = omfs_binning(S, N, W, H, s->capacity, s->P0.as<float>(), s->tt.as<uint32_t>(),
+                                   s->offsets.as<uint32_t>(), s->keys0.as<uint64_t>(), s->keys1.as<uint64_t>(),
+                                   s->vals0.as<uint32_t>(), s->vals1.as<uint32_t>(), s->ranges.as<uint32_t>(),
+                                   d_num_pairs, d_flag, s->ws.p, s->ws_bytes, &sorted, st)))
+                return rc;
+            s->last_sorted_buffer = sorted;
+            // the image buffer may still be draining to the host from two batches ago
+            if (batch_index >= 2 && out_on_host) OMFS_CUDA(cudaStreamWaitEvent(st, s->ev_copied[ib], 0));
+            float* img = s->image[ib].as<float>();
+            uint8_t* img8 = s->image_u8[ib].as<uint8_t>();
+            const size_t seg0 = (size_t)(g0 + b0) * n_views;
+            const bool direct = !out_on_host;  // device output: composite straight into the caller's buffers
+            float* dst_f = direct ? (out_f32 ? out_f32 + seg0 * 3 * hw : nullptr) : (out_f32 ? img : nullptr);
+            uint8_t* dst_8 = direct ? (out_u8 ? out_u8 + seg0 * 3 * hw : nullptr) : (out_u8 ? img8 : nullptr);
+            if (!dst_f && !dst_8) dst_f = img;  // nothing requested: still render (debug taps)
+            if ((rc = omfs_composite(S, N, W, H, s->P0.as<float>(), s->P1.as<float>(), s->P2.as<float>(),
+                                     sorted ? s->vals1.as<uint32_t>() : s->vals0.as<uint32_t>(),
+                                     s->ranges.as<uint32_t>(), s->cfg.bg, dst_f, dst_8, st)))
+                return rc;
+            s->last_image_buffer = ib;
+            s->last_batch_segments = S;
+            if (out_on_host) {
+                OMFS_CUDA(cudaEventRecord(s->ev_done[ib], st));
+                OMFS_CUDA(cudaStreamWaitEvent(s->copy_stream, s->ev_done[ib], 0));
+                if (out_u8)
+                    OMFS_CUDA(cudaMemcpyAsync(out_u8 + seg0 * 3 * hw, img8, (size_t)S * 3 * hw,
+                                              cudaMemcpyDeviceToHost, s->copy_stream));
+                if (out_f32)
+                    OMFS_CUDA(cudaMemcpyAsync(out_f32 + seg0 * 3 * hw, img, sizeof(float) * S * 3 * hw,
+                                              cudaMemcpyDeviceToHost, s->copy_stream));
+                OMFS_CUDA(cudaEventRecord(s->ev_copied[ib], s->copy_stream));
+            }
+            batch_index++;
+        }
+    }
+    s->stats[1] = g_launches - launches0;
+    s->stats[2] = (uint64_t)batch_index;
+    return OMFS_OK;
+}
+
+static int finish_stats(omfs_session* s) {
+    uint32_t h[2] = {0, 0};
+    OMFS_CUDA(cudaMemcpy(h, s->counters.p, sizeof(h), cudaMemcpyDeviceToHost));
+    s->stats[0] = h[0];  // pairs of the last batch
+    s->stats[3] = h[1];
+    if (h[1]) {
+        set_error("tile-pair list overflowed the session capacity (%zu); raise pair_capacity", s->capacity);
+        return OMFS_ERR_CAPACITY;
+    }
+    return OMFS_OK;
+}
+
+extern "C" int omfs_session_render_host(omfs_session* s, const omfs_frames_desc* fr, uint8_t* h_out_u8,
+                                        float* h_out_f32) {
+    OMFS_REQUIRE(s && fr, "null argument");
+    OMFS_REQUIRE(s->subject_set, "omfs_session_set_subject must be called first");
+    OMFS_REQUIRE(fr->n_frames >= 0 && fr->n_views > 0 && fr->n_views <= s->cfg.max_batch, "bad frame/view counts");
+    OMFS_REQUIRE(fr->expr && fr->rotation && fr->neck_pose && fr->jaw_pose && fr->eyes_pose && fr->translation &&
+                     fr->cams,
+                 "null frame array");
+    OMFS_CUDA(cudaSetDevice(s->cfg.device));
+    const int T = fr->n_frames;
+    if (T == 0) return OMFS_OK;
+    cudaStream_t st = s->stream;
+    int rc;
+    if ((rc = upload(s->expr, fr->expr, sizeof(float) * (size_t)T * s->n_expr, st))) return rc;
+    if ((rc = upload(s->rotation, fr->rotation, sizeof(float) * 3 * T, st))) return rc;
+    if ((rc = upload(s->neck, fr->neck_pose, sizeof(float) * 3 * T, st))) return rc;
+    if ((rc = upload(s->jaw, fr->jaw_pose, sizeof(float) * 3 * T, st))) return rc;
+    if ((rc = upload(s->eyes, fr->eyes_pose, sizeof(float) * 6 * T, st))) return rc;
+    if ((rc = upload(s->transl, fr->translation, sizeof(float) * 3 * T, st))) return rc;
+    if (fr->dynamic_offset &&
+        (rc = upload(s->dyn, fr->dynamic_offset, sizeof(float) * 3 * (size_t)s->V * T, st)))
+        return rc;
+    DevBuf cams_in;
+    if ((rc = upload(cams_in, fr->cams, sizeof(float) * kCam * fr->n_views, st))) return rc;
+    rc = render_core(s, T, fr->n_views, s->expr.as<float>(), s->rotation.as<float>(), s->neck.as<float>(),
+                     s->jaw.as<float>(), s->eyes.as<float>(), s->transl.as<float>(),
+                     fr->dynamic_offset ? s->dyn.as<float>() : nullptr, cams_in.as<float>(), h_out_u8, h_out_f32,
+                     true, st);
+    cudaError_t e1 = cudaStreamSynchronize(st);
+    cudaError_t e2 = cudaStreamSynchronize(s->copy_stream);
+    cams_in.release();
+    if (rc) return rc;
+    if (e1 != cudaSuccess) return cuda_fail(e1, "stream sync", __FILE__, __LINE__);
+    if (e2 != cudaSuccess) return cuda_fail(e2, "copy stream sync", __FILE__, __LINE__);
+    return finish_stats(s);
+}
+
+extern "C" int omfs_session_render_device(omfs_session* s, const omfs_frames_desc* fr, uint8_t* d_out_u8,
+                                          float* d_out_f32, void* stream) {
+    OMFS_REQUIRE(s && fr, "null argument");
+    OMFS_REQUIRE(s->subject_set, "omfs_session_set_subject must be called first");
+    OMFS_REQUIRE(fr->n_frames >= 0 && fr->n_views > 0 && fr->n_views <= s->cfg.max_batch, "bad frame/view counts");
+    OMFS_REQUIRE(fr->expr && fr->rotation && fr->neck_pose && fr->jaw_pose && fr->eyes_pose && fr->translation &&
+                     fr->cams,
+                 "null frame array");
+    OMFS_CUDA(cudaSetDevice(s->cfg.device));
+    if (fr->n_frames == 0) return OMFS_OK;
+    cudaStream_t st = stream ? (cudaStream_t)stream : s->stream;
+    return render_core(s, fr->n_frames, fr->n_views, fr->expr, fr->rotation, fr->neck_pose, fr->jaw_pose,
+                       fr->eyes_pose, fr->translation, fr->dynamic_offset, fr->cams, d_out_u8, d_out_f32, false, st);
+}
+
+// Waits for the session's streams and reports overflow; call after render_device before reading results.
+extern "C" int omfs_session_sync(omfs_session* s) {
+    OMFS_REQUIRE(s, "null argument");
+    OMFS_CUDA(cudaSetDevice(s->cfg.device));
+    OMFS_CUDA(cudaStreamSynchronize(s->stream));
+    OMFS_CUDA(cudaStreamSynchronize(s->copy_stream));
+    return finish_stats(s);
+}
+
+extern "C" void* omfs_session_stream(omfs_session* s) { return s ? (void*)s->stream : nullptr; }
+
+extern "C" int omfs_session_stats(omfs_session* s, uint64_t* out4) {
+    OMFS_REQUIRE(s && out4, "null argument");
+    for (int i = 0; i < 4; i++) out4[i] = s->stats[i];
+    return OMFS_OK;
+}
+
+extern "C" int omfs_session_tap(omfs_session* s, const char* name, void** d_ptr, size_t* bytes) {
+    OMFS_REQUIRE(s && name && d_ptr && bytes, "null argument");
+    struct Tap {
+        const char* n;
+        DevBuf* b;
+    };
+    DevBuf* sorted_k = s->last_sorted_buffer ? &s->keys1 : &s->keys0;
+    DevBuf* sorted_v = s->last_sorted_buffer ? &s->vals1 : &s->vals0;
+    Tap taps[] = {{"verts", &s->verts}, {"ff", &s->ff}, {"P0", &s->P0}, {"P1", &s->P1}, {"P2", &s->P2},
+                  {"tiles_touched", &s->tt}, {"offsets", &s->offsets}, {"keys", sorted_k}, {"vals", sorted_v},
+                  {"ranges", &s->ranges}, {"image", &s->image[s->last_image_buffer]},
+                  {"image_u8", &s->image_u8[s->last_image_buffer]}, {"vp", &s->vp}, {"acoef", &s->acoef},
+                  {"base", &s->base}, {"counters", &s->counters}, {"rmats", &s->rmats}};
+    for (const Tap& t : taps)
+        if (strcmp(t.n, name) == 0) {
+            *d_ptr = t.b->p;
+            *bytes = t.b->bytes;
+            return OMFS_OK;
+        }
+    set_error("unknown tap '%s'", name);
+    return OMFS_ERR_INVALID;
+}
+
+extern "C" int omfs_session_dims(omfs_session* s, int32_t* out8) {
+    OMFS_REQUIRE(s && out8, "null argument");
+    out8[0] = s->V; out8[1] = s->F; out8[2] = s->n_expr; out8[3] = s->N;
+    out8[4] = s->kpad; out8[5] = s->npad; out8[6] = s->tiles; out8[7] = s->last_batch_segments;
+    return OMFS_OK;
+}

@@ -1,0 +1,50 @@
+// common.cuh — shared by every translation unit of libomfs_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/omfs_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libomfs_b200 is written for sm_100a (B200) only"
+#endif
+
+namespace omfs {
+
+constexpr int kTile = OMFS_TILE;
+constexpr int kFF = OMFS_FF_STRIDE;
+constexpr int kCam = OMFS_CAM_FLOATS;
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs; grids are sized in multiples of this
+
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
+
+#define OMFS_CUDA(call)                                                         \
+    do {                                                                        \
+        cudaError_t _e = (call);                                                \
+        if (_e != cudaSuccess) return omfs::cuda_fail(_e, #call, __FILE__, __LINE__); \
+    } while (0)
+
+#define OMFS_LAUNCH_CHECK() OMFS_CUDA(cudaGetLastError())
+
+#define OMFS_REQUIRE(cond, msg)                       \
+    do {                                              \
+        if (!(cond)) {                                \
+            omfs::set_error("%s: %s", __func__, msg); \
+            return OMFS_ERR_INVALID;                  \
+        }                                             \
+    } while (0)
+
+inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// launch counter (gpu_launches in bench.py is read from here)
+extern unsigned long long g_launches;
+inline void count_launch(int n = 1) { g_launches += (unsigned long long)n; }
+
+// 128-bit streaming loads / stores.  The frame-invariant avatar streams and per-frame records are
+// read through the read-only path; outputs that the next kernel re-reads stay default-cached so
+// they can live in the 126 MB L2 between the kernels of one batch.
+__device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
+
+}  // namespace omfs

@@ -1,0 +1,144 @@
+// exact_geom.cu — U4 (face frames) and the fused U5+U6 kernel (parent-triangle transform of each
+// Gaussian + cull / project / EWA covariance / SH colour).  Compiled with --fmad=false: every
+// float result here is bit-reproducible against the oracle.
+//
+// Both kernels are pure HBM streams (80 B/face, 288 B/Gaussian).  Layout choices:
+//   * all per-Gaussian inputs and outputs are float4 SoA, so one warp instruction moves 512
+//     contiguous bytes;
+//   * the SH block (192 of the 240 input bytes) is 12 float4 planes and is only read for
+//     Gaussians that survive culling;
+//   * the per-frame face records (5 float4 per face, ~0.8 MB per frame) are gathered through the
+//     read-only path and stay L2-resident across the segments of a batch.
+#include "common.cuh"
+#include "exact_math.cuh"
+
+namespace omfs {
+
+// ---------------------------------------------------------------------------------------- U4
+__global__ void __launch_bounds__(256) face_frames_kernel(int T, int V, int F, const float* __restrict__ verts,
+                                                          const int32_t* __restrict__ faces,
+                                                          float4* __restrict__ ff) {
+    const long long total = (long long)T * F;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int t = (int)(i / F), f = (int)(i % F);
+        const float* vb = verts + (size_t)t * V * 3;
+        const int i0 = __ldg(faces + f * 3 + 0), i1 = __ldg(faces + f * 3 + 1), i2 = __ldg(faces + f * 3 + 2);
+        const float p0[3] = {vb[i0 * 3], vb[i0 * 3 + 1], vb[i0 * 3 + 2]};
+        const float p1[3] = {vb[i1 * 3], vb[i1 * 3 + 1], vb[i1 * 3 + 2]};
+        const float p2[3] = {vb[i2 * 3], vb[i2 * 3 + 1], vb[i2 * 3 + 2]};
+        float o[20];
+        ex_face_frame(p0, p1, p2, o);
+        float4* dst = ff + (size_t)i * 5;
+#pragma unroll
+        for (int k = 0; k < 5; k++) dst[k] = make_float4(o[4 * k], o[4 * k + 1], o[4 * k + 2], o[4 * k + 3]);
+    }
+}
+
+// ------------------------------------------------------------------------------------- U5+U6
+// grid = (ceil(N/256), S).  One thread per (segment, Gaussian).
+__global__ void __launch_bounds__(256) bind_preprocess_kernel(
+    int N, int F, int width, int height, const float4* __restrict__ ff, const int32_t* __restrict__ seg_frame,
+    const float* __restrict__ cams, const float4* __restrict__ xyzb, const float4* __restrict__ scale_lo,
+    const float4* __restrict__ rot, const float4* __restrict__ sh, float4* __restrict__ P0,
+    float4* __restrict__ P1, float4* __restrict__ P2, uint32_t* __restrict__ tiles_touched) {
+    __shared__ float s_cam[kCam];
+    const int seg = blockIdx.y;
+    if (threadIdx.x < kCam) s_cam[threadIdx.x] = __ldg(cams + (size_t)seg * kCam + threadIdx.x);
+    __syncthreads();
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const int frame = __ldg(seg_frame + seg);
+    const int gx = (width + kTile - 1) / kTile, gy = (height + kTile - 1) / kTile;
+
+    const float4 a = ldg4(xyzb + n);
+    const float4 s = ldg4(scale_lo + n);
+    const float4 q = ldg4(rot + n);
+    const int b = __float_as_int(a.w);
+    const float4* fr = ff + ((size_t)frame * F + b) * 5;
+    float frec[20];
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        const float4 v = ldg4(fr + k);
+        frec[4 * k] = v.x;
+        frec[4 * k + 1] = v.y;
+        frec[4 * k + 2] = v.z;
+        frec[4 * k + 3] = v.w;
+    }
+    BindPre o;
+    const bool ok = ex_bind_project(frec, a.x, a.y, a.z, s.x, s.y, s.z, q.x, q.y, q.z, q.w, s_cam, width, height,
+                                    gx, gy, o);
+    const size_t oi = (size_t)seg * N + n;
+    if (!ok) {
+        P0[oi] = make_float4(0.f, 0.f, 0.f, __int_as_float(0));
+        P1[oi] = make_float4(0.f, 0.f, 0.f, 0.f);
+        P2[oi] = make_float4(0.f, 0.f, 0.f, 0.f);
+        tiles_touched[oi] = 0;
+        return;
+    }
+    float dx, dy, dz;
+    ex_view_dir(o.mx, o.my, o.mz, s_cam, dx, dy, dz);
+    float bs[16];
+    ex_sh_basis(dx, dy, dz, bs);
+    // 12 float4 planes; flat index k*3+c lives in plane (flat>>2), lane (flat&3)
+    float coef[48];
+#pragma unroll
+    for (int j = 0; j < 12; j++) {
+        const float4 v = ldg4(sh + (size_t)j * N + n);
+        coef[4 * j] = v.x;
+        coef[4 * j + 1] = v.y;
+        coef[4 * j + 2] = v.z;
+        coef[4 * j + 3] = v.w;
+    }
+    float rgb[3];
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        float acc = bs[0] * coef[c];
+#pragma unroll
+        for (int k = 1; k < 16; k++) acc = acc + bs[k] * coef[k * 3 + c];
+        acc = acc + 0.5f;
+        rgb[c] = fmaxf(acc, 0.0f);
+    }
+    P0[oi] = make_float4(o.px, o.py, o.depth, __int_as_float(o.radius));
+    P1[oi] = make_float4(o.ca, o.cb, o.cc, s.w);
+    P2[oi] = make_float4(rgb[0], rgb[1], rgb[2], 0.f);
+    tiles_touched[oi] = o.tiles;
+}
+
+}  // namespace omfs
+
+using namespace omfs;
+
+extern "C" int omfs_face_frames(int T, int V, int F, const float* d_verts, const int32_t* d_faces, float* d_ff,
+                                void* stream) {
+    OMFS_REQUIRE(T >= 0 && V > 0 && F > 0, "bad sizes");
+    OMFS_REQUIRE(d_verts && d_faces && d_ff, "null pointer");
+    if (T == 0) return OMFS_OK;
+    const long long total = (long long)T * F;
+    int blocks = ceil_div(total, 256);
+    const int cap = kNumSMs * 8 * 4;
+    if (blocks > cap) blocks = cap;
+    face_frames_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(T, V, F, d_verts, d_faces, (float4*)d_ff);
+    count_launch();
+    OMFS_LAUNCH_CHECK();
+    return OMFS_OK;
+}
+
+extern "C" int omfs_bind_preprocess(int S, int N, int F, int width, int height, const float* d_ff,
+                                    const int32_t* d_seg_frame, const float* d_cams, const float* d_xyzb,
+                                    const float* d_scale_lo, const float* d_rot, const float* d_sh, float* d_P0,
+                                    float* d_P1, float* d_P2, uint32_t* d_tiles_touched, void* stream) {
+    OMFS_REQUIRE(S >= 0 && N > 0 && F > 0 && width > 0 && height > 0, "bad sizes");
+    OMFS_REQUIRE(S <= 65535, "at most 65535 segments per call");
+    OMFS_REQUIRE(d_ff && d_seg_frame && d_cams && d_xyzb && d_scale_lo && d_rot && d_sh, "null input");
+    OMFS_REQUIRE(d_P0 && d_P1 && d_P2 && d_tiles_touched, "null output");
+    if (S == 0) return OMFS_OK;
+    dim3 grid(ceil_div(N, 256), S);
+    bind_preprocess_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+        N, F, width, height, (const float4*)d_ff, d_seg_frame, d_cams, (const float4*)d_xyzb,
+        (const float4*)d_scale_lo, (const float4*)d_rot, (const float4*)d_sh, (float4*)d_P0, (float4*)d_P1,
+        (float4*)d_P2, d_tiles_touched);
+    count_launch();
+    OMFS_LAUNCH_CHECK();
+    return OMFS_OK;
+}

@@ -1,0 +1,332 @@
+"""ctypes binding of libomfs_b200.so (include/omfs_b200.h) and the Python-side render session.
+
+This is the thin layer between the reference-facing Python entry points
+(render_surgery.py in this package) and the C-ABI.  There is NO fallback: if the shared library is
+missing or the device is not an sm_100 part, every call raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import re
+from ctypes import POINTER, c_char_p, c_double, c_float, c_int, c_int32, c_size_t, c_uint8, c_uint32, c_uint64, c_void_p
+
+import numpy as np
+
+from . import cameras as cam_mod
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libomfs_b200.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "omfs_b200.h")
+
+_lib = None
+
+
+class OmfsError(RuntimeError):
+    pass
+
+
+def declared_symbols() -> list[str]:
+    """Every function name include/omfs_b200.h declares."""
+    text = open(HEADER_PATH).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(omfs_[a-z0-9_]+)\s*\(", text)))
+
+
+class ModelDesc(ctypes.Structure):
+    _fields_ = [("n_verts", c_int32), ("n_faces", c_int32), ("n_expr", c_int32), ("n_gauss", c_int32),
+                ("v_template", c_void_p), ("shapedirs", c_void_p), ("posedirs", c_void_p),
+                ("j_regressor", c_void_p), ("lbs_weights", c_void_p), ("faces", c_void_p),
+                ("xyzb", c_void_p), ("scale_lo", c_void_p), ("rot", c_void_p), ("sh", c_void_p)]
+
+
+class SessionConfig(ctypes.Structure):
+    _fields_ = [("width", c_int32), ("height", c_int32), ("max_batch", c_int32), ("device", c_int32),
+                ("gemm_impl", c_int32), ("use_graph", c_int32), ("pair_capacity", c_uint64), ("bg", c_float * 3)]
+
+
+class FramesDesc(ctypes.Structure):
+    _fields_ = [("n_frames", c_int32), ("n_views", c_int32), ("expr", c_void_p), ("rotation", c_void_p),
+                ("neck_pose", c_void_p), ("jaw_pose", c_void_p), ("eyes_pose", c_void_p),
+                ("translation", c_void_p), ("dynamic_offset", c_void_p), ("cams", c_void_p)]
+
+
+def load_library():
+    """dlopen the C-ABI library and check that it exports everything the header declares."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise OmfsError(f"{LIB_PATH} is missing: run `python __graft_entry__.py` (build()) first; "
+                        "there is no CPU fallback")
+    L = ctypes.CDLL(LIB_PATH)
+    missing = [s for s in declared_symbols() if not hasattr(L, s)]
+    if missing:
+        raise OmfsError(f"libomfs_b200.so does not export: {missing}")
+    L.omfs_last_error.restype = c_char_p
+    L.omfs_launch_count.restype = ctypes.c_ulonglong
+    L.omfs_binning_workspace_bytes.restype = c_size_t
+    L.omfs_binning_workspace_bytes.argtypes = [c_int, c_int, c_int, c_int, c_size_t]
+    L.omfs_session_stream.restype = c_void_p
+    L.omfs_session_stream.argtypes = [c_void_p]
+    L.omfs_session_create.argtypes = [POINTER(ModelDesc), POINTER(SessionConfig), POINTER(c_void_p)]
+    L.omfs_session_destroy.argtypes = [c_void_p]
+    L.omfs_session_destroy.restype = None
+    L.omfs_session_set_subject.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p]
+    L.omfs_session_render_host.argtypes = [c_void_p, POINTER(FramesDesc), c_void_p, c_void_p]
+    L.omfs_session_render_device.argtypes = [c_void_p, POINTER(FramesDesc), c_void_p, c_void_p, c_void_p]
+    L.omfs_session_sync.argtypes = [c_void_p]
+    L.omfs_session_stats.argtypes = [c_void_p, POINTER(c_uint64)]
+    L.omfs_session_tap.argtypes = [c_void_p, c_char_p, POINTER(c_void_p), POINTER(c_size_t)]
+    L.omfs_session_dims.argtypes = [c_void_p, POINTER(c_int32)]
+    L.omfs_host_alloc.argtypes = [POINTER(c_void_p), c_size_t]
+    L.omfs_host_free.argtypes = [c_void_p]
+    L.omfs_device_alloc.argtypes = [POINTER(c_void_p), c_size_t]
+    L.omfs_device_free.argtypes = [c_void_p]
+    L.omfs_memcpy_h2d.argtypes = [c_void_p, c_void_p, c_size_t]
+    L.omfs_memcpy_d2h.argtypes = [c_void_p, c_void_p, c_size_t]
+    vp = c_void_p
+    L.omfs_flame_pose_prep.argtypes = [c_int, c_int, c_int, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.omfs_flame_blend_gemm.argtypes = [c_int, c_int, c_int, vp, vp, vp, vp, c_int, vp]
+    L.omfs_flame_lbs.argtypes = [c_int, c_int, c_int, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.omfs_flame_joint_dyn.argtypes = [c_int, c_int, vp, vp, vp, vp]
+    L.omfs_flame_fold_subject.argtypes = [c_int, c_int, c_int, vp, vp, vp, vp, vp, vp, vp, vp]
+    L.omfs_face_frames.argtypes = [c_int, c_int, c_int, vp, vp, vp, vp]
+    L.omfs_bind_preprocess.argtypes = [c_int, c_int, c_int, c_int, c_int] + [vp] * 12
+    L.omfs_binning.argtypes = [c_int, c_int, c_int, c_int, c_size_t] + [vp] * 11 + [c_size_t, POINTER(c_int), vp]
+    L.omfs_scan_emit.argtypes = [c_int, c_int, c_int, c_int, c_size_t] + [vp] * 8 + [c_size_t, vp]
+    L.omfs_binning_sort_bits.argtypes = [c_int, c_int, c_int]
+    L.omfs_composite.argtypes = [c_int, c_int, c_int, c_int, vp, vp, vp, vp, vp, POINTER(c_float), vp, vp, vp]
+    L.omfs_to_uint8.argtypes = [c_int, c_int, c_int, vp, vp, vp]
+    L.omfs_displace_points.argtypes = [c_int, vp, POINTER(c_double), POINTER(c_double), vp, c_int, vp, vp, vp, vp]
+    L.omfs_device_check.argtypes = [c_int]
+    _lib = L
+    return L
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = load_library().omfs_last_error().decode(errors="replace")
+        raise OmfsError(f"omfs error {rc}: {msg}")
+
+
+def launch_count() -> int:
+    return int(load_library().omfs_launch_count())
+
+
+def _f32(a) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _ptr(a: np.ndarray | None):
+    return None if a is None else a.ctypes.data_as(c_void_p)
+
+
+class PinnedArray:
+    """A numpy view over page-locked host memory from the library's own allocator."""
+
+    def __init__(self, shape, dtype):
+        self.shape = tuple(int(x) for x in shape)
+        self.dtype = np.dtype(dtype)
+        nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
+        self._p = c_void_p()
+        check(load_library().omfs_host_alloc(ctypes.byref(self._p), max(nbytes, 1)))
+        buf = (ctypes.c_uint8 * max(nbytes, 1)).from_address(self._p.value)
+        self.array = np.frombuffer(buf, dtype=self.dtype, count=int(np.prod(self.shape))).reshape(self.shape)
+
+    def free(self):
+        if self._p is not None and self._p.value:
+            load_library().omfs_host_free(self._p)
+            self._p = None
+            self.array = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Session:
+    """Model + avatar resident on one GPU; renders batches of frames through the C-ABI.
+
+    model : synthetic.FlameModel-like (v_template, shapedirs[400,3V], posedirs, j_regressor, lbs_weights, faces)
+    baked : avatar.bake_avatar(...) dict
+    """
+
+    def __init__(self, model, baked: dict, width: int, height: int, max_batch: int = 32, device: int = 0,
+                 gemm_impl: int = 0, pair_capacity: int = 0, bg=(1.0, 1.0, 1.0), n_expr: int | None = None):
+        L = load_library()
+        self._L = L
+        self.width, self.height = int(width), int(height)
+        self.n_verts = int(model.v_template.shape[0])
+        self.n_faces = int(model.faces.shape[0])
+        self.n_gauss = int(baked["xyzb"].shape[0])
+        self.n_expr = int(n_expr if n_expr is not None else model.shapedirs.shape[0] - 300)
+        self.max_batch = int(max_batch)
+        self.device = int(device)
+        keep = dict(
+            v_template=_f32(model.v_template), shapedirs=_f32(model.shapedirs), posedirs=_f32(model.posedirs),
+            j_regressor=_f32(model.j_regressor), lbs_weights=_f32(model.lbs_weights),
+            faces=np.ascontiguousarray(model.faces, dtype=np.int32),
+            xyzb=_f32(baked["xyzb"]), scale_lo=_f32(baked["scale_lo"]), rot=_f32(baked["rot"]), sh=_f32(baked["sh"]))
+        assert keep["shapedirs"].shape == (300 + self.n_expr, 3 * self.n_verts), keep["shapedirs"].shape
+        assert keep["posedirs"].shape == (36, 3 * self.n_verts)
+        assert keep["sh"].shape == (12, self.n_gauss, 4)
+        md = ModelDesc(self.n_verts, self.n_faces, self.n_expr, self.n_gauss,
+                       *[_ptr(keep[k]) for k in ("v_template", "shapedirs", "posedirs", "j_regressor",
+                                                 "lbs_weights", "faces", "xyzb", "scale_lo", "rot", "sh")])
+        cfg = SessionConfig(self.width, self.height, self.max_batch, self.device, int(gemm_impl), 0,
+                            int(pair_capacity), (c_float * 3)(*[float(x) for x in bg]))
+        self._h = c_void_p()
+        check(L.omfs_session_create(ctypes.byref(md), ctypes.byref(cfg), ctypes.byref(self._h)))
+        del keep  # the library copied everything to the device
+
+    # -- lifetime
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self._L.omfs_session_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- subject
+    def set_subject(self, shape300, static_offset=None, plan_offset=None):
+        sh = _f32(shape300).reshape(-1)
+        assert sh.size == 300
+        so = None if static_offset is None else _f32(static_offset).reshape(-1)
+        po = None if plan_offset is None else _f32(plan_offset).reshape(-1)
+        for a in (so, po):
+            assert a is None or a.size == 3 * self.n_verts
+        check(self._L.omfs_session_set_subject(self._h, _ptr(sh), _ptr(so), _ptr(po)))
+
+    # -- rendering
+    def _frames_desc(self, params, cams, keep: list):
+        T = int(params.expr.shape[0])
+        expr = _f32(params.expr)
+        assert expr.shape[1] == self.n_expr, (expr.shape, self.n_expr)
+        cam_arr = _f32(np.stack([c.pack() if isinstance(c, cam_mod.Camera) else np.asarray(c) for c in cams]))
+        dyn = params.dynamic_offset
+        if dyn is not None and not np.any(dyn):
+            dyn = None
+        arrs = [expr, _f32(params.rotation), _f32(params.neck_pose), _f32(params.jaw_pose), _f32(params.eyes_pose),
+                _f32(params.translation), None if dyn is None else _f32(dyn), cam_arr]
+        keep.extend(arrs)
+        return FramesDesc(T, len(cams), *[_ptr(a) for a in arrs]), T * len(cams)
+
+    def render_host(self, params, cams, want_u8: bool = True, want_f32: bool = False, out_u8=None, out_f32=None):
+        """Host parameters in, host frames out (uint8 [S,H,W,3] and/or float32 [S,3,H,W])."""
+        keep: list = []
+        fd, S = self._frames_desc(params, cams, keep)
+        if want_u8 and out_u8 is None:
+            out_u8 = np.empty((S, self.height, self.width, 3), np.uint8)
+        if want_f32 and out_f32 is None:
+            out_f32 = np.empty((S, 3, self.height, self.width), np.float32)
+        check(self._L.omfs_session_render_host(self._h, ctypes.byref(fd), _ptr(out_u8) if want_u8 else None,
+                                               _ptr(out_f32) if want_f32 else None))
+        return (out_u8 if want_u8 else None), (out_f32 if want_f32 else None)
+
+    def render_device(self, d_params: dict, n_frames: int, n_views: int, d_out_u8=0, d_out_f32=0, stream=0):
+        """Device pointers in (ints), device pointers out.  Asynchronous; call sync()."""
+        fd = FramesDesc(int(n_frames), int(n_views), d_params["expr"], d_params["rotation"],
+                        d_params["neck_pose"], d_params["jaw_pose"], d_params["eyes_pose"],
+                        d_params["translation"], d_params.get("dynamic_offset") or None, d_params["cams"])
+        check(self._L.omfs_session_render_device(self._h, ctypes.byref(fd), d_out_u8 or None, d_out_f32 or None,
+                                                 stream or None))
+
+    def sync(self):
+        check(self._L.omfs_session_sync(self._h))
+
+    @property
+    def stream(self) -> int:
+        return int(self._L.omfs_session_stream(self._h) or 0)
+
+    def stats(self) -> dict:
+        out = (c_uint64 * 4)()
+        check(self._L.omfs_session_stats(self._h, out))
+        return {"pairs_last_batch": int(out[0]), "launches": int(out[1]), "batches": int(out[2]),
+                "overflow": int(out[3])}
+
+    def dims(self) -> dict:
+        out = (c_int32 * 8)()
+        check(self._L.omfs_session_dims(self._h, out))
+        keys = ("V", "F", "n_expr", "N", "kpad", "npad", "tiles", "last_batch_segments")
+        return dict(zip(keys, [int(x) for x in out]))
+
+    def tap(self, name: str):
+        p, n = c_void_p(), c_size_t()
+        check(self._L.omfs_session_tap(self._h, name.encode(), ctypes.byref(p), ctypes.byref(n)))
+        return int(p.value or 0), int(n.value)
+
+    def tap_array(self, name: str, shape, dtype) -> np.ndarray:
+        """Copy a debug tap to the host (tests only)."""
+        ptr, nbytes = self.tap(name)
+        out = np.empty(shape, dtype=dtype)
+        assert out.nbytes <= nbytes, (name, out.nbytes, nbytes)
+        memcpy_d2h(out, ptr)
+        return out
+
+
+# ---------------------------------------------------------------------------------------------
+# device memory helpers through the library's own CUDA runtime (so numpy-only callers work)
+def memcpy_d2h(dst: np.ndarray, src_ptr: int):
+    check(load_library().omfs_memcpy_d2h(dst.ctypes.data_as(c_void_p), c_void_p(src_ptr), dst.nbytes))
+
+
+def memcpy_h2d(dst_ptr: int, src: np.ndarray):
+    src = np.ascontiguousarray(src)
+    check(load_library().omfs_memcpy_h2d(c_void_p(dst_ptr), src.ctypes.data_as(c_void_p), src.nbytes))
+
+
+class DeviceArray:
+    """A device allocation with a shape/dtype, owned through the C-ABI helpers."""
+
+    def __init__(self, shape, dtype, fill_from: np.ndarray | None = None):
+        self.shape = tuple(int(x) for x in np.atleast_1d(shape))
+        self.dtype = np.dtype(dtype)
+        self.nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
+        self._p = c_void_p()
+        check(load_library().omfs_device_alloc(ctypes.byref(self._p), max(self.nbytes, 16)))
+        if fill_from is not None:
+            a = np.ascontiguousarray(fill_from, dtype=self.dtype)
+            assert a.nbytes == self.nbytes, (a.shape, self.shape)
+            memcpy_h2d(self.ptr, a)
+
+    @classmethod
+    def from_numpy(cls, a: np.ndarray) -> "DeviceArray":
+        a = np.ascontiguousarray(a)
+        return cls(a.shape, a.dtype, fill_from=a)
+
+    @property
+    def ptr(self) -> int:
+        return int(self._p.value or 0)
+
+    def numpy(self) -> np.ndarray:
+        out = np.empty(self.shape, self.dtype)
+        if self.nbytes:
+            memcpy_d2h(out, self.ptr)
+        return out
+
+    def zero(self):
+        memcpy_h2d(self.ptr, np.zeros(self.shape, self.dtype))
+
+    def free(self):
+        if self._p is not None and self._p.value:
+            load_library().omfs_device_free(self._p)
+            self._p = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
