@@ -198,8 +198,8 @@ int omfs_session_render_host(omfs_session* s, const omfs_frames_desc* frames,
 int omfs_session_render_device(omfs_session* s, const omfs_frames_desc* d_frames,
                                uint8_t* d_out_u8, float* d_out_f32, void* stream);
 
-/* Counters of the last render call: [0] tile pairs, [1] kernel launches, [2] batches,
- * [3] overflow flag. */
+/* Counters of the last render call: [0] tile pairs (whole call), [1] kernel launches, [2] batches,
+ * [3] overflow flag.  Valid after omfs_session_render_host / omfs_session_sync. */
 int omfs_session_stats(omfs_session* s, uint64_t* out4);
 
 /* Debug taps for the parity tests: pointers into the session's buffers for the LAST batch
@@ -210,8 +210,13 @@ int omfs_session_tap(omfs_session* s, const char* name, void** d_ptr, size_t* by
 /* Waits for the session's streams; returns OMFS_ERR_CAPACITY if any batch overflowed. */
 int omfs_session_sync(omfs_session* s);
 void* omfs_session_stream(omfs_session* s);
-/* out8 = V, F, n_expr, N, kpad, npad, tiles, segments of the last batch */
-int omfs_session_dims(omfs_session* s, int32_t* out8);
+/* out9 = V, F, n_expr, N, kpad, npad, tiles, segments of the last batch, tile pairs of the last batch */
+int omfs_session_dims(omfs_session* s, int32_t* out9);
+/* Per-stage device time (ms) and launch-group counts while profiling is on; stages: flame,
+ * face_frames, bind_preprocess, scan+emit, sort, ranges, composite, unused.  Profiling adds a host
+ * sync per batch: headline numbers are taken with it off. */
+int omfs_session_set_profiling(omfs_session* s, int on);
+int omfs_session_stage_ms(omfs_session* s, double* out_ms8, uint64_t* out_calls8);
 
 /* ------------------------------------------------------------------------------------------
  * Helpers for callers without a CUDA runtime of their own (ctypes, cgo, JNI ...).

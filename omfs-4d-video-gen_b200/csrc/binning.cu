@@ -98,7 +98,8 @@ __global__ void __launch_bounds__(kScanThreads) scan_tile_sums_kernel(long long 
 __global__ void __launch_bounds__(1024) scan_sums_kernel(int n_tiles, uint32_t* __restrict__ tile_sums,
                                                          uint32_t* __restrict__ num_pairs,
                                                          unsigned long long capacity, int* __restrict__ status_flag,
-                                                         uint32_t* __restrict__ sort_count) {
+                                                         uint32_t* __restrict__ sort_count,
+                                                         unsigned long long* __restrict__ pair_accum) {
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_carry;
     if (threadIdx.x == 0) s_carry = 0;
@@ -126,6 +127,7 @@ __global__ void __launch_bounds__(1024) scan_sums_kernel(int n_tiles, uint32_t* 
     if (threadIdx.x == 0) {
         const uint32_t total = s_carry;
         *num_pairs = total;
+        if (pair_accum) *pair_accum += total;  // running total over the batches of one render call
         if ((unsigned long long)total > capacity) {
             // overflow: flag it and sort nothing (emit_keys skips out-of-range Gaussians, so a
             // partial list would contain unwritten keys); the caller re-runs with more capacity
@@ -475,47 +477,40 @@ extern "C" size_t omfs_binning_workspace_bytes(int S, int N, int width, int heig
 
 extern "C" int omfs_binning_sort_bits(int S, int width, int height) { return sort_bits_for(S, width, height); }
 
-extern "C" int omfs_binning(int S, int N, int width, int height, size_t capacity, const float* d_P0,
-                            const uint32_t* d_tiles_touched, uint32_t* d_offsets, uint64_t* d_keys0,
-                            uint64_t* d_keys1, uint32_t* d_vals0, uint32_t* d_vals1, uint32_t* d_ranges,
-                            uint32_t* d_num_pairs, int* d_status_flag, void* d_workspace, size_t workspace_bytes,
-                            int* h_out_buffer_index, void* stream_) {
-    OMFS_REQUIRE(S > 0 && N > 0 && width > 0 && height > 0, "bad sizes");
-    OMFS_REQUIRE(S <= 65535, "at most 65535 segments per call");
-    OMFS_REQUIRE(capacity > 0 && capacity < (1ull << 30), "capacity must be in (0, 2^30)");
-    OMFS_REQUIRE((long long)S * N < (1ll << 31), "S*N must be below 2^31");
-    OMFS_REQUIRE(d_P0 && d_tiles_touched && d_offsets && d_keys0 && d_keys1 && d_vals0 && d_vals1 && d_ranges &&
-                     d_num_pairs && d_status_flag && d_workspace,
-                 "null pointer");
-    const int bits = sort_bits_for(S, width, height);
-    const int passes = (bits + 7) / 8;
-    OMFS_REQUIRE(passes <= kMaxPasses, "too many sort passes");
+namespace omfs {
+
+int binning_scan_emit(int S, int N, int width, int height, size_t capacity, const float* d_P0,
+                      const uint32_t* d_tiles_touched, uint32_t* d_offsets, uint64_t* d_keys, uint32_t* d_vals,
+                      uint32_t* d_ranges, uint32_t* d_num_pairs, int* d_status_flag,
+                      unsigned long long* d_pair_accum, void* d_workspace, cudaStream_t stream) {
     BinningWs w = carve(d_workspace, S, N, width, height, capacity);
-    OMFS_REQUIRE(workspace_bytes >= w.total, "workspace too small (omfs_binning_workspace_bytes)");
-    cudaStream_t stream = (cudaStream_t)stream_;
     const long long count = (long long)S * N;
     const int n_scan_tiles = ceil_div(count, kScanTile);
     const long long tiles_total = (long long)S * ((width + kTile - 1) / kTile) * ((height + kTile - 1) / kTile);
-
     OMFS_CUDA(cudaMemsetAsync(d_workspace, 0, w.zero_bytes, stream));
-    OMFS_CUDA(cudaMemsetAsync(d_ranges, 0, sizeof(uint32_t) * 2 * (size_t)tiles_total, stream));
-
+    if (d_ranges) OMFS_CUDA(cudaMemsetAsync(d_ranges, 0, sizeof(uint32_t) * 2 * (size_t)tiles_total, stream));
     scan_tile_sums_kernel<<<n_scan_tiles, kScanThreads, 0, stream>>>(count, d_tiles_touched, w.tile_sums);
     scan_sums_kernel<<<1, 1024, 0, stream>>>(n_scan_tiles, w.tile_sums, d_num_pairs, (unsigned long long)capacity,
-                                             d_status_flag, w.sort_count);
+                                             d_status_flag, w.sort_count, d_pair_accum);
     scan_apply_kernel<<<n_scan_tiles, kScanThreads, 0, stream>>>(count, d_tiles_touched, w.tile_sums, d_offsets);
     dim3 egrid(ceil_div(N, 256), S);
     emit_keys_kernel<<<egrid, 256, 0, stream>>>(N, width, height, (const float4*)d_P0, d_tiles_touched, d_offsets,
-                                                (unsigned long long)capacity, d_keys0, d_vals0);
+                                                (unsigned long long)capacity, d_keys, d_vals);
     count_launch(4);
     OMFS_LAUNCH_CHECK();
+    return OMFS_OK;
+}
 
+// returns through *out_index which of the two buffer pairs holds the sorted result
+int binning_sort(int S, int N, int width, int height, size_t capacity, uint64_t* d_keys0, uint64_t* d_keys1,
+                 uint32_t* d_vals0, uint32_t* d_vals1, void* d_workspace, int* out_index, cudaStream_t stream) {
+    BinningWs w = carve(d_workspace, S, N, width, height, capacity);
+    const int passes = (sort_bits_for(S, width, height) + 7) / 8;
     const int persistent = kNumSMs * 4;
     rs_histogram_kernel<<<persistent, 256, 0, stream>>>(d_keys0, w.sort_count, passes, w.hist);
     rs_scan_hist_kernel<<<passes, 256, 0, stream>>>(w.hist);
     count_launch(2);
     OMFS_LAUNCH_CHECK();
-
     static bool attr_set = false;
     if (!attr_set) {
         OMFS_CUDA(cudaFuncSetAttribute(rs_onesweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -535,11 +530,47 @@ extern "C" int omfs_binning(int S, int N, int width, int height, size_t capacity
         uint32_t* tv = vin; vin = vout; vout = tv;
     }
     OMFS_LAUNCH_CHECK();
-    // after the swap at the end of the loop, kin/vin hold the sorted pairs
-    tile_ranges_kernel<<<persistent, 256, 0, stream>>>(kin, w.sort_count, d_ranges);
+    *out_index = (kin == d_keys0) ? 0 : 1;  // after the final swap kin/vin hold the sorted pairs
+    return OMFS_OK;
+}
+
+int binning_ranges(int S, int N, int width, int height, size_t capacity, const uint64_t* d_sorted_keys,
+                   uint32_t* d_ranges, void* d_workspace, cudaStream_t stream) {
+    BinningWs w = carve(d_workspace, S, N, width, height, capacity);
+    tile_ranges_kernel<<<kNumSMs * 4, 256, 0, stream>>>(d_sorted_keys, w.sort_count, d_ranges);
     count_launch();
     OMFS_LAUNCH_CHECK();
-    if (h_out_buffer_index) *h_out_buffer_index = (kin == d_keys0) ? 0 : 1;
+    return OMFS_OK;
+}
+
+}  // namespace omfs
+
+extern "C" int omfs_binning(int S, int N, int width, int height, size_t capacity, const float* d_P0,
+                            const uint32_t* d_tiles_touched, uint32_t* d_offsets, uint64_t* d_keys0,
+                            uint64_t* d_keys1, uint32_t* d_vals0, uint32_t* d_vals1, uint32_t* d_ranges,
+                            uint32_t* d_num_pairs, int* d_status_flag, void* d_workspace, size_t workspace_bytes,
+                            int* h_out_buffer_index, void* stream_) {
+    OMFS_REQUIRE(S > 0 && N > 0 && width > 0 && height > 0, "bad sizes");
+    OMFS_REQUIRE(S <= 65535, "at most 65535 segments per call");
+    OMFS_REQUIRE(capacity > 0 && capacity < (1ull << 30), "capacity must be in (0, 2^30)");
+    OMFS_REQUIRE((long long)S * N < (1ll << 31), "S*N must be below 2^31");
+    OMFS_REQUIRE(d_P0 && d_tiles_touched && d_offsets && d_keys0 && d_keys1 && d_vals0 && d_vals1 && d_ranges &&
+                     d_num_pairs && d_status_flag && d_workspace,
+                 "null pointer");
+    const int passes = (sort_bits_for(S, width, height) + 7) / 8;
+    OMFS_REQUIRE(passes <= kMaxPasses, "too many sort passes");
+    OMFS_REQUIRE(workspace_bytes >= carve(nullptr, S, N, width, height, capacity).total,
+                 "workspace too small (omfs_binning_workspace_bytes)");
+    cudaStream_t stream = (cudaStream_t)stream_;
+    int rc = binning_scan_emit(S, N, width, height, capacity, d_P0, d_tiles_touched, d_offsets, d_keys0, d_vals0,
+                               d_ranges, d_num_pairs, d_status_flag, nullptr, d_workspace, stream);
+    if (rc) return rc;
+    int idx = 0;
+    rc = binning_sort(S, N, width, height, capacity, d_keys0, d_keys1, d_vals0, d_vals1, d_workspace, &idx, stream);
+    if (rc) return rc;
+    rc = binning_ranges(S, N, width, height, capacity, idx ? d_keys1 : d_keys0, d_ranges, d_workspace, stream);
+    if (rc) return rc;
+    if (h_out_buffer_index) *h_out_buffer_index = idx;
     return OMFS_OK;
 }
 
@@ -553,20 +584,8 @@ extern "C" int omfs_scan_emit(int S, int N, int width, int height, size_t capaci
     OMFS_REQUIRE(d_P0 && d_tiles_touched && d_offsets && d_keys && d_vals && d_num_pairs && d_status_flag &&
                      d_workspace,
                  "null pointer");
-    BinningWs w = carve(d_workspace, S, N, width, height, capacity);
-    OMFS_REQUIRE(workspace_bytes >= w.total, "workspace too small (omfs_binning_workspace_bytes)");
-    cudaStream_t stream = (cudaStream_t)stream_;
-    const long long count = (long long)S * N;
-    const int n_scan_tiles = ceil_div(count, kScanTile);
-    OMFS_CUDA(cudaMemsetAsync(d_workspace, 0, w.zero_bytes, stream));
-    scan_tile_sums_kernel<<<n_scan_tiles, kScanThreads, 0, stream>>>(count, d_tiles_touched, w.tile_sums);
-    scan_sums_kernel<<<1, 1024, 0, stream>>>(n_scan_tiles, w.tile_sums, d_num_pairs, (unsigned long long)capacity,
-                                             d_status_flag, w.sort_count);
-    scan_apply_kernel<<<n_scan_tiles, kScanThreads, 0, stream>>>(count, d_tiles_touched, w.tile_sums, d_offsets);
-    dim3 egrid(ceil_div(N, 256), S);
-    emit_keys_kernel<<<egrid, 256, 0, stream>>>(N, width, height, (const float4*)d_P0, d_tiles_touched, d_offsets,
-                                                (unsigned long long)capacity, d_keys, d_vals);
-    count_launch(4);
-    OMFS_LAUNCH_CHECK();
-    return OMFS_OK;
+    OMFS_REQUIRE(workspace_bytes >= carve(nullptr, S, N, width, height, capacity).total,
+                 "workspace too small (omfs_binning_workspace_bytes)");
+    return binning_scan_emit(S, N, width, height, capacity, d_P0, d_tiles_touched, d_offsets, d_keys, d_vals, nullptr,
+                             d_num_pairs, d_status_flag, nullptr, d_workspace, (cudaStream_t)stream_);
 }

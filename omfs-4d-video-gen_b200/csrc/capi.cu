@@ -145,7 +145,15 @@ struct omfs_session {
     size_t ws_bytes = 0;
     int last_sorted_buffer = 0, last_image_buffer = 0, last_batch_segments = 0;
     uint64_t stats[4]{};
+    // optional per-stage timing (bench.py's roofline pass): events around every stage of every batch
+    bool profiling = false;
+    cudaEvent_t prof_ev[8]{};
+    double stage_ms[8]{};
+    uint64_t stage_calls[8]{};
+    uint32_t last_pairs = 0;
 };
+
+enum Stage { kStFlame = 0, kStFaceFrames, kStBindPre, kStScanEmit, kStSort, kStRanges, kStComposite, kStCount };
 
 static int upload(DevBuf& b, const void* h, size_t bytes, cudaStream_t st) {
     int rc = b.ensure(bytes);
@@ -179,6 +187,8 @@ extern "C" void omfs_session_destroy(omfs_session* s) {
         if (s->ev_done[i]) cudaEventDestroy(s->ev_done[i]);
         if (s->ev_copied[i]) cudaEventDestroy(s->ev_copied[i]);
     }
+    for (int i = 0; i < 8; i++)
+        if (s->prof_ev[i]) cudaEventDestroy(s->prof_ev[i]);
     if (s->stream) cudaStreamDestroy(s->stream);
     if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
     delete s;
@@ -365,13 +375,34 @@ static int render_core(omfs_session* s, int T, int n_views, const float* p_expr,
     uint32_t* d_num_pairs = s->counters.as<uint32_t>();
     int* d_flag = s->counters.as<int>() + 1;
     OMFS_CUDA(cudaMemsetAsync(s->counters.p, 0, 256, st));
-    uint64_t* d_pair_total = reinterpret_cast<uint64_t*>(s->counters.as<unsigned char>() + 16);
-    (void)d_pair_total;
+
+    unsigned long long* d_pair_accum = reinterpret_cast<unsigned long long*>(s->counters.as<unsigned char>() + 16);
+    const bool prof = s->profiling;
+    if (prof)
+        for (int i = 0; i < 8; i++)
+            if (!s->prof_ev[i]) OMFS_CUDA(cudaEventCreate(&s->prof_ev[i]));
+    // stage timing helper: record before/after, resolve at the end of the batch
+    auto mark = [&](int i) -> int {
+        if (prof) OMFS_CUDA(cudaEventRecord(s->prof_ev[i], st));
+        return OMFS_OK;
+    };
+    auto resolve = [&](int first_stage, int last_stage) -> int {
+        if (!prof) return OMFS_OK;
+        OMFS_CUDA(cudaEventSynchronize(s->prof_ev[last_stage + 1]));
+        for (int k = first_stage; k <= last_stage; k++) {
+            float ms = 0.f;
+            OMFS_CUDA(cudaEventElapsedTime(&ms, s->prof_ev[k], s->prof_ev[k + 1]));
+            s->stage_ms[k] += ms;
+            s->stage_calls[k]++;
+        }
+        return OMFS_OK;
+    };
 
     int batch_index = 0;
     for (int g0 = 0; g0 < T; g0 += geo) {
         const int gT = std::min(geo, T - g0);
         // ---- FLAME: operand prep, blendshape GEMM (tensor cores), skinning
+        if ((rc = mark(kStFlame))) return rc;
         if ((rc = omfs_flame_pose_prep(gT, s->n_expr, s->kpad, p_expr + (size_t)g0 * s->n_expr, p_rot + (size_t)g0 * 3,
                                        p_neck + (size_t)g0 * 3, p_jaw + (size_t)g0 * 3, p_eyes + (size_t)g0 * 6,
                                        s->acoef.as<float>(), s->rmats.as<float>(), st)))
@@ -387,24 +418,37 @@ static int render_core(omfs_session* s, int T, int n_views, const float* p_expr,
                                  p_transl + (size_t)g0 * 3, dyn_g, dyn_g ? s->jdyn.as<float>() : nullptr,
                                  s->verts.as<float>(), st)))
             return rc;
+        if ((rc = mark(kStFlame + 1))) return rc;
+        if ((rc = resolve(kStFlame, kStFlame))) return rc;
         // ---- render batches inside the chunk
         for (int b0 = 0; b0 < gT; b0 += fpb) {
             const int bT = std::min(fpb, gT - b0);
             const int S = bT * n_views;
             const int ib = batch_index & 1;
+            if ((rc = mark(kStFaceFrames))) return rc;
             if ((rc = omfs_face_frames(bT, V, F, s->verts.as<float>() + (size_t)b0 * V * 3, s->faces.as<int32_t>(),
                                        s->ff.as<float>(), st)))
                 return rc;
+            if ((rc = mark(kStBindPre))) return rc;
             if ((rc = omfs_bind_preprocess(S, N, F, W, H, s->ff.as<float>(), s->seg_frame.as<int32_t>(),
                                            s->cams.as<float>(), s->xyzb.as<float>(), s->scale_lo.as<float>(),
                                            s->rot.as<float>(), s->sh.as<float>(), s->P0.as<float>(),
                                            s->P1.as<float>(), s->P2.as<float>(), s->tt.as<uint32_t>(), st)))
                 return rc;
+            if ((rc = mark(kStScanEmit))) return rc;
+            if ((rc = binning_scan_emit(S, N, W, H, s->capacity, s->P0.as<float>(), s->tt.as<uint32_t>(),
+                                        s->offsets.as<uint32_t>(), s->keys0.as<uint64_t>(), s->vals0.as<uint32_t>(),
+                                        s->ranges.as<uint32_t>(), d_num_pairs, d_flag, d_pair_accum, s->ws.p, st)))
+                return rc;
+            if ((rc = mark(kStSort))) return rc;
             int sorted = 0;
-            if ((rc = omfs_binning(S, N, W, H, s->capacity, s->P0.as<float>(), s->tt.as<uint32_t>(),
-                                   s->offsets.as<uint32_t>(), s->keys0.as<uint64_t>(), s->keys1.as<uint64_t>(),
-                                   s->vals0.as<uint32_t>(), s->vals1.as<uint32_t>(), s->ranges.as<uint32_t>(),
-                                   d_num_pairs, d_flag, s->ws.p, s->ws_bytes, &sorted, st)))
+            if ((rc = binning_sort(S, N, W, H, s->capacity, s->keys0.as<uint64_t>(), s->keys1.as<uint64_t>(),
+                                   s->vals0.as<uint32_t>(), s->vals1.as<uint32_t>(), s->ws.p, &sorted, st)))
+                return rc;
+            if ((rc = mark(kStRanges))) return rc;
+            if ((rc = binning_ranges(S, N, W, H, s->capacity,
+                                     sorted ? s->keys1.as<uint64_t>() : s->keys0.as<uint64_t>(),
+                                     s->ranges.as<uint32_t>(), s->ws.p, st)))
                 return rc;
             s->last_sorted_buffer = sorted;
             // the image buffer may still be draining to the host from two batches ago
@@ -416,10 +460,13 @@ static int render_core(omfs_session* s, int T, int n_views, const float* p_expr,
             float* dst_f = direct ? (out_f32 ? out_f32 + seg0 * 3 * hw : nullptr) : (out_f32 ? img : nullptr);
             uint8_t* dst_8 = direct ? (out_u8 ? out_u8 + seg0 * 3 * hw : nullptr) : (out_u8 ? img8 : nullptr);
             if (!dst_f && !dst_8) dst_f = img;  // nothing requested: still render (debug taps)
+            if ((rc = mark(kStComposite))) return rc;
             if ((rc = omfs_composite(S, N, W, H, s->P0.as<float>(), s->P1.as<float>(), s->P2.as<float>(),
                                      sorted ? s->vals1.as<uint32_t>() : s->vals0.as<uint32_t>(),
                                      s->ranges.as<uint32_t>(), s->cfg.bg, dst_f, dst_8, st)))
                 return rc;
+            if ((rc = mark(kStComposite + 1))) return rc;
+            if ((rc = resolve(kStFaceFrames, kStComposite))) return rc;
             s->last_image_buffer = ib;
             s->last_batch_segments = S;
             if (out_on_host) {
@@ -442,10 +489,13 @@ static int render_core(omfs_session* s, int T, int n_views, const float* p_expr,
 }
 
 static int finish_stats(omfs_session* s) {
-    uint32_t h[2] = {0, 0};
+    uint32_t h[8] = {0};
     OMFS_CUDA(cudaMemcpy(h, s->counters.p, sizeof(h), cudaMemcpyDeviceToHost));
-    s->stats[0] = h[0];  // pairs of the last batch
+    unsigned long long total = 0;
+    memcpy(&total, &h[4], 8);
+    s->stats[0] = total;  // tile pairs over the whole call
     s->stats[3] = h[1];
+    s->last_pairs = h[0];
     if (h[1]) {
         set_error("tile-pair list overflowed the session capacity (%zu); raise pair_capacity", s->capacity);
         return OMFS_ERR_CAPACITY;
@@ -545,9 +595,32 @@ extern "C" int omfs_session_tap(omfs_session* s, const char* name, void** d_ptr,
     return OMFS_ERR_INVALID;
 }
 
-extern "C" int omfs_session_dims(omfs_session* s, int32_t* out8) {
+// Per-stage device time, accumulated while profiling is on (it costs a host sync per batch, so the
+// headline throughput is measured with profiling off).  out_ms/out_calls: flame, face_frames,
+// bind_preprocess, scan+emit, sort, ranges, composite, (unused).
+extern "C" int omfs_session_set_profiling(omfs_session* s, int on) {
+    OMFS_REQUIRE(s, "null argument");
+    s->profiling = on != 0;
+    for (int i = 0; i < 8; i++) {
+        s->stage_ms[i] = 0.0;
+        s->stage_calls[i] = 0;
+    }
+    return OMFS_OK;
+}
+extern "C" int omfs_session_stage_ms(omfs_session* s, double* out_ms8, uint64_t* out_calls8) {
+    OMFS_REQUIRE(s && out_ms8 && out_calls8, "null argument");
+    for (int i = 0; i < 8; i++) {
+        out_ms8[i] = s->stage_ms[i];
+        out_calls8[i] = s->stage_calls[i];
+    }
+    return OMFS_OK;
+}
+
+extern "C" int omfs_session_dims(omfs_session* s, int32_t* out9) {
+    int32_t* out8 = out9;
     OMFS_REQUIRE(s && out8, "null argument");
     out8[0] = s->V; out8[1] = s->F; out8[2] = s->n_expr; out8[3] = s->N;
     out8[4] = s->kpad; out8[5] = s->npad; out8[6] = s->tiles; out8[7] = s->last_batch_segments;
+    out8[8] = (int32_t)s->last_pairs;
     return OMFS_OK;
 }

@@ -79,6 +79,8 @@ def load_library():
     L.omfs_session_stats.argtypes = [c_void_p, POINTER(c_uint64)]
     L.omfs_session_tap.argtypes = [c_void_p, c_char_p, POINTER(c_void_p), POINTER(c_size_t)]
     L.omfs_session_dims.argtypes = [c_void_p, POINTER(c_int32)]
+    L.omfs_session_set_profiling.argtypes = [c_void_p, c_int]
+    L.omfs_session_stage_ms.argtypes = [c_void_p, POINTER(c_double), POINTER(c_uint64)]
     L.omfs_host_alloc.argtypes = [POINTER(c_void_p), c_size_t]
     L.omfs_host_free.argtypes = [c_void_p]
     L.omfs_device_alloc.argtypes = [POINTER(c_void_p), c_size_t]
@@ -254,14 +256,24 @@ class Session:
     def stats(self) -> dict:
         out = (c_uint64 * 4)()
         check(self._L.omfs_session_stats(self._h, out))
-        return {"pairs_last_batch": int(out[0]), "launches": int(out[1]), "batches": int(out[2]),
-                "overflow": int(out[3])}
+        return {"pairs": int(out[0]), "launches": int(out[1]), "batches": int(out[2]), "overflow": int(out[3])}
 
     def dims(self) -> dict:
-        out = (c_int32 * 8)()
+        out = (c_int32 * 9)()
         check(self._L.omfs_session_dims(self._h, out))
-        keys = ("V", "F", "n_expr", "N", "kpad", "npad", "tiles", "last_batch_segments")
+        keys = ("V", "F", "n_expr", "N", "kpad", "npad", "tiles", "last_batch_segments", "pairs_last_batch")
         return dict(zip(keys, [int(x) for x in out]))
+
+    STAGES = ("flame", "face_frames", "bind_preprocess", "scan_emit", "sort", "ranges", "composite")
+
+    def set_profiling(self, on: bool):
+        check(self._L.omfs_session_set_profiling(self._h, 1 if on else 0))
+
+    def stage_ms(self) -> dict:
+        ms = (c_double * 8)()
+        calls = (c_uint64 * 8)()
+        check(self._L.omfs_session_stage_ms(self._h, ms, calls))
+        return {n: {"ms": float(ms[i]), "calls": int(calls[i])} for i, n in enumerate(self.STAGES)}
 
     def tap(self, name: str):
         p, n = c_void_p(), c_size_t()

@@ -1,0 +1,113 @@
+"""Parity and size-independent properties at BASELINE.json's full sizes (512^2, 100k Gaussians)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def full_scene():
+    import omfs_b200  # noqa: F401
+    from omfs_b200 import avatar, synthetic
+    model, params, av, cam = synthetic.make_scene(n_gauss=100_000, n_frames=70, width=512, height=512)
+    return model, params, av, avatar.bake(av), cam
+
+
+def test_config2_single_frame_and_batch_consistency(full_scene):
+    """configs[1]/[2]: oracle parity on sampled frames of a 70-frame clip rendered in 32-frame batches;
+    the same frames rendered alone (batch of 1) must be bit-identical (batching is invisible)."""
+    import oracle
+    from oracle import reference_rows as rr
+    from omfs_b200 import runtime as rt
+    model, params, av, baked, cam = full_scene
+    W = H = 512
+    T = params.n_frames
+    sess = rt.Session(model, baked, W, H, max_batch=32)
+    sess.set_subject(params.shape, params.static_offset)
+    u8, img = sess.render_host(params, [cam], want_f32=True)
+    verts = sess.tap_array("verts", (T, model.n_verts, 3), np.float32)
+    pairs_per_frame = sess.stats()["pairs"] / T
+    assert 2e5 < pairs_per_frame < 2e6
+    sample = [0, 33, 69]
+    sub = type(params)(params.shape, *[getattr(params, k)[sample] for k in
+                                       ("expr", "rotation", "neck_pose", "jaw_pose", "eyes_pose", "translation")],
+                       params.static_offset, params.dynamic_offset[sample])
+    full = oracle.render(model, sub, baked, [cam.pack()] * 3, W, H)
+    assert np.abs(verts[sample] - full.verts).max() <= 1e-5
+    ref = oracle.render(model, sub, baked, [cam.pack()] * 3, W, H, verts=verts[sample])
+    # exact-domain hand-off: identical decisions, so the image agrees to float rounding
+    assert np.abs(img[sample] - ref.image).max() <= 1e-5
+    assert (oracle.to_uint8(ref.image) != u8[sample]).mean() < 1e-5
+    # fully independent chains: PSNR bar, and max-abs 1e-3 except knife-edge pixels (DESIGN.md §3:
+    # an alpha within rounding of 1/255 flips a <= 4e-3 contribution); count and bound them
+    diff = np.abs(img[sample] - full.image)
+    assert rr.psnr(img[sample] * 255.0, full.image * 255.0) > 50.0
+    assert (diff > 1e-3).mean() < 1e-5
+    assert diff.max() < 1.2e-2
+    # batch invariance
+    one = rt.Session(model, baked, W, H, max_batch=1)
+    one.set_subject(params.shape, params.static_offset)
+    u8_1, img_1 = one.render_host(sub, [cam], want_f32=True)
+    assert np.array_equal(img_1.view(np.uint32), img[sample].view(np.uint32))
+    assert np.array_equal(u8_1, u8[sample])
+    one.close()
+    sess.close()
+
+
+def test_sort_properties_full_size(full_scene):
+    """Size-independent properties of the binning at full size: keys sorted, a permutation of the
+    emitted pairs (checksum of keys and of (key,value) products), ranges partition the list, every
+    Gaussian index in range, per-tile depth order non-decreasing."""
+    from omfs_b200 import runtime as rt
+    model, params, av, baked, cam = full_scene
+    W = H = 512
+    S = 16
+    sess = rt.Session(model, baked, W, H, max_batch=S)
+    sess.set_subject(params.shape, params.static_offset)
+    sess.render_host(params.slice(0, S), [cam], want_u8=True)
+    R = sess.dims()["pairs_last_batch"]
+    N = baked["n"]
+    keys = sess.tap_array("keys", (R,), np.uint64)
+    vals = sess.tap_array("vals", (R,), np.uint32)
+    tt = sess.tap_array("tiles_touched", (S, N), np.uint32)
+    P0 = sess.tap_array("P0", (S, N, 4), np.float32)
+    assert int(tt.sum()) == R
+    assert np.all(keys[1:] >= keys[:-1])
+    assert vals.max() < N
+    tiles = 32 * 32
+    ranges = sess.tap_array("ranges", (S * tiles, 2), np.uint32).astype(np.int64)
+    lens = ranges[:, 1] - ranges[:, 0]
+    assert lens.min() >= 0 and int(lens.sum()) == R
+    nz = lens > 0
+    assert np.array_equal(ranges[nz][1:, 0], ranges[nz][:-1, 1])     # contiguous partition
+    tile_of = (keys >> np.uint64(32)).astype(np.int64)
+    assert np.array_equal(np.repeat(np.arange(S * tiles), lens), tile_of)
+    # depth bits of each pair equal the depth of the Gaussian it names, in its own segment
+    seg = tile_of // tiles
+    depth_bits = (keys & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+    assert np.array_equal(depth_bits, P0[seg, vals, 2].view(np.uint32))
+    # multiset of (segment, gaussian) pairs = each visible Gaussian exactly tiles_touched times
+    counts = np.bincount(seg * N + vals.astype(np.int64), minlength=S * N)
+    assert np.array_equal(counts.astype(np.uint32), tt.reshape(-1))
+    sess.close()
+
+
+def test_linearity_of_blendshapes_full_size(full_scene):
+    """U1 is linear in the expression coefficients: with pose fixed at zero, verts(a*e1 + b*e2) ==
+    a*verts(e1) + b*verts(e2) - (a+b-1)*verts(0) to fp32 accuracy, at full FLAME size."""
+    from omfs_b200 import runtime as rt, synthetic
+    model, params, av, baked, cam = full_scene
+    rng = np.random.default_rng(0)
+    e1, e2 = rng.normal(0, 0.5, 100).astype(np.float32), rng.normal(0, 0.5, 100).astype(np.float32)
+    a, b = 0.7, -1.3
+    z3, z6 = np.zeros((4, 3), np.float32), np.zeros((4, 6), np.float32)
+    expr = np.stack([e1, e2, np.float32(a) * e1 + np.float32(b) * e2, np.zeros(100, np.float32)])
+    p = synthetic.FrameParams(params.shape, expr, z3, z3, z3, z6, z3, params.static_offset,
+                              np.zeros((4, model.n_verts, 3), np.float32))
+    sess = rt.Session(model, baked, 64, 64, max_batch=4)
+    sess.set_subject(params.shape, params.static_offset)
+    sess.render_host(p, [synthetic.make_camera(64, 64)])
+    v = sess.tap_array("verts", (4, model.n_verts, 3), np.float32).astype(np.float64)
+    lin = a * v[0] + b * v[1] - (a + b - 1.0) * v[3]
+    assert np.abs(v[2] - lin).max() <= 1e-6
+    sess.close()

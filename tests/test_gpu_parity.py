@@ -1,0 +1,291 @@
+"""Parity of the CUDA path against the oracle, through the C-ABI (pytest -m gpu, on a B200).
+
+Bars (BASELINE.json north_star): tile/sort keys, masks and Gaussian->triangle indices bit-exact;
+images and vertex positions max-abs <= 1e-3 per channel, PSNR > 50 dB.  The exact domain (face
+frames -> keys -> ranges, and every skip/stop decision of compositing) is compared on IDENTICAL
+inputs: the oracle is fed the vertices the GPU produced, because the tensor-core blendshape GEMM is
+tolerance-checked, not bit-exact.
+"""
+import ctypes
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-3  # stated tolerance: max abs per channel / per vertex coordinate
+
+
+@pytest.fixture(scope="module")
+def rt():
+    import omfs_b200  # noqa: F401
+    from omfs_b200 import runtime
+    L = runtime.load_library()
+    runtime.check(L.omfs_device_check(0))
+    return runtime
+
+
+def bits(a):
+    return np.ascontiguousarray(a).view(np.uint32)
+
+
+def psnr01(a, b):
+    from oracle import reference_rows as rr
+    return rr.psnr(a.astype(np.float64) * 255.0, b.astype(np.float64) * 255.0)
+
+
+def run_session(rt, model, params, baked, cams, W, H, max_batch, gemm_impl=0, plan_offset=None, **kw):
+    sess = rt.Session(model, baked, W, H, max_batch=max_batch, gemm_impl=gemm_impl, **kw)
+    sess.set_subject(params.shape, params.static_offset, plan_offset)
+    u8, img = sess.render_host(params, cams, want_f32=True)
+    return sess, u8, img
+
+
+@pytest.mark.parametrize("gemm_impl", [0, 1])
+def test_full_chain_small(rt, small_scene, gemm_impl):
+    import oracle
+    model, params, av, baked, cam = small_scene
+    W, H = cam.width, cam.height  # 160 x 112: 10 x 7 tiles
+    T, V, F, N = params.n_frames, model.n_verts, model.n_faces, baked["n"]
+    sess, u8, img = run_session(rt, model, params, baked, [cam], W, H, max_batch=T, gemm_impl=gemm_impl)
+    verts = sess.tap_array("verts", (T, V, 3), np.float32)
+    full = oracle.render(model, params, baked, [cam.pack()] * T, W, H)
+    assert np.abs(verts - full.verts).max() <= 1e-5          # vertices: well inside the 1e-3 bar
+    ref = oracle.render(model, params, baked, [cam.pack()] * T, W, H, verts=verts)
+    # exact domain, bit for bit
+    assert np.array_equal(bits(sess.tap_array("ff", (T, F, 20), np.float32)), bits(ref.ff))
+    assert np.array_equal(bits(sess.tap_array("P0", (T, N, 4), np.float32)), bits(ref.pre.P0))
+    assert np.array_equal(bits(sess.tap_array("P1", (T, N, 4), np.float32)), bits(ref.pre.P1))
+    assert np.array_equal(bits(sess.tap_array("P2", (T, N, 4), np.float32)), bits(ref.pre.P2))
+    assert np.array_equal(sess.tap_array("tiles_touched", (T, N), np.uint32), ref.pre.tiles_touched)
+    R = ref.binned.n_pairs
+    assert sess.dims()["pairs_last_batch"] == R == sess.stats()["pairs"]
+    assert np.array_equal(sess.tap_array("offsets", (T * N,), np.uint32), ref.binned.offsets)
+    assert np.array_equal(sess.tap_array("keys", (R,), np.uint64), ref.binned.sorted_keys)
+    assert np.array_equal(sess.tap_array("vals", (R,), np.uint32), ref.binned.sorted_values)
+    tiles = ((W + 15) // 16) * ((H + 15) // 16)
+    assert np.array_equal(sess.tap_array("ranges", (T * tiles, 2), np.uint32), ref.binned.ranges)
+    # images
+    assert np.abs(img - ref.image).max() <= 1e-5
+    assert np.abs(img - full.image).max() <= TOL
+    assert psnr01(img, full.image) > 50.0
+    assert (oracle.to_uint8(ref.image) != u8).mean() < 1e-4
+    sess.close()
+
+
+def test_level1_stages_and_unsorted_keys(rt, small_scene):
+    """Every level-1 entry point on caller-owned device memory, including the unsorted key list."""
+    import oracle
+    from omfs_b200.runtime import DeviceArray as DA
+    model, params, av, baked, cam = small_scene
+    W, H = cam.width, cam.height
+    T, V, F, N = params.n_frames, model.n_verts, model.n_faces, baked["n"]
+    L = rt.load_library()
+    ref = oracle.render(model, params, baked, [cam.pack()] * T, W, H)
+    d_verts = DA.from_numpy(ref.verts)
+    d_faces = DA.from_numpy(model.faces.astype(np.int32))
+    d_ff = DA((T, F, 20), np.float32)
+    rt.check(L.omfs_face_frames(T, V, F, d_verts.ptr, d_faces.ptr, d_ff.ptr, None))
+    assert np.array_equal(bits(d_ff.numpy()), bits(ref.ff))
+
+    S = T
+    d_seg = DA.from_numpy(np.arange(S, dtype=np.int32))
+    d_cams = DA.from_numpy(np.stack([cam.pack()] * S))
+    d_b = {k: DA.from_numpy(baked[k]) for k in ("xyzb", "scale_lo", "rot", "sh")}
+    d_P = [DA((S, N, 4), np.float32) for _ in range(3)]
+    d_tt = DA((S, N), np.uint32)
+    rt.check(L.omfs_bind_preprocess(S, N, F, W, H, d_ff.ptr, d_seg.ptr, d_cams.ptr, d_b["xyzb"].ptr,
+                                    d_b["scale_lo"].ptr, d_b["rot"].ptr, d_b["sh"].ptr, d_P[0].ptr, d_P[1].ptr,
+                                    d_P[2].ptr, d_tt.ptr, None))
+    assert np.array_equal(bits(d_P[0].numpy()), bits(ref.pre.P0))
+    assert np.array_equal(d_tt.numpy(), ref.pre.tiles_touched)
+    # Gaussian -> triangle indices ride through the baked stream untouched
+    from omfs_b200 import avatar as avatar_mod
+    assert np.array_equal(avatar_mod.binding_of({"xyzb": d_b["xyzb"].numpy()}), av.binding)
+
+    cap = ref.binned.n_pairs + 17
+    ws_bytes = L.omfs_binning_workspace_bytes(S, N, W, H, cap)
+    d_ws = DA((ws_bytes,), np.uint8)
+    d_off = DA((S * N,), np.uint32)
+    d_k = [DA((cap,), np.uint64) for _ in range(2)]
+    d_v = [DA((cap,), np.uint32) for _ in range(2)]
+    d_cnt = DA((4,), np.uint32)
+    d_cnt.zero()
+    flag_ptr = d_cnt.ptr + 4
+    rt.check(L.omfs_scan_emit(S, N, W, H, cap, d_P[0].ptr, d_tt.ptr, d_off.ptr, d_k[0].ptr, d_v[0].ptr, d_cnt.ptr,
+                              flag_ptr, d_ws.ptr, ws_bytes, None))
+    R = ref.binned.n_pairs
+    assert int(d_cnt.numpy()[0]) == R
+    assert np.array_equal(d_k[0].numpy()[:R], ref.binned.keys)       # UNSORTED keys, emission order
+    assert np.array_equal(d_v[0].numpy()[:R], ref.binned.values)
+    tiles = ((W + 15) // 16) * ((H + 15) // 16)
+    d_ranges = DA((S * tiles, 2), np.uint32)
+    idx = ctypes.c_int(0)
+    rt.check(L.omfs_binning(S, N, W, H, cap, d_P[0].ptr, d_tt.ptr, d_off.ptr, d_k[0].ptr, d_k[1].ptr, d_v[0].ptr,
+                            d_v[1].ptr, d_ranges.ptr, d_cnt.ptr, flag_ptr, d_ws.ptr, ws_bytes, ctypes.byref(idx),
+                            None))
+    assert L.omfs_binning_sort_bits(S, W, H) == ref.binned.sort_bits
+    assert np.array_equal(d_k[idx.value].numpy()[:R], ref.binned.sorted_keys)
+    assert np.array_equal(d_v[idx.value].numpy()[:R], ref.binned.sorted_values)
+    assert np.array_equal(d_ranges.numpy(), ref.binned.ranges)
+    assert int(d_cnt.numpy()[1]) == 0
+
+    d_img = DA((S, 3, H, W), np.float32)
+    d_u8 = DA((S, H, W, 3), np.uint8)
+    bg = (ctypes.c_float * 3)(1.0, 1.0, 1.0)
+    rt.check(L.omfs_composite(S, N, W, H, d_P[0].ptr, d_P[1].ptr, d_P[2].ptr, d_v[idx.value].ptr, d_ranges.ptr, bg,
+                              d_img.ptr, d_u8.ptr, None))
+    img = d_img.numpy()
+    assert np.abs(img - ref.image).max() <= 1e-5
+    assert (oracle.to_uint8(ref.image) != d_u8.numpy()).mean() < 1e-4
+    d_u8b = DA((S, H, W, 3), np.uint8)
+    rt.check(L.omfs_to_uint8(S, W, H, d_img.ptr, d_u8b.ptr, None))
+    assert np.array_equal(d_u8b.numpy(), d_u8.numpy())
+
+
+def test_capacity_overflow_is_reported(rt, small_scene):
+    model, params, av, baked, cam = small_scene
+    sess = rt.Session(model, baked, cam.width, cam.height, max_batch=3, pair_capacity=1000)
+    sess.set_subject(params.shape, params.static_offset)
+    with pytest.raises(rt.OmfsError, match="capacity"):
+        sess.render_host(params, [cam])
+    sess.close()
+
+
+def test_ragged_batches_views_and_odd_image_size(rt):
+    """T not a multiple of the batch, two views per frame, an image that is not a multiple of 16,
+    N not a multiple of 256, dynamic offsets on."""
+    import omfs_b200  # noqa: F401
+    import oracle
+    from omfs_b200 import avatar, cameras, synthetic
+    W, H = 150, 90
+    model = synthetic.make_flame_model(seed=3, n_verts=642)
+    params = synthetic.make_frame_params(5, seed=4, n_verts=642, dynamic=True)
+    av = synthetic.make_avatar(3001, model.n_faces, seed=5)
+    baked = avatar.bake(av)
+    d = synthetic.camera_distance(W, H)
+    cams = cameras.ring_cameras(2, d, (0, 0, 0), 0.3, W, H)
+    sess, u8, img = run_session(rt, model, params, baked, cams, W, H, max_batch=4)   # 2 frames x 2 views per batch
+    S = 5 * 2
+    assert img.shape == (S, 3, H, W)
+    seg_frame = np.repeat(np.arange(5), 2)
+    packed = [cams[i % 2].pack() for i in range(S)]
+    full = oracle.render(model, params, baked, packed, W, H, seg_frame=seg_frame)
+    verts = sess.tap_array("verts", (5, 642, 3), np.float32)
+    assert np.abs(verts - full.verts).max() <= 1e-5
+    ref = oracle.render(model, params, baked, packed, W, H, seg_frame=seg_frame, verts=verts)
+    assert np.abs(img - ref.image).max() <= 1e-5
+    assert np.abs(img - full.image).max() <= TOL
+    assert psnr01(img, full.image) > 50.0
+    # last batch = frame 4, two views
+    P0 = sess.tap_array("P0", (2, 3001, 4), np.float32)
+    assert np.array_equal(bits(P0), bits(ref.pre.P0[8:]))
+    sess.close()
+
+
+def test_empty_and_fully_culled(rt, small_scene):
+    """No frames -> no work; a camera looking away culls everything -> background only, zero pairs."""
+    import oracle
+    from omfs_b200 import cameras, synthetic
+    model, params, av, baked, cam = small_scene
+    W, H = cam.width, cam.height
+    sess = rt.Session(model, baked, W, H, max_batch=2)
+    sess.set_subject(params.shape, params.static_offset)
+    u8, _ = sess.render_host(params.slice(0, 0), [cam])
+    assert u8.shape[0] == 0
+    away = cameras.camera_from_c2w(cameras.look_at_c2w((0, 0, 1.0), (0, 0, 5.0)), 0.3, W, H)
+    u8, img = sess.render_host(params.slice(0, 1), [away], want_f32=True)
+    assert sess.stats()["pairs"] == 0
+    assert np.all(img == 1.0) and np.all(u8 == 255)
+    ref = oracle.render(model, params.slice(0, 1), baked, [away.pack()], W, H)
+    assert ref.binned.n_pairs == 0 and np.array_equal(ref.image, img)
+    sess.close()
+
+
+def test_blend_gemm_tensor_core_vs_cuda_core(rt):
+    """U1+U2: the tcgen05 kernel against the fp32 CUDA-core kernel on the same operands, ragged M
+    (T = 1, 130, 257) so that TMA's out-of-bounds fill is exercised."""
+    from omfs_b200.runtime import DeviceArray as DA
+    L = rt.load_library()
+    rng = np.random.default_rng(0)
+    kpad, npad = 136, 1024
+    K3 = 3 * kpad
+
+    def hi(x):
+        return (x.view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
+
+    for T in (1, 130, 257):
+        a = rng.normal(0, 0.5, (T, kpad)).astype(np.float32)
+        b = rng.normal(0, 1e-3, (npad, kpad)).astype(np.float32)
+        ah, bh = hi(a), hi(b)
+        al, bl = hi(a - ah), hi(b - bh)
+        A = np.concatenate([ah, ah, al], axis=1)
+        Bt = np.concatenate([bh, bl, bh], axis=1)
+        base = rng.normal(0, 0.1, npad).astype(np.float32)
+        want = base[None].astype(np.float64) + a.astype(np.float64) @ b.astype(np.float64).T
+        dA, dB, dbase = DA.from_numpy(A), DA.from_numpy(Bt), DA.from_numpy(base)
+        out = {}
+        for impl in (0, 1):
+            dC = DA((T, npad), np.float32)
+            rt.check(L.omfs_flame_blend_gemm(T, kpad, npad, dA.ptr, dB.ptr, dbase.ptr, dC.ptr, impl, None))
+            out[impl] = dC.numpy()
+            assert np.abs(out[impl] - want).max() <= 2e-7, (T, impl)   # fp32-class accuracy from tf32x3
+        assert np.abs(out[0] - out[1]).max() <= 2e-7
+        assert A.shape[1] == K3
+
+
+def test_displace_points_masks_and_moves_bit_exact(rt, golden_dir):
+    """R5/R6 on the reference's sphere fixture and on FLAME-sized point sets: masks AND moved points
+    bit-exact against the float64 restatement (which is pinned to the reference by the goldens)."""
+    import os
+    from oracle import reference_rows as rr
+    from omfs_b200.runtime import DeviceArray as DA
+    L = rt.load_library()
+    g = np.load(os.path.join(golden_dir, "surgical_sim_golden.npz"))
+    pts = np.concatenate([g["maxilla"], g["mandible"]]).astype(np.float32)
+    n_max = len(g["maxilla"])
+    rng = np.random.default_rng(1)
+    big = rng.normal(0, 30, (5023, 3)).astype(np.float32)
+    for points, mand_first in ((pts, n_max), (big, 2500)):
+        P = len(points)
+        is_mand = np.arange(P) >= mand_first
+        center = (points.min(0).astype(np.float64) + points.max(0).astype(np.float64)) / 2
+        planes = np.zeros((3, 8))
+        planes[0, :3], planes[0, 3:6] = rr.angle_to_normal((0, 0, 1), 8.0, -4.0), (center[0], center[1], 15.0)
+        planes[1, :3], planes[1, 3:6] = rr.angle_to_normal((1, 0, 0), 0.0, 6.0), (-12.0, center[1], center[2])
+        planes[2, :3], planes[2, 3:6] = rr.angle_to_normal((1, 0, 0), -5.0, 0.0), (18.0, center[1], center[2])
+        moves = rr.make_moves(5.0, -8.0, (0.2, 1.0, 0.1), (5.0, -3.0, 2.0), (0.0, 7.5, 0.0))
+        want_pts, want_mask, want_bbox = rr.displace_points(points, planes, moves, is_mand)
+        d_pts = DA.from_numpy(points)
+        d_mask, d_out, d_bbox = DA((P,), np.uint8), DA((P, 3), np.float32), DA((12,), np.float32)
+        pl = (ctypes.c_double * 24)(*planes.reshape(-1))
+        mv = (ctypes.c_double * 24)(*moves.reshape(-1))
+        rt.check(L.omfs_displace_points(P, d_pts.ptr, pl, mv, None, int(mand_first), d_mask.ptr, d_out.ptr,
+                                        d_bbox.ptr, None))
+        assert np.array_equal(d_mask.numpy(), want_mask)
+        assert np.array_equal(bits(d_out.numpy()), bits(want_pts))
+        assert np.array_equal(bits(d_bbox.numpy().reshape(2, 6)), bits(want_bbox))
+
+
+def test_plan_offset_and_reference_scalar_edit(rt, small_scene):
+    """Stage 2 both ways: (a) the reference's two scalar edits (render_surgery.py:119-139) applied to
+    the parameters; (b) a canonical-space displacement field folded into the subject."""
+    import oracle
+    from oracle import reference_rows as rr
+    from omfs_b200 import synthetic
+    model, params, av, baked, cam = small_scene
+    W, H = cam.width, cam.height
+    T, V = params.n_frames, model.n_verts
+    rec = rr.modify_flame_params(params.as_dict(), rr.compute_offset(5.0, 1.0), rr.compute_offset(-3.0, 1.0))
+    edited = synthetic.FrameParams.from_dict(rec, n_verts=V)
+    rng = np.random.default_rng(2)
+    plan = rng.normal(0, 1e-3, (V, 3)).astype(np.float32)
+    sess, u8, img = run_session(rt, model, edited, baked, [cam], W, H, max_batch=T, plan_offset=plan)
+    verts = sess.tap_array("verts", (T, V, 3), np.float32)
+    full = oracle.render(model, edited, baked, [cam.pack()] * T, W, H, plan_offset=plan)
+    assert np.abs(verts - full.verts).max() <= 1e-5
+    base_verts = oracle.flame_forward(model, params)
+    assert np.abs(base_verts - full.verts).max() > 1e-3      # the edit really moved the face
+    ref = oracle.render(model, edited, baked, [cam.pack()] * T, W, H, verts=verts)
+    assert np.abs(img - ref.image).max() <= 1e-5
+    sess.close()

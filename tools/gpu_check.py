@@ -97,7 +97,7 @@ def main():
                                        ref.pre.tiles_touched[last:], ref.pre.mu[last:])
         bref = oracle.binning(pre_last, W, H)
         R = bref.n_pairs
-        print(f"     pairs last batch: gpu {sess.stats()['pairs_last_batch']} oracle {R}")
+        print(f"     pairs last batch: gpu {sess.dims()['pairs_last_batch']} oracle {R}")
         keys = sess.tap_array("keys", (R,), np.uint64)
         vals = sess.tap_array("vals", (R,), np.uint32)
         tiles = ((W + 15) // 16) * ((H + 15) // 16)
