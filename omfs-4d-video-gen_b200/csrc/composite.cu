@@ -9,8 +9,10 @@
 //     Gaussian's 9 compositing floats (centre, pre-scaled conic, log2 opacity, colour) from the
 //     [S,N] float4 streams (L2-resident: every Gaussian is referenced by ~3.6 tiles) and stages
 //     them in shared memory; the per-pixel loop then reads them as warp-wide broadcasts;
-//   * a warp owns an 8x4 pixel block (not a 16x2 strip): the tighter footprint makes more
-//     (Gaussian, warp) combinations skip entirely on the `e < log2(1/255)` test;
+//   * a warp owns an 8x4 pixel block (not a 16x2 strip) and culls per block: each lane tests one
+//     staged Gaussian's alpha >= 1/255 footprint (a conservative box, cull_box below) against the
+//     block, a ballot gives the ~1/3 of the tile's Gaussians that can touch it, and only those are
+//     evaluated — the kernel is FP32-issue bound, so skipped (Gaussian, warp) pairs are the win;
 //   * early termination at three levels: per pixel (T < 1e-4), per warp (all 32 pixels done: the
 //     warp stops evaluating and only helps staging), per CTA (__syncthreads_count).
 //   * the optional uint8 HWC image (the save_image quantisation) is produced by the same kernel,
@@ -34,6 +36,23 @@ struct Ex2Dev {
 
 constexpr int kChunk = 256;
 
+// Conservative footprint of one Gaussian for the per-warp cull.  A pixel at offset d from the centre
+// can only pass the `e >= log2(1/255)` test if  q(d) = -(ca dx^2 + cb dx dy + cc dy^2) <= Lq with
+// Lq = lo - log2(1/255); minimising q over dy gives dx^2 <= Lq * (-cc) / (ca*cc - cb^2/4) (and the
+// symmetric bound for dy).  The half-widths are inflated (x1.001 + 0.01 px), far more than the 1e-6
+// relative rounding of the kernel's own evaluation, so the cull never drops a contributing pixel:
+// results stay bit-identical to evaluating every (Gaussian, pixel) pair.
+__device__ __forceinline__ float4 cull_box(float gx, float gy, float ca, float cb, float cc, float lo) {
+    const float Lq = lo - kLog2Inv255;
+    const float D = ca * cc - 0.25f * cb * cb;
+    if (!(Lq >= 0.0f)) return make_float4(INFINITY, -INFINITY, INFINITY, -INFINITY);  // can never contribute
+    if (!(D > 0.0f)) return make_float4(-INFINITY, INFINITY, -INFINITY, INFINITY);    // degenerate: always test
+    const float inv = Lq / D;
+    const float bx = sqrtf(fmaxf(-cc * inv, 0.0f)) * 1.001f + 0.01f;
+    const float by = sqrtf(fmaxf(-ca * inv, 0.0f)) * 1.001f + 0.01f;
+    return make_float4(gx - bx, gx + bx, gy - by, gy + by);
+}
+
 __global__ void __launch_bounds__(256) composite_kernel(int N, int width, int height, const float4* __restrict__ P0,
                                                         const float4* __restrict__ P1,
                                                         const float4* __restrict__ P2,
@@ -41,17 +60,22 @@ __global__ void __launch_bounds__(256) composite_kernel(int N, int width, int he
                                                         const uint2* __restrict__ ranges, float bg0, float bg1,
                                                         float bg2, float* __restrict__ image,
                                                         uint8_t* __restrict__ image_u8) {
-    __shared__ float4 s_a[kChunk];  // gx gy ca cb
-    __shared__ float4 s_b[kChunk];  // cc lo r g
-    __shared__ float s_c[kChunk];   // b
+    __shared__ float4 s_a[kChunk];     // gx gy ca cb
+    __shared__ float4 s_b[kChunk];     // cc lo r g
+    __shared__ float s_c[kChunk];      // b
+    __shared__ float4 s_box[kChunk];   // xmin xmax ymin ymax of the alpha >= 1/255 footprint
 
     const int gxt = (width + kTile - 1) / kTile, gyt = (height + kTile - 1) / kTile;
     const int tile = blockIdx.x, seg = blockIdx.y;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int px = (tile % gxt) * kTile + (warp & 1) * 8 + (lane & 7);
-    const int py = (tile / gxt) * kTile + (warp >> 1) * 4 + (lane >> 3);
+    // a warp owns an 8x4 pixel block of the tile
+    const int bx0 = (tile % gxt) * kTile + (warp & 1) * 8;
+    const int by0 = (tile / gxt) * kTile + (warp >> 1) * 4;
+    const int px = bx0 + (lane & 7);
+    const int py = by0 + (lane >> 3);
     const bool inside = px < width && py < height;
     const float pxf = (float)px, pyf = (float)py;
+    const float wx0 = (float)bx0, wx1 = (float)(bx0 + 7), wy0 = (float)by0, wy1 = (float)(by0 + 3);
     const uint2 range = ranges[(size_t)seg * (gxt * gyt) + tile];
     const float4* p0 = P0 + (size_t)seg * N;
     const float4* p1 = P1 + (size_t)seg * N;
@@ -69,19 +93,37 @@ __global__ void __launch_bounds__(256) composite_kernel(int N, int width, int he
             s_a[tid] = make_float4(a.x, a.y, b.x, b.y);
             s_b[tid] = make_float4(b.z, b.w, c.x, c.y);
             s_c[tid] = c.z;
+            s_box[tid] = cull_box(a.x, a.y, b.x, b.y, b.z, b.w);
         }
         __syncthreads();
         const int n = (int)min((uint32_t)kChunk, range.y - base);
         if (__all_sync(0xffffffffu, done)) continue;  // warp-level: nothing left to shade here
-        for (int j = 0; j < n; j++) {
-            if (!done) {
-                const float4 a = s_a[j];
-                const float4 b = s_b[j];
-                const int r = ex_blend(a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, s_c[j], pxf, pyf, T, C0, C1, C2,
-                                       Ex2Dev());
-                if (r == 2) done = true;
+        // 32 Gaussians at a time: each lane tests ONE Gaussian's footprint against the warp's pixel
+        // block, the ballot is the list of Gaussians worth evaluating (still in depth order)
+        for (int sub = 0; sub < n; sub += 32) {
+            const int jj = sub + lane;
+            bool hit = false;
+            if (jj < n) {
+                const float4 bb = s_box[jj];
+                hit = (bb.y >= wx0) && (bb.x <= wx1) && (bb.w >= wy0) && (bb.z <= wy1);
             }
-            if ((j & 15) == 15 && __all_sync(0xffffffffu, done)) break;
+            uint32_t mask = __ballot_sync(0xffffffffu, hit);
+            bool any_stop = false;
+            while (mask) {
+                const int j = sub + __ffs(mask) - 1;
+                mask &= mask - 1;
+                if (!done) {
+                    const float4 a = s_a[j];
+                    const float4 b = s_b[j];
+                    const int r = ex_blend(a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, s_c[j], pxf, pyf, T, C0, C1, C2,
+                                           Ex2Dev());
+                    if (r == 2) {
+                        done = true;
+                        any_stop = true;
+                    }
+                }
+            }
+            if (__any_sync(0xffffffffu, any_stop) && __all_sync(0xffffffffu, done)) break;
         }
     }
     if (inside) {
