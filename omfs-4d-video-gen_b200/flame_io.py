@@ -1,0 +1,266 @@
+"""On-disk formats either side of the hot path.
+
+  * GaussianAvatars point-cloud PLY (`point_cloud/iteration_<N>/point_cloud.ply`) incl. the
+    per-Gaussian `binding_0` column [UPSTREAM, unverifiable offline];
+  * `flame_param.npz` / `flame_param/%05d.npz` / `canonical_flame_param.npz` records
+    (/root/reference/02_Visual_Engine/flame_fitter.py:431-441, preprocess_video.py:314-354);
+  * `transforms_{train,test,val}.json` (preprocess_video.py:372-401);
+  * the FLAME-like linear model as an .npz (the real pickle is licence-gated; a converter for
+    pickles that load without chumpy is included).
+"""
+from __future__ import annotations
+
+import json
+import os
+import pickle
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import cameras as cam_mod
+from .synthetic import Avatar, FlameModel, FrameParams
+
+_PLY_TYPES = {
+    "char": "i1", "int8": "i1", "uchar": "u1", "uint8": "u1", "short": "i2", "int16": "i2",
+    "ushort": "u2", "uint16": "u2", "int": "i4", "int32": "i4", "uint": "u4", "uint32": "u4",
+    "float": "f4", "float32": "f4", "double": "f8", "float64": "f8",
+}
+
+
+# --------------------------------------------------------------------------------------- PLY
+def read_ply(path: str) -> dict[str, np.ndarray]:
+    """Vertex element of a PLY file (binary little/big endian or ascii), scalar properties only."""
+    with open(path, "rb") as f:
+        if f.readline().strip() != b"ply":
+            raise ValueError(f"{path}: not a PLY file")
+        fmt = None
+        count = None
+        props: list[tuple[str, str]] = []
+        in_vertex = False
+        while True:
+            line = f.readline()
+            if not line:
+                raise ValueError(f"{path}: unterminated PLY header")
+            tok = line.decode("ascii", errors="replace").split()
+            if not tok:
+                continue
+            if tok[0] == "format":
+                fmt = tok[1]
+            elif tok[0] == "element":
+                in_vertex = tok[1] == "vertex"
+                if in_vertex:
+                    count = int(tok[2])
+            elif tok[0] == "property" and in_vertex:
+                if tok[1] == "list":
+                    raise ValueError(f"{path}: list properties on the vertex element are not supported")
+                props.append((tok[2], _PLY_TYPES[tok[1]]))
+            elif tok[0] == "end_header":
+                break
+        if count is None or not props:
+            raise ValueError(f"{path}: no vertex element")
+        if fmt == "ascii":
+            data = np.loadtxt(f, max_rows=count, dtype=np.float64).reshape(count, len(props))
+            return {n: data[:, i].astype(t) for i, (n, t) in enumerate(props)}
+        order = "<" if fmt == "binary_little_endian" else ">"
+        dt = np.dtype([(n, order + t) for n, t in props])
+        rec = np.frombuffer(f.read(count * dt.itemsize), dtype=dt, count=count)
+        return {n: np.ascontiguousarray(rec[n]) for n, _ in props}
+
+
+def write_ply(path: str, columns: dict[str, np.ndarray]) -> None:
+    names = list(columns)
+    n = len(columns[names[0]])
+    dt = np.dtype([(k, "<" + np.asarray(columns[k]).dtype.str[1:]) for k in names])
+    rec = np.empty(n, dtype=dt)
+    for k in names:
+        rec[k] = columns[k]
+    rev = {"f4": "float", "f8": "double", "i4": "int", "u4": "uint", "u1": "uchar", "i2": "short", "u2": "ushort", "i1": "char"}
+    os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
+    with open(path, "wb") as f:
+        f.write(b"ply\nformat binary_little_endian 1.0\n")
+        f.write(f"element vertex {n}\n".encode())
+        for k in names:
+            f.write(f"property {rev[np.asarray(columns[k]).dtype.str[1:]]} {k}\n".encode())
+        f.write(b"end_header\n")
+        f.write(rec.tobytes())
+
+
+def load_avatar_ply(path: str) -> Avatar:
+    """GaussianAvatars checkpoint PLY -> raw avatar.  f_rest is stored channel-major
+    (f_rest_{c*15+k}), as upstream's save_ply flattens features_rest.transpose(1, 2)."""
+    c = read_ply(path)
+    need = ["x", "y", "z", "opacity", "scale_0", "rot_0", "f_dc_0"]
+    for k in need:
+        if k not in c:
+            raise ValueError(f"{path}: missing PLY property '{k}'")
+    n = len(c["x"])
+    xyz = np.stack([c["x"], c["y"], c["z"]], axis=1).astype(np.float32)
+    scaling = np.stack([c[f"scale_{i}"] for i in range(3)], axis=1).astype(np.float32)
+    rot = np.stack([c[f"rot_{i}"] for i in range(4)], axis=1).astype(np.float32)
+    sh = np.zeros((n, 16, 3), np.float32)
+    sh[:, 0, :] = np.stack([c[f"f_dc_{i}"] for i in range(3)], axis=1)
+    n_rest = len([k for k in c if k.startswith("f_rest_")])
+    if n_rest % 3:
+        raise ValueError(f"{path}: f_rest count {n_rest} is not a multiple of 3")
+    per = n_rest // 3
+    if per > 15:
+        raise ValueError(f"{path}: SH degree above 3 is not supported")
+    for ch in range(3):
+        for k in range(per):
+            sh[:, 1 + k, ch] = c[f"f_rest_{ch * per + k}"]
+    if "binding_0" not in c:
+        raise ValueError(f"{path}: no binding_0 column — the avatar is not bound to a mesh (--bind_to_mesh)")
+    binding = np.asarray(c["binding_0"]).astype(np.int64)
+    if np.any(binding < 0):
+        raise ValueError(f"{path}: negative binding index")
+    return Avatar(xyz, scaling, rot, np.asarray(c["opacity"], np.float32), sh, binding.astype(np.int32))
+
+
+def save_avatar_ply(path: str, av: Avatar) -> None:
+    n = av.n
+    cols: dict[str, np.ndarray] = {}
+    for i, k in enumerate("xyz"):
+        cols[k] = av.xyz[:, i].astype(np.float32)
+    for k in ("nx", "ny", "nz"):
+        cols[k] = np.zeros(n, np.float32)
+    for i in range(3):
+        cols[f"f_dc_{i}"] = av.sh[:, 0, i].astype(np.float32)
+    for ch in range(3):
+        for k in range(15):
+            cols[f"f_rest_{ch * 15 + k}"] = av.sh[:, 1 + k, ch].astype(np.float32)
+    cols["opacity"] = av.opacity.astype(np.float32)
+    for i in range(3):
+        cols[f"scale_{i}"] = av.scaling[:, i].astype(np.float32)
+    for i in range(4):
+        cols[f"rot_{i}"] = av.rotation[:, i].astype(np.float32)
+    cols["binding_0"] = av.binding.astype(np.int32)
+    write_ply(path, cols)
+
+
+# --------------------------------------------------------------------------------------- FLAME model
+def save_flame_model(path: str, m: FlameModel) -> None:
+    np.savez(path, v_template=m.v_template, faces=m.faces, shapedirs=m.shapedirs, posedirs=m.posedirs,
+             j_regressor=m.j_regressor, lbs_weights=m.lbs_weights, parents=m.parents)
+
+
+def load_flame_model(path: str) -> FlameModel:
+    """.npz written by save_flame_model, or a FLAME-style pickle whose arrays unpickle as numpy
+    (keys v_template, shapedirs [V,3,400], posedirs [V,3,36], J_regressor, weights, f, kintree_table)."""
+    if not os.path.exists(path):
+        raise FileNotFoundError(f"FLAME model not found: {path}")
+    if path.endswith(".npz"):
+        d = np.load(path)
+        return FlameModel(*(np.ascontiguousarray(d[k]) for k in
+                            ("v_template", "faces", "shapedirs", "posedirs", "j_regressor", "lbs_weights", "parents")))
+    with open(path, "rb") as f:
+        d = pickle.load(f, encoding="latin1")
+    v = np.asarray(d["v_template"], np.float32)
+    V = v.shape[0]
+    sd = np.asarray(d["shapedirs"], np.float32)            # (V,3,400)
+    pd = np.asarray(d["posedirs"], np.float32)             # (V,3,36)
+    jr = d["J_regressor"]
+    jr = np.asarray(jr.todense() if hasattr(jr, "todense") else jr, np.float32)
+    return FlameModel(
+        v_template=v, faces=np.asarray(d["f"], np.int32),
+        shapedirs=np.ascontiguousarray(sd.reshape(V * 3, -1).T),
+        posedirs=np.ascontiguousarray(pd.reshape(V * 3, -1).T),
+        j_regressor=np.ascontiguousarray(jr), lbs_weights=np.asarray(d["weights"], np.float32))
+
+
+# --------------------------------------------------------------------------------------- parameters
+PARAM_KEYS = ("shape", "expr", "rotation", "neck_pose", "jaw_pose", "eyes_pose", "translation",
+              "static_offset", "dynamic_offset")
+
+
+def load_flame_params(path: str, n_verts: int) -> FrameParams:
+    d = dict(np.load(path, allow_pickle=True))
+    return FrameParams.from_dict(d, n_verts=n_verts)
+
+
+def save_flame_params(path: str, p: FrameParams) -> None:
+    np.savez(path, **p.as_dict())
+
+
+def stack_frame_params(records: list[FrameParams]) -> FrameParams:
+    """Per-frame records (T=1 each, as `flame_param/%05d.npz` holds) -> one batched record."""
+    first = records[0]
+    cat = lambda k: np.concatenate([getattr(r, k) for r in records], axis=0)
+    return FrameParams(first.shape, cat("expr"), cat("rotation"), cat("neck_pose"), cat("jaw_pose"),
+                       cat("eyes_pose"), cat("translation"), first.static_offset, cat("dynamic_offset"))
+
+
+@dataclass
+class DatasetFrame:
+    file_path: str
+    flame_param_path: str
+    timestep_index: int
+    camera_index: int
+    camera: cam_mod.Camera
+
+
+def load_transforms(data_dir: str, split: str = "train") -> list[DatasetFrame]:
+    path = os.path.join(data_dir, f"transforms_{split}.json")
+    if not os.path.exists(path):
+        raise FileNotFoundError(f"transforms file not found: {path}")
+    with open(path, "r") as f:
+        t = json.load(f)
+    out = []
+    for i, fr in enumerate(t.get("frames", [])):
+        w = int(fr.get("w", t.get("w", 512)))
+        h = int(fr.get("h", t.get("h", 512)))
+        fovx = float(fr.get("camera_angle_x", t.get("camera_angle_x", 0.3)))
+        cam = cam_mod.camera_from_c2w(np.array(fr["transform_matrix"], dtype=np.float64), fovx, w, h)
+        out.append(DatasetFrame(fr.get("file_path", f"images/{i:05d}_00.png"),
+                                fr.get("flame_param_path", f"flame_param/{int(fr.get('timestep_index', i)):05d}.npz"),
+                                int(fr.get("timestep_index", i)), int(fr.get("camera_index", 0)), cam))
+    return out
+
+
+def load_dataset_params(data_dir: str, frames: list[DatasetFrame], n_verts: int) -> FrameParams:
+    """One FrameParams row per dataset frame, read from each frame's own flame_param file (what the
+    reference's modified dataset points at, render_surgery.py:211-215)."""
+    cache: dict[str, FrameParams] = {}
+    recs = []
+    for fr in frames:
+        p = os.path.join(data_dir, fr.flame_param_path)
+        if p not in cache:
+            if not os.path.exists(p):
+                raise FileNotFoundError(f"FLAME parameter file not found: {p}")
+            cache[p] = load_flame_params(p, n_verts)
+        rec = cache[p]
+        if rec.n_frames == 1:
+            recs.append(rec)
+        else:  # a batched file: pick the row of this timestep
+            t = fr.timestep_index
+            recs.append(rec.slice(t, t + 1))
+    return stack_frame_params(recs)
+
+
+# --------------------------------------------------------------------------------------- synthetic dataset on disk
+def write_synthetic_dataset(data_dir: str, model_dir: str, model: FlameModel, params: FrameParams, avatar: Avatar,
+                            cam_c2w: np.ndarray, camera_angle_x: float, width: int, height: int,
+                            iteration: int = 30000) -> None:
+    """Lay a synthetic subject out exactly as the reference's pipeline leaves a real one on disk:
+    dataset dir (preprocess_video.py:246-416) + trained-model dir (render_surgery.py:271-287)."""
+    os.makedirs(os.path.join(data_dir, "images"), exist_ok=True)
+    os.makedirs(os.path.join(data_dir, "flame_param"), exist_ok=True)
+    T = params.n_frames
+    for t in range(T):
+        save_flame_params(os.path.join(data_dir, "flame_param", f"{t:05d}.npz"), params.slice(t, t + 1))
+    save_flame_params(os.path.join(data_dir, "flame_param.npz"), params)
+    z = lambda *s: np.zeros(s, np.float32)
+    canon = FrameParams(params.shape, z(1, params.expr.shape[1]), z(1, 3), z(1, 3), z(1, 3), z(1, 6), z(1, 3),
+                        params.static_offset, z(1, params.static_offset.shape[1], 3))
+    save_flame_params(os.path.join(data_dir, "canonical_flame_param.npz"), canon)
+    frames = [{"file_path": f"images/{t:05d}_00.png", "flame_param_path": f"flame_param/{t:05d}.npz",
+               "transform_matrix": np.asarray(cam_c2w).tolist(), "timestep_index": t, "camera_index": 0,
+               "camera_angle_x": camera_angle_x, "w": width, "h": height} for t in range(T)]
+    top = {"camera_angle_x": camera_angle_x, "w": width, "h": height, "frames": frames,
+           "timestep_indices": list(range(T)), "camera_indices": [0]}
+    split = max(1, T - T // 10)
+    for name, fr in (("train", frames[:split]), ("test", frames[split:]), ("val", frames[split:])):
+        with open(os.path.join(data_dir, f"transforms_{name}.json"), "w") as f:
+            json.dump({**top, "frames": fr}, f, indent=2)
+    write_ply(os.path.join(data_dir, "points3d.ply"), {"x": z(1), "y": z(1), "z": z(1)})
+    save_avatar_ply(os.path.join(model_dir, "point_cloud", f"iteration_{iteration}", "point_cloud.ply"), avatar)
+    save_flame_model(os.path.join(model_dir, "flame_model.npz"), model)

@@ -1,0 +1,350 @@
+"""Drop-in for the reference's `02_Visual_Engine/render_surgery.py`, rendering in-process on a B200.
+
+Same public names, argument meaning, on-disk contract and error behaviour as the reference module
+(file:line cited per function); the one thing that changes is the BODY of `render_with_gaussians`,
+which no longer spawns the un-vendored GaussianAvatars `render.py` (reference :289-315) but drives
+the C-ABI session in libomfs_b200.so (include/omfs_b200.h).  There is no CPU fallback: without the
+library or an sm_100 device the call raises RuntimeError("Rendering failed: ...") exactly where the
+reference raised on a non-zero child exit (:317-322).
+
+Additions (not in the reference): `render_surgery_frames`, an in-memory path that
+applies the parameter edit without rewriting T npz files and returns the frames as arrays.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+from pathlib import Path
+from typing import Any
+
+import numpy as np
+
+from . import avatar as avatar_mod
+from . import flame_io
+from .synthetic import FrameParams
+
+SCALE_FACTOR = 0.001  # mm -> FLAME units (reference :35)
+FLAME_MODEL_ENV = "OMFS_FLAME_MODEL"
+BATCH_ENV = "OMFS_RENDER_BATCH"
+
+
+# ----------------------------------------------------------------------------- R1 (reference :40-42)
+def compute_offset(input_mm: float, sensitivity: float) -> float:
+    return input_mm * sensitivity * SCALE_FACTOR
+
+
+def _get_ffmpeg_path() -> str:
+    """Bundled (imageio-ffmpeg) or system ffmpeg; FileNotFoundError otherwise (reference :45-57)."""
+    try:
+        import imageio_ffmpeg
+        return imageio_ffmpeg.get_ffmpeg_exe()
+    except ImportError:
+        pass
+    found = shutil.which("ffmpeg")
+    if found:
+        return found
+    raise FileNotFoundError("ffmpeg not found. Install via: pip install imageio-ffmpeg")
+
+
+def load_deformation_map(path: str | None) -> dict[str, Any]:
+    """Optional JSON object with translation_axis / jaw_axis / lefort_scale / bsso_scale (reference :60-71)."""
+    if not path:
+        return {}
+    p = Path(path)
+    if not p.exists():
+        raise FileNotFoundError(f"Deformation map not found: {p}")
+    with open(p, "r", encoding="utf-8") as f:
+        payload = json.load(f)
+    if not isinstance(payload, dict):
+        raise ValueError("Deformation map JSON must contain an object at the top level.")
+    return payload
+
+
+def choose_rig_mode(requested_mode: str, canonical_head_asset: str | None) -> tuple[str, str]:
+    """Effective rig mode and the reason (reference :74-85)."""
+    if requested_mode == "flame_only":
+        return "flame_only", "explicitly requested"
+    if canonical_head_asset and Path(canonical_head_asset).exists():
+        return "hybrid_full_head", "canonical head asset found"
+    return "flame_only", "hybrid requested but canonical head asset missing"
+
+
+# ----------------------------------------------------------------------------- R2 (reference :88-141)
+def _edit_record(data: dict, lefort_offset: float, bsso_offset: float, deformation_map: dict | None) -> dict:
+    """The reference's two scalar edits on an in-memory record: translation[..., axis] += lefort and
+    jaw_pose[..., axis] += bsso, each times its scale; every other key passes through untouched."""
+    dm = deformation_map or {}
+    axis_t = int(dm.get("translation_axis", 1))
+    axis_j = int(dm.get("jaw_axis", 0))
+    add_t = lefort_offset * float(dm.get("lefort_scale", 1.0))
+    add_j = bsso_offset * float(dm.get("bsso_scale", 1.0))
+    out = dict(data)
+    for key, axis, add in (("translation", axis_t, add_t), ("jaw_pose", axis_j, add_j)):
+        if key in out:
+            arr = np.array(out[key], copy=True)
+            arr[..., axis] += add  # python-float addend: numpy keeps the array's float32
+            out[key] = arr
+    return out
+
+
+def modify_flame_params(source_npz: str, output_npz: str, lefort_offset: float, bsso_offset: float,
+                        deformation_map: dict[str, Any] | None = None) -> None:
+    data = dict(np.load(source_npz, allow_pickle=True))
+    np.savez(output_npz, **_edit_record(data, lefort_offset, bsso_offset, deformation_map))
+
+
+# ----------------------------------------------------------------------------- R3 (reference :144-242)
+def create_modified_dataset(data_dir: str, lefort_offset: float, bsso_offset: float,
+                            deformation_map: dict[str, Any] | None = None) -> str:
+    """Temporary copy of the dataset with edited FLAME parameters; the caller deletes it."""
+    temp_dir = tempfile.mkdtemp(prefix="surgical_render_")
+    src_images = os.path.join(data_dir, "images")
+    if os.path.isdir(src_images):
+        dst_images = os.path.join(temp_dir, "images")
+        try:
+            os.symlink(os.path.abspath(src_images), dst_images, target_is_directory=True)
+        except (OSError, NotImplementedError):
+            shutil.copytree(src_images, dst_images)
+    per_frame = os.path.join(data_dir, "flame_param")
+    if os.path.isdir(per_frame):
+        os.makedirs(os.path.join(temp_dir, "flame_param"), exist_ok=True)
+        for name in sorted(os.listdir(per_frame)):
+            if name.endswith(".npz"):
+                modify_flame_params(os.path.join(per_frame, name), os.path.join(temp_dir, "flame_param", name),
+                                    lefort_offset, bsso_offset, deformation_map=deformation_map)
+    batched = os.path.join(data_dir, "flame_param.npz")
+    if os.path.exists(batched):
+        modify_flame_params(batched, os.path.join(temp_dir, "flame_param.npz"), lefort_offset, bsso_offset,
+                            deformation_map=deformation_map)
+    for name in ("points3d.ply", "canonical_flame_param.npz"):
+        src = os.path.join(data_dir, name)
+        if os.path.exists(src):
+            shutil.copy2(src, os.path.join(temp_dir, name))
+    for name in ("transforms_train.json", "transforms_test.json", "transforms_val.json"):
+        src = os.path.join(data_dir, name)
+        if not os.path.exists(src):
+            continue
+        with open(src, "r") as f:
+            transforms = json.load(f)
+        for frame in transforms.get("frames", []):
+            rel = f"flame_param/{int(frame.get('timestep_index', 0)):05d}.npz"
+            if os.path.exists(os.path.join(temp_dir, rel)):
+                frame["flame_param_path"] = rel
+        with open(os.path.join(temp_dir, name), "w") as f:
+            json.dump(transforms, f, indent=2)
+    print(f"[render_surgery] Modified dataset at: {temp_dir}")
+    return temp_dir
+
+
+# ----------------------------------------------------------------------------- R4 (reference :245-362)
+def _pick_iteration(model_path: str, iteration: int) -> int:
+    pc = os.path.join(model_path, "point_cloud")
+    found = []
+    if os.path.isdir(pc):
+        for d in os.listdir(pc):
+            if d.startswith("iteration_"):
+                try:
+                    found.append(int(d.split("_")[1]))
+                except (ValueError, IndexError):
+                    pass
+    if iteration > 0:
+        return iteration
+    if not found:
+        raise FileNotFoundError(f"No point_cloud/iteration_* checkpoint under {model_path}")
+    return max(found)
+
+
+def _find_flame_model(model_path: str) -> str:
+    for cand in (os.environ.get(FLAME_MODEL_ENV), os.path.join(model_path, "flame_model.npz"),
+                 os.path.join(model_path, "flame_model.pkl")):
+        if cand and os.path.exists(cand):
+            return cand
+    raise FileNotFoundError(f"FLAME model not found: set ${FLAME_MODEL_ENV} or put flame_model.npz in {model_path}")
+
+
+def _write_png(path: str, rgb_u8: np.ndarray) -> None:
+    from PIL import Image
+    Image.fromarray(rgb_u8, mode="RGB").save(path, compress_level=1)
+
+
+def render_with_gaussians(model_path: str, data_dir: str, iteration: int = -1,
+                          clear_old_renders: bool = True) -> str:
+    """Render every train-split frame of `data_dir` with the avatar in `model_path`.
+
+    Writes `model_path/train/ours_<iter>/renders/%05d.png` (the layout the reference's caller and
+    validation report expect, :324-362) and returns that directory."""
+    train_dir = os.path.join(model_path, "train")
+    if clear_old_renders and os.path.isdir(train_dir):  # stale frames must never be picked up (:260-267)
+        for d in os.listdir(train_dir):
+            renders = os.path.join(train_dir, d, "renders")
+            if os.path.isdir(renders):
+                print(f"[render_surgery] Clearing old renders: {renders}")
+                shutil.rmtree(renders)
+    it = _pick_iteration(model_path, iteration)
+    ply = os.path.join(model_path, "point_cloud", f"iteration_{it}", "point_cloud.ply")
+    if not os.path.exists(ply):
+        raise FileNotFoundError(f"Checkpoint not found: {ply}")
+    model = flame_io.load_flame_model(_find_flame_model(model_path))
+    frames = flame_io.load_transforms(data_dir, "train")
+    if not frames:
+        raise FileNotFoundError("No rendered frames found after GaussianAvatars rendering.")
+    params = flame_io.load_dataset_params(data_dir, frames, model.n_verts)
+    av = flame_io.load_avatar_ply(ply)
+    if int(av.binding.max()) >= model.n_faces:
+        raise ValueError("avatar binding index exceeds the FLAME face count")
+    print(f"[render_surgery] Rendering {len(frames)} frames, {av.n} Gaussians, iteration {it} (in-process, B200)")
+    try:
+        images = _render_frames(model, params, av, [f.camera for f in frames])
+    except Exception as e:  # the reference surfaces renderer failures as RuntimeError (:317-322)
+        raise RuntimeError(f"Rendering failed:\n{str(e)[-2000:]}") from e
+    renders_dir = os.path.join(train_dir, f"ours_{it}", "renders")
+    os.makedirs(renders_dir, exist_ok=True)
+    for i, img in enumerate(images):
+        _write_png(os.path.join(renders_dir, f"{i:05d}.png"), img)
+    print(f"[render_surgery] Frames rendered to: {renders_dir}")
+    return renders_dir
+
+
+def _render_frames(model, params: FrameParams, av, cams, plan_offset=None, device: int | None = None) -> np.ndarray:
+    """uint8 [T,H,W,3].  Frames may have different cameras (one per frame) but one image size."""
+    from . import runtime
+    sizes = {(c.width, c.height) for c in cams}
+    if len(sizes) != 1:
+        raise ValueError(f"all frames must share one image size, got {sorted(sizes)}")
+    (W, H), = sizes
+    T = params.n_frames
+    baked = avatar_mod.bake(av)
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0"))
+    batch = int(os.environ.get(BATCH_ENV, "32"))
+    out = np.empty((T, H, W, 3), np.uint8)
+    with runtime.Session(model, baked, W, H, max_batch=batch, device=device,
+                         n_expr=params.expr.shape[1]) as sess:
+        sess.set_subject(params.shape, params.static_offset, plan_offset)
+        # runs of consecutive frames with the same camera are one call
+        keys = [c.pack().tobytes() for c in cams]
+        t0 = 0
+        while t0 < T:
+            t1 = t0 + 1
+            while t1 < T and keys[t1] == keys[t0]:
+                t1 += 1
+            u8, _ = sess.render_host(params.slice(t0, t1), [cams[t0]], want_u8=True)
+            out[t0:t1] = u8
+            t0 = t1
+    return out
+
+
+def render_surgery_frames(model, params: FrameParams, av, cams, lefort_mm: float, bsso_mm: float,
+                          sensitivity: float = 1.0, deformation_map: dict | None = None, plan_offset=None,
+                          device: int | None = None) -> np.ndarray:
+    """In-memory variant of main(): the reference's parameter edit (R1+R2) then the render, with no
+    temporary dataset.  Returns uint8 frames [T,H,W,3]."""
+    rec = _edit_record(params.as_dict(), compute_offset(lefort_mm, sensitivity), compute_offset(bsso_mm, sensitivity),
+                       deformation_map)
+    edited = FrameParams.from_dict(rec, n_verts=params.static_offset.shape[1])
+    return _render_frames(model, edited, av, cams, plan_offset=plan_offset, device=device)
+
+
+# ----------------------------------------------------------------------------- reference :365-409
+def export_deterministic_frames(frames_dir: str, output_dir: str, index_file: str | None = None,
+                                max_frames: int = 24) -> str:
+    os.makedirs(output_dir, exist_ok=True)
+    frames = sorted(f for f in os.listdir(frames_dir) if f.endswith(".png"))
+    if not frames:
+        raise FileNotFoundError(f"No PNG frames in {frames_dir}")
+    if index_file:
+        with open(index_file, "r", encoding="utf-8") as f:
+            payload = json.load(f)
+        indices = payload.get("indices", payload) if isinstance(payload, dict) else payload
+        if not isinstance(indices, list) or not all(isinstance(i, int) for i in indices):
+            raise ValueError("index_file must contain a JSON list of frame indices or {'indices': [...]} ")
+        selected = [i for i in indices if 0 <= i < len(frames)]
+    else:
+        count = max(1, min(max_frames, len(frames)))
+        if count == 1:
+            selected = [0]
+        else:
+            selected = sorted({int(round(i * (len(frames) - 1) / (count - 1))) for i in range(count)})
+    manifest = {"source_frames_dir": frames_dir, "selected_indices": selected, "exports": []}
+    for i in selected:
+        dst_name = f"idx_{i:05d}.png"
+        shutil.copy2(os.path.join(frames_dir, frames[i]), os.path.join(output_dir, dst_name))
+        manifest["exports"].append({"index": i, "source": frames[i], "exported": dst_name})
+    with open(os.path.join(output_dir, "deterministic_indices_manifest.json"), "w", encoding="utf-8") as f:
+        json.dump(manifest, f, indent=2)
+    print(f"[render_surgery] Deterministic frame export written to: {output_dir}")
+    return output_dir
+
+
+# ----------------------------------------------------------------------------- reference :412-449
+def stitch_video(frames_dir: str, output_path: str, fps: int = 30):
+    ffmpeg_bin = _get_ffmpeg_path()
+    out_dir = os.path.dirname(output_path)
+    if out_dir:
+        os.makedirs(out_dir, exist_ok=True)
+    frames = sorted(f for f in os.listdir(frames_dir) if f.endswith(".png"))
+    if not frames:
+        raise FileNotFoundError(f"No PNG frames in {frames_dir}")
+    seq = tempfile.mkdtemp(prefix="stitch_")
+    try:
+        for i, name in enumerate(frames):
+            shutil.copy2(os.path.join(frames_dir, name), os.path.join(seq, f"frame_{i:05d}.png"))
+        cmd = [ffmpeg_bin, "-y", "-framerate", str(fps), "-i", os.path.join(seq, "frame_%05d.png"),
+               "-c:v", "libx264", "-pix_fmt", "yuv420p", "-preset", "medium", "-crf", "18", output_path]
+        result = subprocess.run(cmd, capture_output=True, text=True)
+    finally:
+        shutil.rmtree(seq, ignore_errors=True)
+    if result.returncode != 0:
+        raise RuntimeError(f"ffmpeg failed:\n{result.stderr}")
+    print(f"[render_surgery] Video saved to {output_path}")
+
+
+# ----------------------------------------------------------------------------- reference :452-541
+def build_parser() -> argparse.ArgumentParser:
+    p = argparse.ArgumentParser(description="Render post-surgical prediction video.")
+    p.add_argument("--lefort_mm", type=float, required=True)
+    p.add_argument("--bsso_mm", type=float, required=True)
+    p.add_argument("--sensitivity", type=float, default=1.0)
+    p.add_argument("--model_path", type=str, default="02_Visual_Engine/output/model")
+    p.add_argument("--data_dir", type=str, default="02_Visual_Engine/data")
+    p.add_argument("--output", type=str, default="final_prediction.mp4")
+    p.add_argument("--fps", type=int, default=30)
+    p.add_argument("--iteration", type=int, default=-1, help="Explicit model iteration to render.")
+    p.add_argument("--rig_mode", type=str, default="flame_only", choices=("flame_only", "hybrid_full_head"))
+    p.add_argument("--canonical_head_asset", type=str, default="")
+    p.add_argument("--deformation_map", type=str, default="")
+    p.add_argument("--export_frames_dir", type=str, default="")
+    p.add_argument("--deterministic_indices", type=str, default="")
+    p.add_argument("--deterministic_max_frames", type=int, default=24)
+    return p
+
+
+def main(argv: list[str] | None = None):
+    args = build_parser().parse_args(argv)
+    lefort_offset = compute_offset(args.lefort_mm, args.sensitivity)
+    bsso_offset = compute_offset(args.bsso_mm, args.sensitivity)
+    mode, reason = choose_rig_mode(args.rig_mode, args.canonical_head_asset)
+    deformation_map = load_deformation_map(args.deformation_map if mode == "hybrid_full_head" else None)
+    print(f"[render_surgery] Le Fort: {args.lefort_mm} mm -> offset {lefort_offset:.6f}")
+    print(f"[render_surgery] BSSO:    {args.bsso_mm} mm -> offset {bsso_offset:.6f}")
+    print(f"[render_surgery] Rig mode: {mode} ({reason})")
+    modified_dir = create_modified_dataset(args.data_dir, lefort_offset, bsso_offset, deformation_map=deformation_map)
+    try:
+        frames_dir = render_with_gaussians(args.model_path, modified_dir, iteration=args.iteration)
+        if args.export_frames_dir:
+            export_deterministic_frames(frames_dir, args.export_frames_dir,
+                                        index_file=args.deterministic_indices or None,
+                                        max_frames=args.deterministic_max_frames)
+        stitch_video(frames_dir, args.output, fps=args.fps)
+    finally:
+        shutil.rmtree(modified_dir, ignore_errors=True)
+    print("[render_surgery] Done.")
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,119 @@
+"""CPU-side checks of the exact domain (no GPU needed):
+
+  * the PRODUCT's per-element math (csrc/exact_math.cuh, the source the CUDA kernels compile),
+    built for the host by tests/emu with -ffp-contract=off, is bit-identical to the independently
+    written C oracle on face frames, bind+preprocess and compositing;
+  * the oracle's tiled pipeline equals a brute-force numpy renderer that knows nothing about tiles,
+    keys or sorting (every pixel walks ALL Gaussians in depth order) — a check of the oracle itself.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def emu():
+    subprocess.check_call(["make", "-s", "-C", os.path.join(HERE, "emu")])
+    L = ctypes.CDLL(os.path.join(HERE, "emu", "libemu.so"))
+    f = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
+    u32 = np.ctypeslib.ndpointer(dtype=np.uint32, flags="C_CONTIGUOUS")
+    i32 = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+    L.emu_face_frames.argtypes = [ctypes.c_int] * 3 + [f, i32, f]
+    L.emu_bind_preprocess.argtypes = [ctypes.c_int] * 4 + [f] * 9 + [u32]
+    L.emu_composite.argtypes = [ctypes.c_int] * 4 + [f, f, f, u32, u32, f, f]
+    return L
+
+
+def bits(a):
+    return np.ascontiguousarray(a).view(np.uint32)
+
+
+def test_product_math_is_bit_identical_to_oracle(emu, small_scene):
+    model, params, av, baked, cam = small_scene
+    W, H = cam.width, cam.height
+    T, N = params.n_frames, baked["n"]
+    res = oracle.render(model, params, baked, [cam.pack()] * T, W, H)
+    ff = np.zeros_like(res.ff)
+    emu.emu_face_frames(T, model.n_verts, model.n_faces, res.verts, model.faces, ff)
+    assert np.array_equal(bits(ff), bits(res.ff))
+    for s in range(T):
+        P = [np.zeros((N, 4), np.float32) for _ in range(3)]
+        tt = np.zeros(N, np.uint32)
+        emu.emu_bind_preprocess(N, model.n_faces, W, H, np.ascontiguousarray(ff[s]), baked["xyzb"], baked["scale_lo"],
+                                baked["rot"], baked["sh"], cam.pack(), P[0], P[1], P[2], tt)
+        assert np.array_equal(bits(P[0]), bits(res.pre.P0[s]))
+        assert np.array_equal(bits(P[1]), bits(res.pre.P1[s]))
+        assert np.array_equal(bits(P[2]), bits(res.pre.P2[s]))
+        assert np.array_equal(tt, res.pre.tiles_touched[s])
+    img = np.zeros_like(res.image)
+    emu.emu_composite(T, N, W, H, res.pre.P0.reshape(-1), res.pre.P1.reshape(-1), res.pre.P2.reshape(-1),
+                      res.binned.sorted_values, res.binned.ranges.reshape(-1), np.ones(3, np.float32), img.reshape(-1))
+    assert np.array_equal(bits(img), bits(res.image))
+
+
+def test_oracle_binning_invariants(small_scene):
+    model, params, av, baked, cam = small_scene
+    W, H = cam.width, cam.height
+    T, N = params.n_frames, baked["n"]
+    res = oracle.render(model, params, baked, [cam.pack()] * T, W, H)
+    b = res.binned
+    assert b.n_pairs == int(res.pre.tiles_touched.sum()) > 0
+    order = np.argsort(b.keys, kind="stable")           # numpy's stable sort = the definition
+    assert np.array_equal(b.sorted_keys, b.keys[order])
+    assert np.array_equal(b.sorted_values, b.values[order])
+    tiles = ((W + 15) // 16) * ((H + 15) // 16)
+    assert b.sort_bits == 32 + int(np.ceil(np.log2(T * tiles)))
+    lens = b.ranges[:, 1].astype(np.int64) - b.ranges[:, 0]
+    assert int(lens.sum()) == b.n_pairs
+    assert np.array_equal(np.repeat(np.arange(T * tiles), lens), (b.sorted_keys >> np.uint64(32)).astype(np.int64))
+    assert np.array_equal(res.pre.radii > 0, res.pre.tiles_touched > 0)
+
+
+def test_oracle_matches_untiled_brute_force():
+    import omfs_b200  # noqa: F401
+    from omfs_b200 import avatar, synthetic
+    W, H = 48, 32
+    model, params, av, cam = synthetic.make_scene(n_gauss=300, n_frames=1, width=W, height=H, n_verts=162)
+    baked = avatar.bake(av)
+    res = oracle.render(model, params, baked, [cam.pack()], W, H)
+    P0, P1, P2 = res.pre.P0[0].astype(np.float64), res.pre.P1[0].astype(np.float64), res.pre.P2[0].astype(np.float64)
+    radii = res.pre.radii[0]
+    vis = np.where(radii > 0)[0]
+    vis = vis[np.argsort(res.pre.P0[0][vis, 2], kind="stable")]     # depth order, ties by index
+    img = np.ones((3, H, W))
+    thr = np.log2(1.0 / 255.0)
+    gx, gy = (W + 15) // 16, (H + 15) // 16
+    for y in range(H):
+        for x in range(W):
+            T_, C = 1.0, np.zeros(3)
+            for g in vis:
+                # the tile rectangle is part of the published algorithm: a Gaussian is only seen by
+                # pixels of the tiles its 3-sigma square touches
+                r = float(radii[g])
+                minx, maxx = int((P0[g, 0] - r) / 16), int((P0[g, 0] + r + 15) / 16)
+                miny, maxy = int((P0[g, 1] - r) / 16), int((P0[g, 1] + r + 15) / 16)
+                minx, maxx = min(gx, max(0, minx)), min(gx, max(0, maxx))
+                miny, maxy = min(gy, max(0, miny)), min(gy, max(0, maxy))
+                if not (minx <= x // 16 < maxx and miny <= y // 16 < maxy):
+                    continue
+                dx, dy = P0[g, 0] - x, P0[g, 1] - y
+                pw = P1[g, 0] * dx * dx + P1[g, 1] * dx * dy + P1[g, 2] * dy * dy
+                if pw > 0:
+                    continue
+                e = pw + P1[g, 3]
+                if e < thr:
+                    continue
+                a = min(0.99, 2.0 ** e)
+                if T_ * (1 - a) < 1e-4:
+                    break
+                C += P2[g, :3] * a * T_
+                T_ *= 1 - a
+            img[:, y, x] = C + T_ * 1.0
+    assert np.abs(img - res.image[0]).max() < 1e-5

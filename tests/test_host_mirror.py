@@ -1,0 +1,176 @@
+"""The host-side mirror of the reference interface (render_surgery.py / surgical_sim.py names,
+arguments, errors, on-disk formats) — CPU only.  The cases follow the reference's own unit tests
+(/root/reference/test/test_render_surgery.py) so they read the same way."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import omfs_b200  # noqa: F401
+from omfs_b200 import flame_io, render_surgery as rs, surgical_sim as ss, synthetic, validation_reporting
+
+
+def test_compute_offset_cases():
+    assert rs.compute_offset(0.0, 1.0) == 0.0
+    assert rs.compute_offset(5.0, 1.0) == pytest.approx(5.0 * 1.0 * rs.SCALE_FACTOR)
+    assert rs.compute_offset(-3.0, 1.0) == pytest.approx(-3.0 * rs.SCALE_FACTOR)
+    assert rs.compute_offset(5.0, 2.5) == pytest.approx(5.0 * 2.5 * rs.SCALE_FACTOR)
+    assert rs.compute_offset(10.0, 0.0) == 0.0
+
+
+def test_compute_offset_and_modify_match_reference_goldens(golden_dir, tmp_path):
+    g = np.load(os.path.join(golden_dir, "render_surgery_golden.npz"))
+    for (mm, s), want in zip(g["offset_cases"], g["offset_values"]):
+        assert rs.compute_offset(float(mm), float(s)) == float(want)
+    maps = json.loads(str(g["mod_maps"]))
+    for kind in ("batched", "single"):
+        src = tmp_path / f"{kind}.npz"
+        np.savez(src, **{k: g[f"mod_{kind}_in_{k}"] for k in ("jaw_pose", "translation", "expr", "shape")})
+        for i, ((lo, bo), dm) in enumerate(zip(g["mod_args"], maps)):
+            dst = tmp_path / f"{kind}_{i}.npz"
+            rs.modify_flame_params(str(src), str(dst), float(lo), float(bo), deformation_map=dm)
+            got = np.load(dst)
+            for k in ("jaw_pose", "translation", "expr", "shape"):
+                want = g[f"mod_{kind}_{i}_{k}"]
+                assert np.array_equal(got[k].view(np.uint32), want.view(np.uint32)), (kind, i, k)
+        again = np.load(src)
+        assert np.array_equal(again["translation"], g[f"mod_{kind}_in_translation"])   # source untouched
+
+
+def test_modify_flame_params_reference_cases(tmp_path):
+    src, dst = tmp_path / "source.npz", tmp_path / "modified.npz"
+    np.savez(src, jaw_pose=np.zeros((10, 3), np.float32), translation=np.zeros((10, 3), np.float32),
+             expr=np.zeros((10, 100), np.float32), shape=np.zeros(300, np.float32))
+    rs.modify_flame_params(str(src), str(dst), 0.005, 0.0)
+    assert float(np.load(dst)["translation"][0, 1]) == pytest.approx(0.005, abs=1e-5)
+    rs.modify_flame_params(str(src), str(dst), 0.0, 0.003)
+    assert float(np.load(dst)["jaw_pose"][0, 0]) == pytest.approx(0.003, abs=1e-5)
+    rs.modify_flame_params(str(src), str(dst), 0.01, 0.02)
+    assert float(np.load(src)["translation"][0, 1]) == 0.0 and float(np.load(src)["jaw_pose"][0, 0]) == 0.0
+    dm = {"translation_axis": 2, "jaw_axis": 1, "lefort_scale": 2.0, "bsso_scale": 0.5}
+    rs.modify_flame_params(str(src), str(dst), 0.01, 0.02, deformation_map=dm)
+    d = np.load(dst)
+    assert float(d["translation"][0, 2]) == pytest.approx(0.02, abs=1e-5)
+    assert float(d["jaw_pose"][0, 1]) == pytest.approx(0.01, abs=1e-5)
+
+
+def test_rig_mode_and_deformation_map(tmp_path):
+    mode, reason = rs.choose_rig_mode("hybrid_full_head", "")
+    assert mode == "flame_only" and "missing" in reason
+    asset = tmp_path / "asset.npz"
+    np.savez(asset, version=np.array([1]))
+    assert rs.choose_rig_mode("hybrid_full_head", str(asset))[0] == "hybrid_full_head"
+    assert rs.choose_rig_mode("flame_only", str(asset)) == ("flame_only", "explicitly requested")
+    assert rs.load_deformation_map(None) == {}
+    with pytest.raises(FileNotFoundError):
+        rs.load_deformation_map(str(tmp_path / "nope.json"))
+    bad = tmp_path / "bad.json"
+    bad.write_text("[1, 2]")
+    with pytest.raises(ValueError):
+        rs.load_deformation_map(str(bad))
+
+
+def test_deterministic_frame_export(tmp_path):
+    from PIL import Image
+    frames_dir, out_dir = tmp_path / "renders", tmp_path / "out"
+    frames_dir.mkdir()
+    for i in range(6):
+        Image.fromarray(np.full((8, 8, 3), i * 20, dtype=np.uint8)).save(frames_dir / f"{i:05d}.png")
+    idx = tmp_path / "idx.json"
+    idx.write_text(json.dumps({"indices": [0, 3, 5]}))
+    rs.export_deterministic_frames(str(frames_dir), str(out_dir), str(idx))
+    manifest = json.loads((out_dir / "deterministic_indices_manifest.json").read_text())
+    assert manifest["selected_indices"] == [0, 3, 5]
+    for i in (0, 3, 5):
+        assert (out_dir / f"idx_{i:05d}.png").exists()
+    out2 = tmp_path / "out2"
+    rs.export_deterministic_frames(str(frames_dir), str(out2), None, max_frames=3)
+    assert json.loads((out2 / "deterministic_indices_manifest.json").read_text())["selected_indices"] == [0, 2, 5]
+    empty = tmp_path / "empty"
+    empty.mkdir()
+    with pytest.raises(FileNotFoundError):
+        rs.export_deterministic_frames(str(empty), str(tmp_path / "o3"))
+    bad = tmp_path / "bad_idx.json"
+    bad.write_text(json.dumps({"indices": ["a"]}))
+    with pytest.raises(ValueError):
+        rs.export_deterministic_frames(str(frames_dir), str(tmp_path / "o4"), str(bad))
+
+
+def test_create_modified_dataset_round_trip(tmp_path):
+    model = synthetic.make_flame_model(n_verts=162)
+    params = synthetic.make_frame_params(4, n_verts=162)
+    av = synthetic.make_avatar(50, model.n_faces)
+    cam_c2w = np.eye(4)
+    cam_c2w[2, 3] = 1.0
+    data, mdl = tmp_path / "data", tmp_path / "model"
+    flame_io.write_synthetic_dataset(str(data), str(mdl), model, params, av, cam_c2w, 0.3, 64, 48, iteration=1234)
+    tmp = rs.create_modified_dataset(str(data), rs.compute_offset(5.0, 1.0), rs.compute_offset(2.0, 1.0))
+    try:
+        for t in range(4):
+            a = np.load(os.path.join(tmp, "flame_param", f"{t:05d}.npz"))
+            np.testing.assert_allclose(a["translation"][0, 1], params.translation[t, 1] + np.float32(0.005), atol=1e-7)
+            np.testing.assert_allclose(a["jaw_pose"][0, 0], params.jaw_pose[t, 0] + np.float32(0.002), atol=1e-7)
+            assert np.array_equal(a["expr"], params.expr[t:t + 1])
+        tr = json.load(open(os.path.join(tmp, "transforms_train.json")))
+        assert all(f["flame_param_path"] == f"flame_param/{f['timestep_index']:05d}.npz" for f in tr["frames"])
+        assert os.path.exists(os.path.join(tmp, "canonical_flame_param.npz"))
+        frames = flame_io.load_transforms(tmp, "train")
+        got = flame_io.load_dataset_params(tmp, frames, 162)
+        assert got.n_frames == len(frames) == 4 - 4 // 10
+    finally:
+        import shutil
+        shutil.rmtree(tmp)
+    # PLY round trip incl. binding indices (bit-exact) and SH layout
+    av2 = flame_io.load_avatar_ply(os.path.join(mdl, "point_cloud", "iteration_1234", "point_cloud.ply"))
+    assert np.array_equal(av2.binding, av.binding)
+    for k in ("xyz", "scaling", "rotation", "opacity", "sh"):
+        assert np.array_equal(getattr(av2, k), getattr(av, k)), k
+    m2 = flame_io.load_flame_model(os.path.join(mdl, "flame_model.npz"))
+    assert np.array_equal(m2.shapedirs, model.shapedirs) and np.array_equal(m2.faces, model.faces)
+
+
+def test_render_with_gaussians_errors(tmp_path):
+    with pytest.raises(FileNotFoundError):
+        rs.render_with_gaussians(str(tmp_path / "model"), str(tmp_path / "data"))
+    # no PNG frames (or no ffmpeg at all): FileNotFoundError either way, as in the reference
+    with pytest.raises(FileNotFoundError):
+        rs.stitch_video(str(tmp_path), str(tmp_path / "o.mp4"))
+
+
+def test_surgical_sim_host_pieces(golden_dir):
+    g = np.load(os.path.join(golden_dir, "surgical_sim_golden.npz"))
+    for bi, base in enumerate([(0, 0, 1), (1, 0, 0)]):
+        for ai, (p, y) in enumerate(g["angles"]):
+            assert np.array_equal(np.array(ss._angle_to_normal(base, float(p), float(y))), g["normals"][bi, ai])
+    for d_in, want in zip(g["dirs_in"], g["dirs"]):
+        assert np.array_equal(ss._normalise_direction(tuple(d_in)), want)
+    with pytest.raises(ValueError):
+        ss._normalise_direction((0.0, 0.0, 0.0))
+    cutter = ss.SurgicalCutter(ss.PointMesh(g["maxilla"]), ss.PointMesh(g["mandible"]))
+    with pytest.raises(RuntimeError):
+        cutter.move_segments(maxilla_mm=5.0)
+    keys = cutter.preview_planes(lefort_z=20, bsso_l_x=-15, bsso_r_x=15)
+    for k in ("maxilla", "mandible", "combined", "lefort", "bsso_l", "bsso_r"):
+        assert k in keys
+    from oracle import reference_rows as rr
+    assert np.allclose(ss._rotation(5.0, -3.0, 2.0), rr.rotation_xzy(5.0, -3.0, 2.0), atol=0)
+
+
+def test_psnr_mirror(golden_dir):
+    g = np.load(os.path.join(golden_dir, "psnr_golden.npz"))
+    assert validation_reporting.psnr(g["a"], g["b"]) == float(g["psnr_ab"])
+    assert validation_reporting.psnr(g["a"], g["a"]) == 99.0
+
+
+def test_avatar_bake_is_the_upstream_activation():
+    from omfs_b200 import avatar
+    av = synthetic.make_avatar(500, 100, seed=3)
+    b = avatar.bake(av)
+    np.testing.assert_allclose(b["scale_lo"][:, :3], np.exp(av.scaling.astype(np.float64)), rtol=1e-7)
+    sig = 1.0 / (1.0 + np.exp(-av.opacity.astype(np.float64)))
+    np.testing.assert_allclose(np.exp2(b["scale_lo"][:, 3].astype(np.float64)), sig, rtol=1e-6)
+    np.testing.assert_allclose(np.linalg.norm(b["rot"], axis=1), 1.0, atol=1e-6)
+    assert np.array_equal(avatar.binding_of(b), av.binding)
+    flat = av.sh.reshape(500, 48)
+    assert np.array_equal(b["sh"][5, :, 2], flat[:, 22])      # flat index 22 -> plane 5, lane 2
