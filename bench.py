@@ -117,10 +117,11 @@ class ClockSampler:
 def cpu_oracle_fps(model, params, baked, cam, n_sample):
     """Frames/s of the oracle port on the host cores for the first n_sample frames."""
     import oracle
-    sub = params.slice(0, n_sample)
-    cams = [cam.pack()] * n_sample
+    chunk = 20  # frames per oracle call: bounds the host memory of the pair lists
     t0 = time.perf_counter()
-    oracle.render(model, sub, baked, cams, WIDTH, HEIGHT)
+    for lo in range(0, n_sample, chunk):
+        hi = min(n_sample, lo + chunk)
+        oracle.render(model, params.slice(lo, hi), baked, [cam.pack()] * (hi - lo), WIDTH, HEIGHT)
     dt = time.perf_counter() - t0
     return n_sample / dt, dt, oracle.num_threads()
 
@@ -133,8 +134,8 @@ def run_reference(args, rank):
     import oracle
     n_sample = args.ref_frames
     model, params, baked, cam = make_inputs(max(n_sample, 1))
-    for _ in range(args.warmup):
-        cpu_oracle_fps(model, params, baked, cam, min(2, n_sample))
+    for _ in range(min(args.warmup, 1)):
+        cpu_oracle_fps(model, params, baked, cam, min(4, n_sample))
     t0 = time.perf_counter()
     for _ in range(args.steps):
         cpu_oracle_fps(model, params, baked, cam, n_sample)
@@ -164,8 +165,8 @@ def main():
     ap.add_argument("--frames", type=int, default=N_FRAMES)
     ap.add_argument("--batch", type=int, default=60, help="segments (frames) per launch group")
     ap.add_argument("--gemm", type=int, default=0, help="0 tensor-core blendshape GEMM, 1 CUDA-core")
-    ap.add_argument("--cpu-frames", type=int, default=24, help="frames of the cpu_baseline sample")
-    ap.add_argument("--ref-frames", type=int, default=12, help="frames per step of --impl reference")
+    ap.add_argument("--cpu-frames", type=int, default=300, help="frames of the cpu_baseline sample")
+    ap.add_argument("--ref-frames", type=int, default=60, help="frames per step of --impl reference")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
 
@@ -210,7 +211,9 @@ def main():
     d_ptrs["cams"] = d_cam.data_ptr()
     frames_u8 = torch.empty((T, HEIGHT, WIDTH, 3), dtype=torch.uint8, device=dev)
     gathered = torch.empty((world, T, HEIGHT, WIDTH, 3), dtype=torch.uint8, device=dev) if (world > 1 and rank == 0) else None
-    stream = torch.cuda.current_stream()
+    # a dedicated stream: the kernels, the NCCL gather and the timing events all go through it
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
 
     def step_device():
         sess.render_device(d_ptrs, T, 1, d_out_u8=frames_u8.data_ptr(), stream=stream.cuda_stream)
@@ -303,17 +306,22 @@ def main():
         hbm, tflops, peak_kind = peaks()
         R = pairs_per_frame
         d = sess.dims()
-        passes = (runtime.load_library().omfs_binning_sort_bits(args.batch, WIDTH, HEIGHT) + 7) // 8
-        # algorithmic bytes per FRAME for each stage
+        sort_bits = runtime.load_library().omfs_binning_sort_bits(args.batch, WIDTH, HEIGHT)
+        tile_passes = (sort_bits - 32 + 7) // 8
+        # algorithmic bytes per FRAME for each stage.  flame .. ranges, composite: SURVEY.md §8d.  The
+        # binning is charged what THIS design has to move: depth sort = one 4-byte
+        # histogram read + 4 passes x 16 B per Gaussian; tile sort = 4 B + passes x 16 B per pair.
         alg = {
             "flame": 4.0 * 3 * d["V"] * 2 + 44.0 * d["V"],                  # GEMM output + LBS stream
             "face_frames": 80.0 * d["F"],
             "bind_preprocess": 288.0 * N_GAUSS,
-            "scan_emit": 12.0 * R + 8.0 * N_GAUSS,
-            "sort": (8.0 + 2 * 12.0 * passes) * R,
-            "ranges": 8.0 * R,
+            "depth_sort": (4.0 + 16.0 * 4) * N_GAUSS,
+            "scan_emit": 8.0 * R + 24.0 * N_GAUSS,
+            "tile_sort": (4.0 + 16.0 * tile_passes) * R,
+            "ranges": 4.0 * R,
             "composite": 40.0 * R + 12.0 * hw,
         }
+        published_sort_bytes = (8.0 + 24.0 * ((sort_bits + 7) // 8)) * R   # SURVEY's single 64-bit-key sort
         stages = {}
         total_ms = sum(v["ms"] for v in st.values())
         for name, v in st.items():
@@ -335,15 +343,18 @@ def main():
         flops_gemm = 2.0 * 3 * d["kpad"] * d["npad"]
         cpu = None
         if not args.no_cpu:
-            fps, dtc, cores = cpu_oracle_fps(model, params, baked, cam, args.cpu_frames)
+            n_cpu = min(args.cpu_frames, T)
+            fps, dtc, cores = cpu_oracle_fps(model, params, baked, cam, n_cpu)
             cpu = {"value": fps, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": f"first {args.cpu_frames} of {T} frames of the same clip, {dtc:.1f} s of host time"}
+                   "sample": f"first {n_cpu} of {T} frames of the same clip, {dtc:.1f} s of host time"}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(T), "frames_per_step_per_rank": T, "batch_segments": args.batch,
-                       "tile_pairs_per_frame": R, "sort_passes": passes,
+                       "tile_pairs_per_frame": R, "sort": "depth sort 4 passes/Gaussian + tile sort %d passes/pair "
+                       "(published single sort: %d passes, %.1f MB/frame)" % (tile_passes, (sort_bits + 7) // 8,
+                                                                             published_sort_bytes / 1e6),
                        "gemm": "tcgen05 tf32x3" if args.gemm == 0 else "cuda-core fp32",
                        "l2": "per-batch working set (P0-P2 %.0f MB + keys/values %.0f MB) exceeds the 126 MB L2; "
                              "frame-invariant avatar streams (24 MB) stay L2-resident by design" % (

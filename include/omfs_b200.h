@@ -92,24 +92,29 @@ int omfs_face_frames(int T, int V, int F, const float* d_verts, const int32_t* d
 /* U5+U6 fused: parent-triangle transform of every Gaussian, then cull / project / EWA / SH.
  * One segment = one (frame, camera) pair; d_seg_frame[S] gives the frame of each segment and
  * d_cams[S,40] its camera.  Outputs are [S,N,4] float4 streams plus d_tiles_touched[S,N]:
- *   P0 = (px, py, depth, radius as int32 bits)  P1 = (ca, cb, cc, lo)  P2 = (r, g, b, 0). */
+ *   P0 = (px, py, depth, radius as int32 bits)  P1 = (ca, cb, cc, lo)  P2 = (r, g, b, 0)
+ * and (optional) d_depth_keys[S,N] = the depth's float bits, 0 for culled Gaussians: the key of the
+ * depth sort in omfs_binning. */
 int omfs_bind_preprocess(int S, int N, int F, int width, int height,
                          const float* d_ff, const int32_t* d_seg_frame, const float* d_cams,
                          const float* d_xyzb, const float* d_scale_lo, const float* d_rot, const float* d_sh,
-                         float* d_P0, float* d_P1, float* d_P2, uint32_t* d_tiles_touched, void* stream);
+                         float* d_P0, float* d_P1, float* d_P2, uint32_t* d_tiles_touched,
+                         uint32_t* d_depth_keys, void* stream);
 
-/* U7+U8+U9: inclusive scan of tiles_touched, key emission ((seg*tiles+tile)<<32 | depth bits,
- * value = Gaussian index in its segment), onesweep LSD radix sort on the low sort_bits bits,
- * tile ranges.  capacity = max tile pairs the key/value buffers hold.  The sorted pairs end up
- * in d_keys[out]/d_vals[out] where *h_out_buffer_index (0 or 1) is returned immediately (it only
- * depends on sort_bits).  d_num_pairs (uint32 on device) receives the pair count; if it exceeds
- * capacity the batch is truncated and d_status_flag (int on device) is set to 1. */
+/* U7+U8+U9.  Result: the pair list of the batch ordered by the published key
+ * ((seg*tiles+tile)<<32 | depth bits, ties by Gaussian index): d_sorted_vals[capacity] (Gaussian index
+ * inside its segment) and d_ranges[S*tiles,2].  Internally: segmented depth sort of the Gaussians
+ * (onesweep, 4 passes), scan + emission in depth order, stable onesweep sort by tile id (binning.cu).
+ * Optional outputs for parity / debugging: d_sorted_keys[capacity] (the 64-bit keys in final order),
+ * d_emitted_keys / d_emitted_vals (the list as emitted, before the tile sort).
+ * d_num_pairs (uint32 on device) receives the pair count; if it exceeds capacity nothing is sorted and
+ * d_status_flag (int on device) is set to 1.  All scratch comes from d_workspace. */
 size_t omfs_binning_workspace_bytes(int S, int N, int width, int height, size_t capacity);
 int omfs_binning(int S, int N, int width, int height, size_t capacity,
-                 const float* d_P0, const uint32_t* d_tiles_touched,
-                 uint32_t* d_offsets, uint64_t* d_keys0, uint64_t* d_keys1, uint32_t* d_vals0, uint32_t* d_vals1,
-                 uint32_t* d_ranges /*[S*tiles,2]*/, uint32_t* d_num_pairs, int* d_status_flag,
-                 void* d_workspace, size_t workspace_bytes, int* h_out_buffer_index, void* stream);
+                 const float* d_P0, const uint32_t* d_depth_keys, const uint32_t* d_tiles_touched,
+                 uint32_t* d_sorted_vals, uint64_t* d_sorted_keys, uint64_t* d_emitted_keys,
+                 uint32_t* d_emitted_vals, uint32_t* d_ranges /*[S*tiles,2]*/, uint32_t* d_num_pairs,
+                 int* d_status_flag, void* d_workspace, size_t workspace_bytes, void* stream);
 
 /* U10: front-to-back alpha compositing, one 16x16 tile per CTA.  d_image[S,3,H,W];
  * d_image_u8 (optional) [S,H,W,3] gets the save_image quantisation in the same kernel. */
@@ -161,7 +166,7 @@ typedef struct omfs_session_config {
     int32_t max_batch;          /* segments (frame x view) per launch group */
     int32_t device;
     int32_t gemm_impl;          /* 0 tensor core, 1 CUDA core */
-    int32_t use_graph;          /* replay each batch as a CUDA graph */
+    int32_t debug_keys;         /* also materialise the 64-bit sorted keys of each batch (parity taps) */
     uint64_t pair_capacity;     /* tile pairs per batch; 0 = 24 * max_batch * n_gauss / 4 */
     float bg[3];
 } omfs_session_config;
@@ -204,7 +209,7 @@ int omfs_session_stats(omfs_session* s, uint64_t* out4);
 
 /* Debug taps for the parity tests: pointers into the session's buffers for the LAST batch
  * rendered (valid until the next call).  Names: "verts" "ff" "P0" "P1" "P2" "tiles_touched"
- * "offsets" "keys_unsorted" "vals_unsorted" "keys" "vals" "ranges" "image" "vp" "acoef". */
+ * "depth_keys" "keys" (needs debug_keys) "vals" "ranges" "image" "image_u8" "vp" "acoef" "base" "rmats". */
 int omfs_session_tap(omfs_session* s, const char* name, void** d_ptr, size_t* bytes);
 
 /* Waits for the session's streams; returns OMFS_ERR_CAPACITY if any batch overflowed. */
@@ -234,10 +239,6 @@ unsigned long long omfs_launch_count(void);    /* kernels launched by this libra
 int omfs_flame_fold_subject(int V, int n_shape, int npad, const float* d_template, const float* d_shapedirs,
                             const float* d_shape, const float* d_static, const float* d_plan, const float* d_jreg,
                             float* d_base, void* stream);
-int omfs_scan_emit(int S, int N, int width, int height, size_t capacity, const float* d_P0,
-                   const uint32_t* d_tiles_touched, uint32_t* d_offsets, uint64_t* d_keys, uint32_t* d_vals,
-                   uint32_t* d_num_pairs, int* d_status_flag, void* d_workspace, size_t workspace_bytes,
-                   void* stream);
 int omfs_binning_sort_bits(int S, int width, int height);
 int omfs_to_uint8(int S, int width, int height, const float* d_image, uint8_t* d_out, void* stream);
 

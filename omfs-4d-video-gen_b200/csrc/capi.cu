@@ -141,19 +141,23 @@ struct omfs_session {
     // per geometry chunk
     DevBuf acoef, rmats, vp, verts;
     // per batch
-    DevBuf ff, P0, P1, P2, tt, offsets, keys0, keys1, vals0, vals1, ranges, counters, ws, image[2], image_u8[2];
+    DevBuf ff, P0, P1, P2, tt, depth_keys, vals, keys64, ranges, counters, ws, image[2], image_u8[2];
     size_t ws_bytes = 0;
     int last_sorted_buffer = 0, last_image_buffer = 0, last_batch_segments = 0;
     uint64_t stats[4]{};
     // optional per-stage timing (bench.py's roofline pass): events around every stage of every batch
     bool profiling = false;
-    cudaEvent_t prof_ev[8]{};
+    std::vector<cudaEvent_t> prof_pool;   // events recorded during a call, resolved after the final sync
+    std::vector<int> prof_stage;          // stage id each event OPENS (-1: closes the previous one only)
     double stage_ms[8]{};
     uint64_t stage_calls[8]{};
     uint32_t last_pairs = 0;
+    cudaStream_t user_stream = nullptr;   // stream of the last render_device call
+    std::vector<int32_t> seg_frame_host;
+    int seg_table_fpb = -1, seg_table_views = -1;
 };
 
-enum Stage { kStFlame = 0, kStFaceFrames, kStBindPre, kStScanEmit, kStSort, kStRanges, kStComposite, kStCount };
+enum Stage { kStFlame = 0, kStFaceFrames, kStBindPre, kStDepthSort, kStScanEmit, kStTileSort, kStRanges, kStComposite, kStCount };
 
 static int upload(DevBuf& b, const void* h, size_t bytes, cudaStream_t st) {
     int rc = b.ensure(bytes);
@@ -180,15 +184,14 @@ extern "C" void omfs_session_destroy(omfs_session* s) {
                      &s->scale_lo, &s->rot, &s->sh, &s->base, &s->shape, &s->static_off, &s->plan_off,
                      &s->expr, &s->rotation, &s->neck, &s->jaw, &s->eyes, &s->transl, &s->dyn, &s->jdyn,
                      &s->cams, &s->seg_frame, &s->acoef, &s->rmats, &s->vp, &s->verts, &s->ff, &s->P0, &s->P1,
-                     &s->P2, &s->tt, &s->offsets, &s->keys0, &s->keys1, &s->vals0, &s->vals1, &s->ranges,
+                     &s->P2, &s->tt, &s->depth_keys, &s->vals, &s->keys64, &s->ranges,
                      &s->counters, &s->ws, &s->image[0], &s->image[1], &s->image_u8[0], &s->image_u8[1]};
     for (DevBuf* b : all) b->release();
     for (int i = 0; i < 2; i++) {
         if (s->ev_done[i]) cudaEventDestroy(s->ev_done[i]);
         if (s->ev_copied[i]) cudaEventDestroy(s->ev_copied[i]);
     }
-    for (int i = 0; i < 8; i++)
-        if (s->prof_ev[i]) cudaEventDestroy(s->prof_ev[i]);
+    for (cudaEvent_t e : s->prof_pool) cudaEventDestroy(e);
     if (s->stream) cudaStreamDestroy(s->stream);
     if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
     delete s;
@@ -295,11 +298,9 @@ extern "C" int omfs_session_create(const omfs_model_desc* m, const omfs_session_
     TRY(s->P1.ensure(sizeof(float) * 4 * Sb * N));
     TRY(s->P2.ensure(sizeof(float) * 4 * Sb * N));
     TRY(s->tt.ensure(sizeof(uint32_t) * Sb * N));
-    TRY(s->offsets.ensure(sizeof(uint32_t) * Sb * N));
-    TRY(s->keys0.ensure(sizeof(uint64_t) * s->capacity));
-    TRY(s->keys1.ensure(sizeof(uint64_t) * s->capacity));
-    TRY(s->vals0.ensure(sizeof(uint32_t) * s->capacity));
-    TRY(s->vals1.ensure(sizeof(uint32_t) * s->capacity));
+    TRY(s->depth_keys.ensure(sizeof(uint32_t) * Sb * N));
+    TRY(s->vals.ensure(sizeof(uint32_t) * s->capacity));
+    if (cfg->debug_keys) TRY(s->keys64.ensure(sizeof(uint64_t) * s->capacity));
     TRY(s->ranges.ensure(sizeof(uint32_t) * 2 * Sb * s->tiles));
     TRY(s->counters.ensure(256));
     TRY_CUDA(cudaMemsetAsync(s->counters.p, 0, 256, st));
@@ -358,14 +359,20 @@ static int render_core(omfs_session* s, int T, int n_views, const float* p_expr,
     if ((rc = s->vp.ensure(sizeof(float) * (size_t)s->npad * geo))) return rc;
     if ((rc = s->verts.ensure(sizeof(float) * 3 * (size_t)V * geo))) return rc;
     if (p_dyn && (rc = s->jdyn.ensure(sizeof(float) * 15 * (size_t)geo))) return rc;
-    // segment tables for one full batch: seg -> local frame, seg -> camera
+    // segment tables for one full batch: seg -> local frame, seg -> camera.  The seg->frame table only
+    // depends on (frames per batch, views): it is uploaded once and reused by later calls.
     {
         const int Sb = fpb * n_views;
-        std::vector<int32_t> sf(Sb);
-        for (int i = 0; i < Sb; i++) sf[i] = i / n_views;
-        if ((rc = s->seg_frame.ensure(sizeof(int32_t) * Sb))) return rc;
-        OMFS_CUDA(cudaMemcpyAsync(s->seg_frame.p, sf.data(), sizeof(int32_t) * Sb, cudaMemcpyHostToDevice, st));
-        OMFS_CUDA(cudaStreamSynchronize(st));  // sf is a stack-lifetime vector
+        if (s->seg_table_fpb != fpb || s->seg_table_views != n_views) {
+            s->seg_frame_host.resize(Sb);
+            for (int i = 0; i < Sb; i++) s->seg_frame_host[i] = i / n_views;
+            if ((rc = s->seg_frame.ensure(sizeof(int32_t) * Sb))) return rc;
+            OMFS_CUDA(cudaMemcpyAsync(s->seg_frame.p, s->seg_frame_host.data(), sizeof(int32_t) * Sb,
+                                      cudaMemcpyHostToDevice, st));
+            OMFS_CUDA(cudaStreamSynchronize(st));
+            s->seg_table_fpb = fpb;
+            s->seg_table_views = n_views;
+        }
         // cameras tiled per frame of the batch
         if ((rc = s->cams.ensure(sizeof(float) * kCam * Sb))) return rc;
         for (int f = 0; f < fpb; f++)
@@ -378,23 +385,20 @@ static int render_core(omfs_session* s, int T, int n_views, const float* p_expr,
 
     unsigned long long* d_pair_accum = reinterpret_cast<unsigned long long*>(s->counters.as<unsigned char>() + 16);
     const bool prof = s->profiling;
-    if (prof)
-        for (int i = 0; i < 8; i++)
-            if (!s->prof_ev[i]) OMFS_CUDA(cudaEventCreate(&s->prof_ev[i]));
-    // stage timing helper: record before/after, resolve at the end of the batch
-    auto mark = [&](int i) -> int {
-        if (prof) OMFS_CUDA(cudaEventRecord(s->prof_ev[i], st));
-        return OMFS_OK;
-    };
-    auto resolve = [&](int first_stage, int last_stage) -> int {
+    size_t prof_used = 0;
+    s->prof_stage.clear();
+    // stage timing: mark(stage) records an event that closes the previous stage and opens `stage`
+    // (-1 = only close).  Nothing is synchronised here — the CPU keeps running ahead of the GPU, so the
+    // intervals contain kernel time, not launch gaps; they are resolved after the call's final sync.
+    auto mark = [&](int stage) -> int {
         if (!prof) return OMFS_OK;
-        OMFS_CUDA(cudaEventSynchronize(s->prof_ev[last_stage + 1]));
-        for (int k = first_stage; k <= last_stage; k++) {
-            float ms = 0.f;
-            OMFS_CUDA(cudaEventElapsedTime(&ms, s->prof_ev[k], s->prof_ev[k + 1]));
-            s->stage_ms[k] += ms;
-            s->stage_calls[k]++;
+        if (prof_used == s->prof_pool.size()) {
+            cudaEvent_t e;
+            OMFS_CUDA(cudaEventCreate(&e));
+            s->prof_pool.push_back(e);
         }
+        OMFS_CUDA(cudaEventRecord(s->prof_pool[prof_used++], st));
+        s->prof_stage.push_back(stage);
         return OMFS_OK;
     };
 
@@ -418,8 +422,7 @@ static int render_core(omfs_session* s, int T, int n_views, const float* p_expr,
                                  p_transl + (size_t)g0 * 3, dyn_g, dyn_g ? s->jdyn.as<float>() : nullptr,
                                  s->verts.as<float>(), st)))
             return rc;
-        if ((rc = mark(kStFlame + 1))) return rc;
-        if ((rc = resolve(kStFlame, kStFlame))) return rc;
+        if ((rc = mark(-1))) return rc;
         // ---- render batches inside the chunk
         for (int b0 = 0; b0 < gT; b0 += fpb) {
             const int bT = std::min(fpb, gT - b0);
@@ -433,24 +436,28 @@ static int render_core(omfs_session* s, int T, int n_views, const float* p_expr,
             if ((rc = omfs_bind_preprocess(S, N, F, W, H, s->ff.as<float>(), s->seg_frame.as<int32_t>(),
                                            s->cams.as<float>(), s->xyzb.as<float>(), s->scale_lo.as<float>(),
                                            s->rot.as<float>(), s->sh.as<float>(), s->P0.as<float>(),
-                                           s->P1.as<float>(), s->P2.as<float>(), s->tt.as<uint32_t>(), st)))
+                                           s->P1.as<float>(), s->P2.as<float>(), s->tt.as<uint32_t>(),
+                                           s->depth_keys.as<uint32_t>(), st)))
+                return rc;
+            if ((rc = mark(kStDepthSort))) return rc;
+            if ((rc = binning_depth_sort(S, N, W, H, s->capacity, s->depth_keys.as<uint32_t>(), s->ws.p, st)))
                 return rc;
             if ((rc = mark(kStScanEmit))) return rc;
             if ((rc = binning_scan_emit(S, N, W, H, s->capacity, s->P0.as<float>(), s->tt.as<uint32_t>(),
-                                        s->offsets.as<uint32_t>(), s->keys0.as<uint64_t>(), s->vals0.as<uint32_t>(),
-                                        s->ranges.as<uint32_t>(), d_num_pairs, d_flag, d_pair_accum, s->ws.p, st)))
+                                        s->vals.as<uint32_t>(), s->ranges.as<uint32_t>(), d_num_pairs, d_flag,
+                                        d_pair_accum, s->ws.p, st)))
                 return rc;
-            if ((rc = mark(kStSort))) return rc;
-            int sorted = 0;
-            if ((rc = binning_sort(S, N, W, H, s->capacity, s->keys0.as<uint64_t>(), s->keys1.as<uint64_t>(),
-                                   s->vals0.as<uint32_t>(), s->vals1.as<uint32_t>(), s->ws.p, &sorted, st)))
+            if ((rc = mark(kStTileSort))) return rc;
+            const uint32_t* sorted_tiles = nullptr;
+            if ((rc = binning_tile_sort(S, N, W, H, s->capacity, s->vals.as<uint32_t>(), s->ws.p, &sorted_tiles, st)))
                 return rc;
             if ((rc = mark(kStRanges))) return rc;
-            if ((rc = binning_ranges(S, N, W, H, s->capacity,
-                                     sorted ? s->keys1.as<uint64_t>() : s->keys0.as<uint64_t>(),
-                                     s->ranges.as<uint32_t>(), s->ws.p, st)))
+            if ((rc = binning_ranges(S, N, W, H, s->capacity, sorted_tiles, s->ranges.as<uint32_t>(), s->ws.p, st)))
                 return rc;
-            s->last_sorted_buffer = sorted;
+            if (s->cfg.debug_keys &&
+                (rc = binning_rebuild_keys(S, N, W, H, s->capacity, sorted_tiles, s->vals.as<uint32_t>(),
+                                           s->P0.as<float>(), s->keys64.as<uint64_t>(), s->ws.p, st)))
+                return rc;
             // the image buffer may still be draining to the host from two batches ago
             if (batch_index >= 2 && out_on_host) OMFS_CUDA(cudaStreamWaitEvent(st, s->ev_copied[ib], 0));
             float* img = s->image[ib].as<float>();
@@ -462,11 +469,10 @@ static int render_core(omfs_session* s, int T, int n_views, const float* p_expr,
             if (!dst_f && !dst_8) dst_f = img;  // nothing requested: still render (debug taps)
             if ((rc = mark(kStComposite))) return rc;
             if ((rc = omfs_composite(S, N, W, H, s->P0.as<float>(), s->P1.as<float>(), s->P2.as<float>(),
-                                     sorted ? s->vals1.as<uint32_t>() : s->vals0.as<uint32_t>(),
-                                     s->ranges.as<uint32_t>(), s->cfg.bg, dst_f, dst_8, st)))
+                                     s->vals.as<uint32_t>(), s->ranges.as<uint32_t>(), s->cfg.bg, dst_f, dst_8,
+                                     st)))
                 return rc;
-            if ((rc = mark(kStComposite + 1))) return rc;
-            if ((rc = resolve(kStFaceFrames, kStComposite))) return rc;
+            if ((rc = mark(-1))) return rc;
             s->last_image_buffer = ib;
             s->last_batch_segments = S;
             if (out_on_host) {
@@ -488,7 +494,26 @@ static int render_core(omfs_session* s, int T, int n_views, const float* p_expr,
     return OMFS_OK;
 }
 
+static int resolve_profile(omfs_session* s) {
+    const size_t n = s->prof_stage.size();
+    for (size_t i = 0; i + 1 < n; i++) {
+        const int stage = s->prof_stage[i];
+        if (stage < 0) continue;
+        float ms = 0.f;
+        OMFS_CUDA(cudaEventElapsedTime(&ms, s->prof_pool[i], s->prof_pool[i + 1]));
+        s->stage_ms[stage] += ms;
+        s->stage_calls[stage]++;
+    }
+    s->prof_stage.clear();
+    return OMFS_OK;
+}
+
 static int finish_stats(omfs_session* s) {
+    if (s->profiling) {
+        OMFS_CUDA(cudaDeviceSynchronize());  // the caller may have rendered on its own stream
+        int prc = resolve_profile(s);
+        if (prc) return prc;
+    }
     uint32_t h[8] = {0};
     OMFS_CUDA(cudaMemcpy(h, s->counters.p, sizeof(h), cudaMemcpyDeviceToHost));
     unsigned long long total = 0;
@@ -550,7 +575,8 @@ extern "C" int omfs_session_render_device(omfs_session* s, const omfs_frames_des
                  "null frame array");
     OMFS_CUDA(cudaSetDevice(s->cfg.device));
     if (fr->n_frames == 0) return OMFS_OK;
-    cudaStream_t st = stream ? (cudaStream_t)stream : s->stream;
+    cudaStream_t st = (cudaStream_t)stream;  // NULL = the legacy default stream, as everywhere in this ABI
+    s->user_stream = st;
     return render_core(s, fr->n_frames, fr->n_views, fr->expr, fr->rotation, fr->neck_pose, fr->jaw_pose,
                        fr->eyes_pose, fr->translation, fr->dynamic_offset, fr->cams, d_out_u8, d_out_f32, false, st);
 }
@@ -559,6 +585,7 @@ extern "C" int omfs_session_render_device(omfs_session* s, const omfs_frames_des
 extern "C" int omfs_session_sync(omfs_session* s) {
     OMFS_REQUIRE(s, "null argument");
     OMFS_CUDA(cudaSetDevice(s->cfg.device));
+    OMFS_CUDA(cudaStreamSynchronize(s->user_stream));
     OMFS_CUDA(cudaStreamSynchronize(s->stream));
     OMFS_CUDA(cudaStreamSynchronize(s->copy_stream));
     return finish_stats(s);
@@ -578,15 +605,19 @@ extern "C" int omfs_session_tap(omfs_session* s, const char* name, void** d_ptr,
         const char* n;
         DevBuf* b;
     };
-    DevBuf* sorted_k = s->last_sorted_buffer ? &s->keys1 : &s->keys0;
-    DevBuf* sorted_v = s->last_sorted_buffer ? &s->vals1 : &s->vals0;
+    DevBuf* sorted_k = &s->keys64;
+    DevBuf* sorted_v = &s->vals;
     Tap taps[] = {{"verts", &s->verts}, {"ff", &s->ff}, {"P0", &s->P0}, {"P1", &s->P1}, {"P2", &s->P2},
-                  {"tiles_touched", &s->tt}, {"offsets", &s->offsets}, {"keys", sorted_k}, {"vals", sorted_v},
+                  {"tiles_touched", &s->tt}, {"depth_keys", &s->depth_keys}, {"keys", sorted_k}, {"vals", sorted_v},
                   {"ranges", &s->ranges}, {"image", &s->image[s->last_image_buffer]},
                   {"image_u8", &s->image_u8[s->last_image_buffer]}, {"vp", &s->vp}, {"acoef", &s->acoef},
                   {"base", &s->base}, {"counters", &s->counters}, {"rmats", &s->rmats}};
     for (const Tap& t : taps)
         if (strcmp(t.n, name) == 0) {
+            if (!t.b->p) {
+                set_error("tap '%s' is not materialised (create the session with debug_keys=1)", name);
+                return OMFS_ERR_INVALID;
+            }
             *d_ptr = t.b->p;
             *bytes = t.b->bytes;
             return OMFS_OK;
@@ -597,7 +628,7 @@ extern "C" int omfs_session_tap(omfs_session* s, const char* name, void** d_ptr,
 
 // Per-stage device time, accumulated while profiling is on (it costs a host sync per batch, so the
 // headline throughput is measured with profiling off).  out_ms/out_calls: flame, face_frames,
-// bind_preprocess, scan+emit, sort, ranges, composite, (unused).
+// bind_preprocess, depth_sort, scan+emit, tile_sort, ranges, composite.
 extern "C" int omfs_session_set_profiling(omfs_session* s, int on) {
     OMFS_REQUIRE(s, "null argument");
     s->profiling = on != 0;

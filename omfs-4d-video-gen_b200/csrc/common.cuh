@@ -43,14 +43,19 @@ extern unsigned long long g_launches;
 inline void count_launch(int n = 1) { g_launches += (unsigned long long)n; }
 
 // binning stages (binning.cu), called separately by the session so that it can time them
+int binning_depth_sort(int S, int N, int width, int height, size_t capacity, const uint32_t* d_depth_keys,
+                       void* d_workspace, cudaStream_t stream);
 int binning_scan_emit(int S, int N, int width, int height, size_t capacity, const float* d_P0,
-                      const uint32_t* d_tiles_touched, uint32_t* d_offsets, uint64_t* d_keys, uint32_t* d_vals,
-                      uint32_t* d_ranges, uint32_t* d_num_pairs, int* d_status_flag,
-                      unsigned long long* d_pair_accum, void* d_workspace, cudaStream_t stream);
-int binning_sort(int S, int N, int width, int height, size_t capacity, uint64_t* d_keys0, uint64_t* d_keys1,
-                 uint32_t* d_vals0, uint32_t* d_vals1, void* d_workspace, int* out_index, cudaStream_t stream);
-int binning_ranges(int S, int N, int width, int height, size_t capacity, const uint64_t* d_sorted_keys,
+                      const uint32_t* d_tiles_touched, uint32_t* d_sorted_vals, uint32_t* d_ranges,
+                      uint32_t* d_num_pairs, int* d_status_flag, unsigned long long* d_pair_accum,
+                      void* d_workspace, cudaStream_t stream);
+int binning_tile_sort(int S, int N, int width, int height, size_t capacity, uint32_t* d_sorted_vals,
+                      void* d_workspace, const uint32_t** d_sorted_tiles_out, cudaStream_t stream);
+int binning_ranges(int S, int N, int width, int height, size_t capacity, const uint32_t* d_sorted_tiles,
                    uint32_t* d_ranges, void* d_workspace, cudaStream_t stream);
+int binning_rebuild_keys(int S, int N, int width, int height, size_t capacity, const uint32_t* d_tile_ids,
+                         const uint32_t* d_vals, const float* d_P0, uint64_t* d_keys64, void* d_workspace,
+                         cudaStream_t stream);
 
 // 128-bit streaming loads / stores.  The frame-invariant avatar streams and per-frame records are
 // read through the read-only path; outputs that the next kernel re-reads stay default-cached so

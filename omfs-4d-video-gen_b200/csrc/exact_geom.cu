@@ -41,7 +41,8 @@ __global__ void __launch_bounds__(256) bind_preprocess_kernel(
     int N, int F, int width, int height, const float4* __restrict__ ff, const int32_t* __restrict__ seg_frame,
     const float* __restrict__ cams, const float4* __restrict__ xyzb, const float4* __restrict__ scale_lo,
     const float4* __restrict__ rot, const float4* __restrict__ sh, float4* __restrict__ P0,
-    float4* __restrict__ P1, float4* __restrict__ P2, uint32_t* __restrict__ tiles_touched) {
+    float4* __restrict__ P1, float4* __restrict__ P2, uint32_t* __restrict__ tiles_touched,
+    uint32_t* __restrict__ depth_keys) {
     __shared__ float s_cam[kCam];
     const int seg = blockIdx.y;
     if (threadIdx.x < kCam) s_cam[threadIdx.x] = __ldg(cams + (size_t)seg * kCam + threadIdx.x);
@@ -74,6 +75,7 @@ __global__ void __launch_bounds__(256) bind_preprocess_kernel(
         P1[oi] = make_float4(0.f, 0.f, 0.f, 0.f);
         P2[oi] = make_float4(0.f, 0.f, 0.f, 0.f);
         tiles_touched[oi] = 0;
+        if (depth_keys) depth_keys[oi] = 0u;
         return;
     }
     float dx, dy, dz;
@@ -103,6 +105,7 @@ __global__ void __launch_bounds__(256) bind_preprocess_kernel(
     P1[oi] = make_float4(o.ca, o.cb, o.cc, s.w);
     P2[oi] = make_float4(rgb[0], rgb[1], rgb[2], 0.f);
     tiles_touched[oi] = o.tiles;
+    if (depth_keys) depth_keys[oi] = __float_as_uint(o.depth);  // sort key of the depth sort (binning.cu)
 }
 
 }  // namespace omfs
@@ -127,7 +130,8 @@ extern "C" int omfs_face_frames(int T, int V, int F, const float* d_verts, const
 extern "C" int omfs_bind_preprocess(int S, int N, int F, int width, int height, const float* d_ff,
                                     const int32_t* d_seg_frame, const float* d_cams, const float* d_xyzb,
                                     const float* d_scale_lo, const float* d_rot, const float* d_sh, float* d_P0,
-                                    float* d_P1, float* d_P2, uint32_t* d_tiles_touched, void* stream) {
+                                    float* d_P1, float* d_P2, uint32_t* d_tiles_touched, uint32_t* d_depth_keys,
+                                    void* stream) {
     OMFS_REQUIRE(S >= 0 && N > 0 && F > 0 && width > 0 && height > 0, "bad sizes");
     OMFS_REQUIRE(S <= 65535, "at most 65535 segments per call");
     OMFS_REQUIRE(d_ff && d_seg_frame && d_cams && d_xyzb && d_scale_lo && d_rot && d_sh, "null input");
@@ -137,7 +141,7 @@ extern "C" int omfs_bind_preprocess(int S, int N, int F, int width, int height, 
     bind_preprocess_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
         N, F, width, height, (const float4*)d_ff, d_seg_frame, d_cams, (const float4*)d_xyzb,
         (const float4*)d_scale_lo, (const float4*)d_rot, (const float4*)d_sh, (float4*)d_P0, (float4*)d_P1,
-        (float4*)d_P2, d_tiles_touched);
+        (float4*)d_P2, d_tiles_touched, d_depth_keys);
     count_launch();
     OMFS_LAUNCH_CHECK();
     return OMFS_OK;

@@ -42,7 +42,7 @@ class ModelDesc(ctypes.Structure):
 
 class SessionConfig(ctypes.Structure):
     _fields_ = [("width", c_int32), ("height", c_int32), ("max_batch", c_int32), ("device", c_int32),
-                ("gemm_impl", c_int32), ("use_graph", c_int32), ("pair_capacity", c_uint64), ("bg", c_float * 3)]
+                ("gemm_impl", c_int32), ("debug_keys", c_int32), ("pair_capacity", c_uint64), ("bg", c_float * 3)]
 
 
 class FramesDesc(ctypes.Structure):
@@ -94,9 +94,8 @@ def load_library():
     L.omfs_flame_joint_dyn.argtypes = [c_int, c_int, vp, vp, vp, vp]
     L.omfs_flame_fold_subject.argtypes = [c_int, c_int, c_int, vp, vp, vp, vp, vp, vp, vp, vp]
     L.omfs_face_frames.argtypes = [c_int, c_int, c_int, vp, vp, vp, vp]
-    L.omfs_bind_preprocess.argtypes = [c_int, c_int, c_int, c_int, c_int] + [vp] * 12
-    L.omfs_binning.argtypes = [c_int, c_int, c_int, c_int, c_size_t] + [vp] * 11 + [c_size_t, POINTER(c_int), vp]
-    L.omfs_scan_emit.argtypes = [c_int, c_int, c_int, c_int, c_size_t] + [vp] * 8 + [c_size_t, vp]
+    L.omfs_bind_preprocess.argtypes = [c_int, c_int, c_int, c_int, c_int] + [vp] * 13
+    L.omfs_binning.argtypes = [c_int, c_int, c_int, c_int, c_size_t] + [vp] * 11 + [c_size_t, vp]
     L.omfs_binning_sort_bits.argtypes = [c_int, c_int, c_int]
     L.omfs_composite.argtypes = [c_int, c_int, c_int, c_int, vp, vp, vp, vp, vp, POINTER(c_float), vp, vp, vp]
     L.omfs_to_uint8.argtypes = [c_int, c_int, c_int, vp, vp, vp]
@@ -157,7 +156,8 @@ class Session:
     """
 
     def __init__(self, model, baked: dict, width: int, height: int, max_batch: int = 32, device: int = 0,
-                 gemm_impl: int = 0, pair_capacity: int = 0, bg=(1.0, 1.0, 1.0), n_expr: int | None = None):
+                 gemm_impl: int = 0, pair_capacity: int = 0, bg=(1.0, 1.0, 1.0), n_expr: int | None = None,
+                 debug_keys: bool = False):
         L = load_library()
         self._L = L
         self.width, self.height = int(width), int(height)
@@ -178,7 +178,7 @@ class Session:
         md = ModelDesc(self.n_verts, self.n_faces, self.n_expr, self.n_gauss,
                        *[_ptr(keep[k]) for k in ("v_template", "shapedirs", "posedirs", "j_regressor",
                                                  "lbs_weights", "faces", "xyzb", "scale_lo", "rot", "sh")])
-        cfg = SessionConfig(self.width, self.height, self.max_batch, self.device, int(gemm_impl), 0,
+        cfg = SessionConfig(self.width, self.height, self.max_batch, self.device, int(gemm_impl), int(bool(debug_keys)),
                             int(pair_capacity), (c_float * 3)(*[float(x) for x in bg]))
         self._h = c_void_p()
         check(L.omfs_session_create(ctypes.byref(md), ctypes.byref(cfg), ctypes.byref(self._h)))
@@ -264,7 +264,8 @@ class Session:
         keys = ("V", "F", "n_expr", "N", "kpad", "npad", "tiles", "last_batch_segments", "pairs_last_batch")
         return dict(zip(keys, [int(x) for x in out]))
 
-    STAGES = ("flame", "face_frames", "bind_preprocess", "scan_emit", "sort", "ranges", "composite")
+    STAGES = ("flame", "face_frames", "bind_preprocess", "depth_sort", "scan_emit", "tile_sort", "ranges",
+              "composite")
 
     def set_profiling(self, on: bool):
         check(self._L.omfs_session_set_profiling(self._h, 1 if on else 0))

@@ -65,7 +65,7 @@ def test_sort_properties_full_size(full_scene):
     model, params, av, baked, cam = full_scene
     W = H = 512
     S = 16
-    sess = rt.Session(model, baked, W, H, max_batch=S)
+    sess = rt.Session(model, baked, W, H, max_batch=S, debug_keys=True)
     sess.set_subject(params.shape, params.static_offset)
     sess.render_host(params.slice(0, S), [cam], want_u8=True)
     R = sess.dims()["pairs_last_batch"]

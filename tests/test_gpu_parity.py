@@ -48,7 +48,7 @@ def assert_independent_image_parity(img, full_image):
 
 
 def run_session(rt, model, params, baked, cams, W, H, max_batch, gemm_impl=0, plan_offset=None, **kw):
-    sess = rt.Session(model, baked, W, H, max_batch=max_batch, gemm_impl=gemm_impl, **kw)
+    sess = rt.Session(model, baked, W, H, max_batch=max_batch, gemm_impl=gemm_impl, debug_keys=True, **kw)
     sess.set_subject(params.shape, params.static_offset, plan_offset)
     u8, img = sess.render_host(params, cams, want_f32=True)
     return sess, u8, img
@@ -73,7 +73,7 @@ def test_full_chain_small(rt, small_scene, gemm_impl):
     assert np.array_equal(sess.tap_array("tiles_touched", (T, N), np.uint32), ref.pre.tiles_touched)
     R = ref.binned.n_pairs
     assert sess.dims()["pairs_last_batch"] == R == sess.stats()["pairs"]
-    assert np.array_equal(sess.tap_array("offsets", (T * N,), np.uint32), ref.binned.offsets)
+    assert np.array_equal(sess.tap_array("depth_keys", (T, N), np.uint32), ref.pre.P0[..., 2].view(np.uint32))
     assert np.array_equal(sess.tap_array("keys", (R,), np.uint64), ref.binned.sorted_keys)
     assert np.array_equal(sess.tap_array("vals", (R,), np.uint32), ref.binned.sorted_values)
     tiles = ((W + 15) // 16) * ((H + 15) // 16)
@@ -108,44 +108,52 @@ def test_level1_stages_and_unsorted_keys(rt, small_scene):
     d_tt = DA((S, N), np.uint32)
     rt.check(L.omfs_bind_preprocess(S, N, F, W, H, d_ff.ptr, d_seg.ptr, d_cams.ptr, d_b["xyzb"].ptr,
                                     d_b["scale_lo"].ptr, d_b["rot"].ptr, d_b["sh"].ptr, d_P[0].ptr, d_P[1].ptr,
-                                    d_P[2].ptr, d_tt.ptr, None))
+                                    d_P[2].ptr, d_tt.ptr, None, None))
     assert np.array_equal(bits(d_P[0].numpy()), bits(ref.pre.P0))
     assert np.array_equal(d_tt.numpy(), ref.pre.tiles_touched)
     # Gaussian -> triangle indices ride through the baked stream untouched
     from omfs_b200 import avatar as avatar_mod
     assert np.array_equal(avatar_mod.binding_of({"xyzb": d_b["xyzb"].numpy()}), av.binding)
 
+    d_dk = DA((S, N), np.uint32)
+    rt.check(L.omfs_bind_preprocess(S, N, F, W, H, d_ff.ptr, d_seg.ptr, d_cams.ptr, d_b["xyzb"].ptr,
+                                    d_b["scale_lo"].ptr, d_b["rot"].ptr, d_b["sh"].ptr, d_P[0].ptr, d_P[1].ptr,
+                                    d_P[2].ptr, d_tt.ptr, d_dk.ptr, None))
+    assert np.array_equal(d_dk.numpy(), ref.pre.P0[..., 2].view(np.uint32))
     cap = ref.binned.n_pairs + 17
     ws_bytes = L.omfs_binning_workspace_bytes(S, N, W, H, cap)
     d_ws = DA((ws_bytes,), np.uint8)
-    d_off = DA((S * N,), np.uint32)
-    d_k = [DA((cap,), np.uint64) for _ in range(2)]
-    d_v = [DA((cap,), np.uint32) for _ in range(2)]
+    d_vals, d_keys = DA((cap,), np.uint32), DA((cap,), np.uint64)
+    d_ek, d_ev = DA((cap,), np.uint64), DA((cap,), np.uint32)
     d_cnt = DA((4,), np.uint32)
     d_cnt.zero()
     flag_ptr = d_cnt.ptr + 4
-    rt.check(L.omfs_scan_emit(S, N, W, H, cap, d_P[0].ptr, d_tt.ptr, d_off.ptr, d_k[0].ptr, d_v[0].ptr, d_cnt.ptr,
-                              flag_ptr, d_ws.ptr, ws_bytes, None))
-    R = ref.binned.n_pairs
-    assert int(d_cnt.numpy()[0]) == R
-    assert np.array_equal(d_k[0].numpy()[:R], ref.binned.keys)       # UNSORTED keys, emission order
-    assert np.array_equal(d_v[0].numpy()[:R], ref.binned.values)
     tiles = ((W + 15) // 16) * ((H + 15) // 16)
     d_ranges = DA((S * tiles, 2), np.uint32)
-    idx = ctypes.c_int(0)
-    rt.check(L.omfs_binning(S, N, W, H, cap, d_P[0].ptr, d_tt.ptr, d_off.ptr, d_k[0].ptr, d_k[1].ptr, d_v[0].ptr,
-                            d_v[1].ptr, d_ranges.ptr, d_cnt.ptr, flag_ptr, d_ws.ptr, ws_bytes, ctypes.byref(idx),
-                            None))
+    rt.check(L.omfs_binning(S, N, W, H, cap, d_P[0].ptr, d_dk.ptr, d_tt.ptr, d_vals.ptr, d_keys.ptr, d_ek.ptr,
+                            d_ev.ptr, d_ranges.ptr, d_cnt.ptr, flag_ptr, d_ws.ptr, ws_bytes, None))
+    R = ref.binned.n_pairs
+    assert int(d_cnt.numpy()[0]) == R and int(d_cnt.numpy()[1]) == 0
     assert L.omfs_binning_sort_bits(S, W, H) == ref.binned.sort_bits
-    assert np.array_equal(d_k[idx.value].numpy()[:R], ref.binned.sorted_keys)
-    assert np.array_equal(d_v[idx.value].numpy()[:R], ref.binned.sorted_values)
+    # the list as EMITTED: the same multiset of (key, value) pairs as the oracle's index-order
+    # emission, here in (segment, depth, index) order
+    ek, ev = d_ek.numpy()[:R], d_ev.numpy()[:R]
+    o1 = np.lexsort((ev, ek))
+    o2 = np.lexsort((ref.binned.values, ref.binned.keys))
+    assert np.array_equal(ek[o1], ref.binned.keys[o2]) and np.array_equal(ev[o1], ref.binned.values[o2])
+    seg_of = (ek >> np.uint64(32)).astype(np.int64) // tiles
+    depth_of = (ek & np.uint64(0xFFFFFFFF)).astype(np.int64)
+    order_key = (seg_of << 49) + (depth_of << 17) + ev.astype(np.int64)     # N < 2^17 here
+    assert np.all(np.diff(order_key) >= 0)
+    # the sorted list: bit-exact keys, values and ranges
+    assert np.array_equal(d_keys.numpy()[:R], ref.binned.sorted_keys)
+    assert np.array_equal(d_vals.numpy()[:R], ref.binned.sorted_values)
     assert np.array_equal(d_ranges.numpy(), ref.binned.ranges)
-    assert int(d_cnt.numpy()[1]) == 0
 
     d_img = DA((S, 3, H, W), np.float32)
     d_u8 = DA((S, H, W, 3), np.uint8)
     bg = (ctypes.c_float * 3)(1.0, 1.0, 1.0)
-    rt.check(L.omfs_composite(S, N, W, H, d_P[0].ptr, d_P[1].ptr, d_P[2].ptr, d_v[idx.value].ptr, d_ranges.ptr, bg,
+    rt.check(L.omfs_composite(S, N, W, H, d_P[0].ptr, d_P[1].ptr, d_P[2].ptr, d_vals.ptr, d_ranges.ptr, bg,
                               d_img.ptr, d_u8.ptr, None))
     img = d_img.numpy()
     assert np.abs(img - ref.image).max() <= 2e-4
