@@ -307,21 +307,21 @@ def main():
         R = pairs_per_frame
         d = sess.dims()
         sort_bits = runtime.load_library().omfs_binning_sort_bits(args.batch, WIDTH, HEIGHT)
-        tile_passes = (sort_bits - 32 + 7) // 8
-        # algorithmic bytes per FRAME for each stage.  flame .. ranges, composite: SURVEY.md §8d.  The
-        # binning is charged what THIS design has to move: depth sort = one 4-byte
-        # histogram read + 4 passes x 16 B per Gaussian; tile sort = 4 B + passes x 16 B per pair.
+        tiles = ((WIDTH + 15) // 16) * ((HEIGHT + 15) // 16)
+        # algorithmic bytes per FRAME for each stage.  flame .. bind_preprocess, composite: SURVEY.md §8d.
+        # The binning is charged what THIS design has to move: depth sort = one 4-byte
+        # histogram read + 4 passes x 16 B per Gaussian; tile counts/ranges = 20 B per Gaussian + 16 B per
+        # tile; emit+scatter = 24 B per Gaussian read + 4 B per pair written once.
         alg = {
             "flame": 4.0 * 3 * d["V"] * 2 + 44.0 * d["V"],                  # GEMM output + LBS stream
             "face_frames": 80.0 * d["F"],
             "bind_preprocess": 288.0 * N_GAUSS,
             "depth_sort": (4.0 + 16.0 * 4) * N_GAUSS,
-            "scan_emit": 8.0 * R + 24.0 * N_GAUSS,
-            "tile_sort": (4.0 + 16.0 * tile_passes) * R,
-            "ranges": 4.0 * R,
+            "tile_ranges": 20.0 * N_GAUSS + 16.0 * tiles,
+            "emit_scatter": 24.0 * N_GAUSS + 4.0 * R,
             "composite": 40.0 * R + 12.0 * hw,
         }
-        published_sort_bytes = (8.0 + 24.0 * ((sort_bits + 7) // 8)) * R   # SURVEY's single 64-bit-key sort
+        published_sort_bytes = (12.0 + 8.0 + 24.0 * ((sort_bits + 7) // 8) + 8.0) * R   # SURVEY U7+U8+U9
         stages = {}
         total_ms = sum(v["ms"] for v in st.values())
         for name, v in st.items():
@@ -352,9 +352,9 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(T), "frames_per_step_per_rank": T, "batch_segments": args.batch,
-                       "tile_pairs_per_frame": R, "sort": "depth sort 4 passes/Gaussian + tile sort %d passes/pair "
-                       "(published single sort: %d passes, %.1f MB/frame)" % (tile_passes, (sort_bits + 7) // 8,
-                                                                             published_sort_bytes / 1e6),
+                       "tile_pairs_per_frame": R, "binning": "segmented depth sort (4 passes/Gaussian) + tile counts + fused emit/counting-sort "
+                       "(published U7-U9: %d-pass 64-bit-key sort, %.1f MB/frame)" % ((sort_bits + 7) // 8,
+                                                                                      published_sort_bytes / 1e6),
                        "gemm": "tcgen05 tf32x3" if args.gemm == 0 else "cuda-core fp32",
                        "l2": "per-batch working set (P0-P2 %.0f MB + keys/values %.0f MB) exceeds the 126 MB L2; "
                              "frame-invariant avatar streams (24 MB) stay L2-resident by design" % (

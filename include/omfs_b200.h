@@ -103,18 +103,18 @@ int omfs_bind_preprocess(int S, int N, int F, int width, int height,
 
 /* U7+U8+U9.  Result: the pair list of the batch ordered by the published key
  * ((seg*tiles+tile)<<32 | depth bits, ties by Gaussian index): d_sorted_vals[capacity] (Gaussian index
- * inside its segment) and d_ranges[S*tiles,2].  Internally: segmented depth sort of the Gaussians
- * (onesweep, 4 passes), scan + emission in depth order, stable onesweep sort by tile id (binning.cu).
- * Optional outputs for parity / debugging: d_sorted_keys[capacity] (the 64-bit keys in final order),
- * d_emitted_keys / d_emitted_vals (the list as emitted, before the tile sort).
- * d_num_pairs (uint32 on device) receives the pair count; if it exceeds capacity nothing is sorted and
- * d_status_flag (int on device) is set to 1.  All scratch comes from d_workspace. */
+ * inside its segment) and d_ranges[S*tiles,2] (untouched tiles stay (0,0)).  Internally (binning.cu):
+ * segmented onesweep depth sort of the Gaussians, per-tile counts and their scan, then one fused
+ * emit + counting-sort-by-tile kernel that writes every index straight to its final position.
+ * d_sorted_keys[capacity] (optional) receives the 64-bit keys in final order, for parity / debugging.
+ * d_num_pairs (uint32 on device) receives the pair count; if it exceeds capacity nothing is emitted
+ * and d_status_flag (int on device) is set to 1.  All scratch comes from d_workspace. */
 size_t omfs_binning_workspace_bytes(int S, int N, int width, int height, size_t capacity);
 int omfs_binning(int S, int N, int width, int height, size_t capacity,
                  const float* d_P0, const uint32_t* d_depth_keys, const uint32_t* d_tiles_touched,
-                 uint32_t* d_sorted_vals, uint64_t* d_sorted_keys, uint64_t* d_emitted_keys,
-                 uint32_t* d_emitted_vals, uint32_t* d_ranges /*[S*tiles,2]*/, uint32_t* d_num_pairs,
-                 int* d_status_flag, void* d_workspace, size_t workspace_bytes, void* stream);
+                 uint32_t* d_sorted_vals, uint64_t* d_sorted_keys, uint32_t* d_ranges /*[S*tiles,2]*/,
+                 uint32_t* d_num_pairs, int* d_status_flag, void* d_workspace, size_t workspace_bytes,
+                 void* stream);
 
 /* U10: front-to-back alpha compositing, one 16x16 tile per CTA.  d_image[S,3,H,W];
  * d_image_u8 (optional) [S,H,W,3] gets the save_image quantisation in the same kernel. */
@@ -218,7 +218,7 @@ void* omfs_session_stream(omfs_session* s);
 /* out9 = V, F, n_expr, N, kpad, npad, tiles, segments of the last batch, tile pairs of the last batch */
 int omfs_session_dims(omfs_session* s, int32_t* out9);
 /* Per-stage device time (ms) and launch-group counts while profiling is on; stages: flame,
- * face_frames, bind_preprocess, scan+emit, sort, ranges, composite, unused.  Profiling adds a host
+ * face_frames, bind_preprocess, depth_sort, tile_ranges, emit_scatter, composite, unused.  Profiling adds a host
  * sync per batch: headline numbers are taken with it off. */
 int omfs_session_set_profiling(omfs_session* s, int on);
 int omfs_session_stage_ms(omfs_session* s, double* out_ms8, uint64_t* out_calls8);

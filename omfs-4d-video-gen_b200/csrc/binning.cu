@@ -6,26 +6,29 @@
 //
 // How it is produced.  A single 6-pass sort of 12-byte pairs (R ~ 3.6 N of them) is what the
 // published pipeline does; on B200 that is the largest HBM consumer of the frame.  The same order
-// comes out of two much smaller sorts, because an LSD radix sort is stable:
-//   1. DEPTH SORT, segmented: the N Gaussians of every segment are sorted by depth bits
-//      (uint32 key, value = Gaussian index; 4 passes over S*N 8-byte items).  Index order is the
-//      tie-break because the first pass starts from the identity permutation.
-//   2. scan of tiles_touched in that order, then EMISSION in depth order: pair = (global tile id,
-//      Gaussian index).  The depth bits are never written: inside a tile, emission order already IS
-//      depth order.
-//   3. TILE SORT: one stable sort of the pairs by global tile id only (uint32 key, 2 passes while
-//      S*tiles <= 2^16).
-// Traffic per pair drops from (8 + 24*6) = 152 B to about 4 + 16*2 = 36 B, plus 4 + 16*4 B per
-// Gaussian; all keys are 32-bit, which also halves the ranking registers.
-// The 64-bit keys exist only on request (rebuild_keys_kernel) for the parity tests / debug taps.
+// comes out of far less traffic, because a counting / LSD radix sort is stable:
+//   1. DEPTH SORT, segmented: the N Gaussians of every segment are sorted by depth bits (uint32 key,
+//      value = Gaussian index; 4 onesweep passes over S*N 8-byte items).  Index order is the tie-break
+//      because the first pass starts from the identity permutation.
+//   2. TILE COUNTS: how many Gaussians touch each tile (shared-memory histograms), then ONE scan over
+//      the S*tiles counters — which is already the tile-range table (U9) and the pair count.
+//   3. EMIT + SCATTER, fused: chunks of 1024 depth-ordered Gaussians expand their pairs in shared
+//      memory, rank them per tile with warp ballots, resolve the chunk's offset inside every tile by
+//      decoupled look-back over the chunks before it, and write each Gaussian index straight to its
+//      FINAL position.  It is a one-pass onesweep with one bin per tile; inside a tile, emission order
+//      IS depth order, so the depth bits are never written and no pair is ever moved twice.
+// Traffic per pair drops from (8 + 24*6) = 152 B to 4 B written once (L2 merges the 4-byte scatters of
+// neighbouring chunks: the whole value array of a batch fits in the 126 MB L2), plus 4 + 16*4 B per
+// Gaussian for the depth sort.  The 64-bit keys exist only on request (rebuild_keys_kernel) for the
+// parity tests / debug taps.
 //
-// Both sorts are the same onesweep kernel (Adinets & Merrill 2022): one upfront histogram kernel per
-// sort, then ONE kernel per pass that ranks a 4096-key tile with warp ballots (8 VOTEs per key give
-// the lanes holding the same digit — MATCH.ANY retires at ~1 per 22 clk per SM on sm_100 and was the
-// top stall of the first version), resolves global offsets by decoupled look-back, and scatters
-// through shared memory so global writes are contiguous per digit run.  Tiles are handed out by an
-// atomic counter, so a tile's predecessors are always already running (no deadlock); segments are
-// independent look-back chains.  Counts live on the device: nothing here synchronises with the host.
+// The depth sort is onesweep (Adinets & Merrill 2022): one upfront histogram kernel, then ONE kernel
+// per pass that ranks a 4096-key tile with warp ballots (8 VOTEs per key give the lanes holding the
+// same digit — MATCH.ANY retires at ~1 per 22 clk per SM on sm_100 and was the top stall of the first
+// version), resolves global offsets by decoupled look-back, and scatters through shared memory so
+// global writes are contiguous per digit run.  Work items are handed out by an atomic counter, so an
+// item's predecessors are always already running (no deadlock); segments are independent look-back
+// chains.  Counts live on the device: nothing here synchronises with the host.
 #include "common.cuh"
 #include "exact_math.cuh"
 
@@ -76,24 +79,40 @@ __device__ __forceinline__ uint32_t block_excl_scan_256(uint32_t v, uint32_t* s_
     return wp + inc - v;
 }
 
-// per-tile sums of tiles_touched taken in DEPTH order (perm holds indices inside the segment)
-__global__ void __launch_bounds__(kScanThreads) scan_tile_sums_kernel(long long count, int N,
-                                                                      const uint32_t* __restrict__ tt,
-                                                                      const uint32_t* __restrict__ perm,
-                                                                      uint32_t* __restrict__ tile_sums) {
-    __shared__ uint32_t s_warp[8];
-    const long long first = (long long)blockIdx.x * kScanTile + (long long)threadIdx.x * kScanItems;
-    uint32_t acc = 0;
-#pragma unroll
-    for (int k = 0; k < kScanItems; k++)
-        if (first + k < count) acc += __ldg(tt + ((first + k) / N) * N + __ldg(perm + first + k));
-    uint32_t total;
-    block_excl_scan_256(acc, s_warp, total);
-    if (threadIdx.x == 0) tile_sums[blockIdx.x] = total;
+// ---------------------------------------------------------------------------------- tile counts
+// cnt[seg*tiles + tile] = number of Gaussians of the segment whose rectangle covers the tile.
+// grid = (blocks per segment, S); dynamic smem = tiles * 4 bytes.
+__global__ void __launch_bounds__(256) tile_count_kernel(int N, int width, int height, int tiles,
+                                                         const float4* __restrict__ P0,
+                                                         const uint32_t* __restrict__ tt,
+                                                         uint32_t* __restrict__ cnt) {
+    extern __shared__ uint32_t s_cnt[];
+    for (int i = threadIdx.x; i < tiles; i += blockDim.x) s_cnt[i] = 0;
+    __syncthreads();
+    const int seg = blockIdx.y;
+    const int gx = (width + kTile - 1) / kTile, gy = (height + kTile - 1) / kTile;
+    for (int n = blockIdx.x * blockDim.x + threadIdx.x; n < N; n += gridDim.x * blockDim.x) {
+        const size_t i = (size_t)seg * N + n;
+        if (__ldg(tt + i) == 0) continue;
+        const float4 p = ldg4(P0 + i);
+        int minx, miny, maxx, maxy;
+        ex_tile_rect(p.x, p.y, __float_as_int(p.w), gx, gy, minx, miny, maxx, maxy);
+        for (int y = miny; y < maxy; y++)
+            for (int x = minx; x < maxx; x++) atomicAdd(&s_cnt[y * gx + x], 1u);
+    }
+    __syncthreads();
+    uint32_t* out = cnt + (size_t)seg * tiles;
+    for (int i = threadIdx.x; i < tiles; i += blockDim.x) {
+        const uint32_t v = s_cnt[i];
+        if (v) atomicAdd(out + i, v);
+    }
 }
 
-// one CTA: exclusive scan of the tile sums in place; pair count, overflow flag, running total
-__global__ void __launch_bounds__(1024) scan_sums_kernel(int n_tiles, uint32_t* __restrict__ tile_sums,
+// one CTA: exclusive scan of the S*tiles counters -> tile_start (final position of each tile's first
+// pair), the tile ranges (U9; untouched tiles stay (0,0)), the pair count and the overflow flag.
+__global__ void __launch_bounds__(1024) tile_scan_kernel(int n_tiles_total, const uint32_t* __restrict__ cnt,
+                                                         uint32_t* __restrict__ tile_start,
+                                                         uint32_t* __restrict__ ranges,
                                                          uint32_t* __restrict__ num_pairs,
                                                          unsigned long long capacity, int* __restrict__ status_flag,
                                                          uint32_t* __restrict__ sort_count,
@@ -103,9 +122,9 @@ __global__ void __launch_bounds__(1024) scan_sums_kernel(int n_tiles, uint32_t* 
     if (threadIdx.x == 0) s_carry = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int base = 0; base < n_tiles; base += 1024) {
+    for (int base = 0; base < n_tiles_total; base += 1024) {
         const int i = base + threadIdx.x;
-        const uint32_t v = (i < n_tiles) ? tile_sums[i] : 0u;
+        const uint32_t v = (i < n_tiles_total) ? cnt[i] : 0u;
         const uint32_t inc = warp_incl_scan(v);
         if (lane == 31) s_warp[warp] = inc;
         __syncthreads();
@@ -116,63 +135,219 @@ __global__ void __launch_bounds__(1024) scan_sums_kernel(int n_tiles, uint32_t* 
         }
         __syncthreads();
         const uint32_t excl = s_carry + s_warp[warp] + inc - v;
-        if (i < n_tiles) tile_sums[i] = excl;
+        if (i < n_tiles_total) {
+            tile_start[i] = excl;
+            ranges[2 * i] = v ? excl : 0u;
+            ranges[2 * i + 1] = v ? excl + v : 0u;
+        }
         __syncthreads();
         if (threadIdx.x == 1023) s_carry = excl + v;
         __syncthreads();
     }
+    const bool overflow = (unsigned long long)s_carry > capacity;
     if (threadIdx.x == 0) {
         const uint32_t total = s_carry;
         *num_pairs = total;
         if (pair_accum) *pair_accum += total;  // running total over the batches of one render call
-        if ((unsigned long long)total > capacity) {
-            // overflow: flag it and sort nothing; the caller re-runs with more capacity
+        if (overflow) {
+            // flag it and emit nothing; the caller re-runs with more capacity
             *status_flag = 1;
             *sort_count = 0;
         } else {
             *sort_count = total;
         }
     }
+    if (overflow)  // no tile may point past the value buffer: the compositing pass then renders background
+        for (int i = threadIdx.x; i < 2 * n_tiles_total; i += 1024) ranges[i] = 0u;
 }
 
-// offsets in depth order + key emission, fused: thread t owns 16 consecutive sorted Gaussians, so its
-// pairs are one contiguous run of the output
-__global__ void __launch_bounds__(kScanThreads) scan_emit_kernel(
-    long long count, int N, int width, int height, const uint32_t* __restrict__ tt,
-    const uint32_t* __restrict__ perm, const uint32_t* __restrict__ tile_sums, const float4* __restrict__ P0,
-    const uint32_t* __restrict__ sort_count, uint32_t* __restrict__ tile_ids, uint32_t* __restrict__ vals) {
-    __shared__ uint32_t s_warp[8];
-    const long long first = (long long)blockIdx.x * kScanTile + (long long)threadIdx.x * kScanItems;
-    uint32_t g[kScanItems], t[kScanItems];
-    uint32_t acc = 0;
-#pragma unroll
-    for (int k = 0; k < kScanItems; k++) {
-        g[k] = 0;
-        t[k] = 0;
-        if (first + k < count) {
-            g[k] = __ldg(perm + first + k);
-            t[k] = __ldg(tt + ((first + k) / N) * N + g[k]);
-        }
-        acc += t[k];
-    }
-    uint32_t total;
-    uint32_t off = block_excl_scan_256(acc, s_warp, total) + tile_sums[blockIdx.x];
-    if (*sort_count == 0) return;  // empty batch or overflow (flagged by scan_sums_kernel)
+// ---------------------------------------------------------------------------------- fused emit + scatter
+constexpr int kEsThreads = 256;
+constexpr int kEsGpt = 4;                            // Gaussians per thread
+constexpr int kEsChunk = kEsThreads * kEsGpt;        // 1024 depth-ordered Gaussians per work item
+constexpr int kEsWin = 1024;                         // pairs per warp per window
+constexpr int kEsWarps = kEsThreads / 32;
+
+// dynamic shared memory: pair[8][kEsWin] u32 | gidx[kEsChunk] u32 | base[tiles] u32 | wcnt[8][tiles] u16
+constexpr int kEsWinShift = 10;
+static_assert((1 << kEsWinShift) == kEsWin, "window size must match its shift");
+static inline size_t emit_scatter_smem(int tiles) {
+    const int tp = (tiles + 1) & ~1;  // even row stride: the packed 16-bit counters are updated as 32-bit words
+    return sizeof(uint32_t) * (kEsWarps * kEsWin + kEsChunk + tiles) + sizeof(uint16_t) * kEsWarps * tp + 64;
+}
+
+__global__ void __launch_bounds__(kEsThreads) emit_scatter_kernel(
+    int S, int N, int width, int height, int tiles, int tile_bits, const uint32_t* __restrict__ perm,
+    const uint32_t* __restrict__ tt, const float4* __restrict__ P0, const uint32_t* __restrict__ tile_start,
+    const uint32_t* __restrict__ sort_count, uint32_t* __restrict__ chunk_counter,
+    volatile uint32_t* __restrict__ status /*[chunks][tiles]*/, uint32_t* __restrict__ vals_out) {
+    extern __shared__ __align__(16) unsigned char es_raw[];
+    uint32_t* s_pair = reinterpret_cast<uint32_t*>(es_raw);            // [8][kEsWin]: tile << 10 | local Gaussian
+    uint32_t* s_gidx = s_pair + kEsWarps * kEsWin;                     // [kEsChunk]
+    uint32_t* s_base = s_gidx + kEsChunk;                              // [tiles]
+    uint16_t* s_wcnt = reinterpret_cast<uint16_t*>(s_base + tiles);    // [8][tp]
+    const int tp = (tiles + 1) & ~1;
+    __shared__ uint32_t s_scan[8];
+    __shared__ uint32_t s_chunk;
+
+    if (*sort_count == 0) return;  // empty batch, or overflow (flagged by tile_scan_kernel)
     const int gx = (width + kTile - 1) / kTile, gy = (height + kTile - 1) / kTile;
+    const int cps = (N + kEsChunk - 1) / kEsChunk;  // chunks per segment
+    const uint32_t n_chunks = (uint32_t)cps * (uint32_t)S;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lanemask_lt = (1u << lane) - 1u;
+
+    while (true) {
+        // chunks are handed out in increasing order: every predecessor a chunk looks back at is owned
+        // by a CTA that is already running
+        if (threadIdx.x == 0) s_chunk = atomicAdd(chunk_counter, 1u);
+        {
+            uint32_t* z = reinterpret_cast<uint32_t*>(s_wcnt);
+            for (int i = threadIdx.x; i < kEsWarps * tp / 2; i += kEsThreads) z[i] = 0;
+        }
+        __syncthreads();
+        const uint32_t chunk = s_chunk;
+        if (chunk >= n_chunks) break;
+        const int seg = (int)(chunk / cps), lc = (int)(chunk % cps);
+        const int g0 = lc * kEsChunk;
+        const int n_g = min(kEsChunk, N - g0);
+        const size_t seg_off = (size_t)seg * N;
+
+        // ---- my 4 consecutive depth-ordered Gaussians: tile rectangles and pair counts
+        int rminx[kEsGpt], rminy[kEsGpt], rw[kEsGpt];
+        uint32_t cnt[kEsGpt];
+        uint32_t acc = 0;
 #pragma unroll
-    for (int k = 0; k < kScanItems; k++) {
-        if (t[k] == 0) continue;
-        const long long seg = (first + k) / N;
-        const float4 p = ldg4(P0 + seg * N + g[k]);
-        int minx, miny, maxx, maxy;
-        ex_tile_rect(p.x, p.y, __float_as_int(p.w), gx, gy, minx, miny, maxx, maxy);
-        const uint32_t seg_base = (uint32_t)seg * (uint32_t)(gx * gy);
-        for (int y = miny; y < maxy; y++)
-            for (int x = minx; x < maxx; x++) {
-                tile_ids[off] = seg_base + (uint32_t)(y * gx + x);
-                vals[off] = g[k];
-                off++;
+        for (int q = 0; q < kEsGpt; q++) {
+            const int li = threadIdx.x * kEsGpt + q;
+            cnt[q] = 0;
+            rminx[q] = rminy[q] = 0;
+            rw[q] = 1;
+            if (li < n_g) {
+                const uint32_t g = __ldg(perm + seg_off + g0 + li);
+                s_gidx[li] = g;
+                const uint32_t t = __ldg(tt + seg_off + g);
+                if (t) {
+                    const float4 p = ldg4(P0 + seg_off + g);
+                    int minx, miny, maxx, maxy;
+                    ex_tile_rect(p.x, p.y, __float_as_int(p.w), gx, gy, minx, miny, maxx, maxy);
+                    rminx[q] = minx;
+                    rminy[q] = miny;
+                    rw[q] = maxx - minx;
+                    cnt[q] = t;
+                }
             }
+            acc += cnt[q];
+        }
+        uint32_t total_pairs;
+        const uint32_t my_off = block_excl_scan_256(acc, s_scan, total_pairs);
+        // warp w owns the contiguous pair range [w*per_warp, (w+1)*per_warp) of the chunk, consumed in
+        // windows of kEsWin pairs; all warps step through their windows together
+        const uint32_t per_warp = (total_pairs + kEsWarps - 1) / kEsWarps;
+        const uint32_t n_win = (per_warp + kEsWin - 1) / kEsWin;
+        const uint32_t my_lo = min(total_pairs, (uint32_t)warp * per_warp);
+        const uint32_t my_n = min(total_pairs, (uint32_t)(warp + 1) * per_warp) - my_lo;
+
+        for (int sweep = 0; sweep < 2; sweep++) {
+            if (sweep == 1) {
+                // ---- per tile: offsets of the warps inside the chunk, chunk aggregate, look-back
+                __syncthreads();
+                for (int t = threadIdx.x; t < tiles; t += kEsThreads) {
+                    uint32_t off = 0;
+#pragma unroll
+                    for (int w = 0; w < kEsWarps; w++) {
+                        const uint32_t c = s_wcnt[w * tp + t];
+                        s_wcnt[w * tp + t] = (uint16_t)off;
+                        off += c;
+                    }
+                    volatile uint32_t* my_status = status + (size_t)chunk * tiles;
+                    my_status[t] = (lc == 0 ? kFlagPrefix : kFlagAgg) | off;
+                    uint32_t excl = 0;
+                    if (lc > 0) {
+                        uint32_t look = chunk - 1;
+                        uint32_t spins = 0;
+                        while (true) {
+                            if (++spins > (1u << 28)) __trap();  // a lost predecessor is a bug: fail, do not hang
+                            const uint32_t sv = status[(size_t)look * tiles + t];
+                            const uint32_t flag = sv & kFlagMask;
+                            if (flag == kFlagPrefix) {
+                                excl += sv & kValMask;
+                                break;
+                            }
+                            if (flag == kFlagAgg) {
+                                excl += sv & kValMask;
+                                look--;
+                            }
+                        }
+                        my_status[t] = kFlagPrefix | ((excl + off) & kValMask);
+                    }
+                    s_base[t] = __ldg(tile_start + (size_t)seg * tiles + t) + excl;
+                }
+            }
+            for (uint32_t win = 0; win < n_win; win++) {
+                __syncthreads();  // the pair windows are free (and, for sweep 1, s_base / s_wcnt are final)
+                // ---- expand the pairs that fall into the current window of their owning warp
+#pragma unroll
+                for (int q = 0; q < kEsGpt; q++) {
+                    if (cnt[q] == 0) continue;
+                    uint32_t j = my_off;
+#pragma unroll
+                    for (int qq = 0; qq < kEsGpt; qq++)
+                        if (qq < q) j += cnt[qq];
+                    uint32_t owner = j / per_warp;
+                    uint32_t wi = j - owner * per_warp;
+                    int cx = 0, cy = 0;
+                    const uint32_t li = (uint32_t)(threadIdx.x * kEsGpt + q);
+                    for (uint32_t k = 0; k < cnt[q]; k++) {
+                        if ((wi >> kEsWinShift) == win) {
+                            const uint32_t tile = (uint32_t)((rminy[q] + cy) * gx + rminx[q] + cx);
+                            s_pair[owner * kEsWin + (wi & (kEsWin - 1))] = (tile << 10) | li;
+                        }
+                        if (++cx == rw[q]) {
+                            cx = 0;
+                            cy++;
+                        }
+                        if (++wi == per_warp) {
+                            wi = 0;
+                            owner++;
+                        }
+                    }
+                }
+                __syncthreads();
+                // ---- my warp's window, 32 pairs per step, in pair order
+                const uint32_t w_lo = win * kEsWin;
+                const uint32_t w_n = (my_n > w_lo) ? min((uint32_t)kEsWin, my_n - w_lo) : 0u;
+                const uint32_t* wp = s_pair + warp * kEsWin;
+                uint16_t* wc = s_wcnt + warp * tp;
+                for (uint32_t s0 = 0; s0 < w_n; s0 += 32) {
+                    const bool valid = s0 + lane < w_n;
+                    const uint32_t pr = valid ? wp[s0 + lane] : 0u;
+                    const uint32_t t = pr >> 10;
+                    if (sweep == 0) {
+                        // counting only: order does not matter, a packed 16-bit shared atomic does it
+                        if (valid)
+                            atomicAdd(reinterpret_cast<uint32_t*>(wc) + (t >> 1), 1u << (16 * (t & 1u)));
+                    } else {
+                        uint32_t peers = __ballot_sync(0xffffffffu, valid);
+                        for (int b = 0; b < tile_bits; b++) {
+                            const bool bit = (t >> b) & 1u;
+                            const uint32_t bal = __ballot_sync(0xffffffffu, bit);
+                            peers &= bit ? bal : ~bal;
+                        }
+                        const int leader = __ffs(peers) - 1;
+                        uint32_t pre = 0;
+                        if (valid && lane == leader) {
+                            pre = wc[t];
+                            wc[t] = (uint16_t)(pre + __popc(peers));
+                        }
+                        pre = __shfl_sync(0xffffffffu, pre, leader & 31);
+                        if (valid) vals_out[s_base[t] + pre + __popc(peers & lanemask_lt)] = s_gidx[pr & 1023u];
+                        __syncwarp();
+                    }
+                }
+            }
+        }
+        __syncthreads();
     }
 }
 
@@ -376,38 +551,20 @@ __global__ void __launch_bounds__(kRsThreads, 4) rs_onesweep_kernel(
     }
 }
 
-// ---------------------------------------------------------------------------------- tile ranges
-__global__ void __launch_bounds__(256) tile_ranges_kernel(const uint32_t* __restrict__ sorted_tiles,
-                                                          const uint32_t* __restrict__ sort_count,
-                                                          uint32_t* __restrict__ ranges) {
-    const uint32_t count = *sort_count;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
-        const uint32_t cur = __ldg(sorted_tiles + i);
-        if (i == 0) {
-            ranges[2 * cur] = 0;
-        } else {
-            const uint32_t prev = __ldg(sorted_tiles + i - 1);
-            if (cur != prev) {
-                ranges[2 * prev + 1] = i;
-                ranges[2 * cur] = i;
-            }
-        }
-        if (i == count - 1) ranges[2 * cur + 1] = count;
-    }
-}
-
-// the published 64-bit key of every pair of a list, on request (parity tests, debug taps)
-__global__ void __launch_bounds__(256) rebuild_keys_kernel(int N, int tiles, const uint32_t* __restrict__ tile_ids,
+// the published 64-bit key of every sorted pair, on request (parity tests, debug taps): one thread per
+// (global tile, position) via the range table
+__global__ void __launch_bounds__(256) rebuild_keys_kernel(int N, int tiles, long long n_tiles_total,
+                                                           const uint32_t* __restrict__ ranges,
                                                            const uint32_t* __restrict__ vals,
                                                            const float4* __restrict__ P0,
-                                                           const uint32_t* __restrict__ sort_count,
                                                            uint64_t* __restrict__ keys64) {
-    const uint32_t count = *sort_count;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
-        const uint32_t t = tile_ids[i], g = vals[i];
-        const uint32_t seg = t / (uint32_t)tiles;
-        const float4 p = ldg4(P0 + (size_t)seg * N + g);
-        keys64[i] = ((uint64_t)t << 32) | (uint64_t)__float_as_uint(p.z);
+    for (long long tg = blockIdx.x; tg < n_tiles_total; tg += gridDim.x) {
+        const uint32_t lo = ranges[2 * tg], hi = ranges[2 * tg + 1];
+        const long long seg = tg / tiles;
+        for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
+            const float4 p = ldg4(P0 + seg * N + vals[i]);
+            keys64[i] = ((uint64_t)tg << 32) | (uint64_t)__float_as_uint(p.z);
+        }
     }
 }
 
@@ -423,29 +580,29 @@ static inline int tile_bits_for(int S, int width, int height) {
 struct BinningWs {
     // zeroed per call
     uint32_t* hist_depth;     // [S][4][256]
-    uint32_t* hist_tile;      // [tile passes][256]
-    uint32_t* tile_counter;   // [8]
+    uint32_t* counters;       // [8]: 0..3 depth-sort tile counters, 4 emit-scatter chunk counter
     uint32_t* sort_count;     // [4]
+    uint32_t* tile_cnt;       // [S*tiles]
     uint32_t* status_depth;   // [4][S*tiles_per_seg][256]
-    uint32_t* status_tile;    // [tile passes][max tiles][256]
+    uint32_t* status_emit;    // [S*chunks_per_seg][tiles]
     size_t zero_bytes;
     // scratch
-    uint32_t* tile_sums;
+    uint32_t* tile_start;     // [S*tiles]
     uint32_t* dkeys[2];       // depth keys ping-pong  [S*N]
     uint32_t* perm[2];        // Gaussian index ping-pong [S*N]
-    uint32_t* tkeys[2];       // tile ids ping-pong [capacity]
-    uint32_t* tvals;          // second value buffer [capacity] (the other one is the caller's output)
-    size_t status_depth_stride, status_tile_stride, total;
-    int tile_passes;
+    size_t status_depth_stride, total;
+    int tiles, tile_bits;
 };
 
 static BinningWs carve(void* base, int S, int N, int width, int height, size_t capacity) {
+    (void)capacity;
     BinningWs w{};
     const size_t count = (size_t)S * N;
-    const size_t n_scan_tiles = (count + kScanTile - 1) / kScanTile + 1;
-    w.tile_passes = (tile_bits_for(S, width, height) + 7) / 8;
+    w.tiles = ((width + kTile - 1) / kTile) * ((height + kTile - 1) / kTile);
+    w.tile_bits = 1;
+    while ((1 << w.tile_bits) < w.tiles) w.tile_bits++;
     const size_t depth_tiles = (size_t)S * (((size_t)N + kRsTile - 1) / kRsTile);
-    const size_t max_pair_tiles = (capacity + kRsTile - 1) / kRsTile + 1;
+    const size_t emit_chunks = (size_t)S * (((size_t)N + kEsChunk - 1) / kEsChunk);
     size_t off = 0;
     auto take = [&](size_t bytes) {
         unsigned char* p = base ? (unsigned char*)base + off : nullptr;
@@ -453,36 +610,32 @@ static BinningWs carve(void* base, int S, int N, int width, int height, size_t c
         return p;
     };
     w.hist_depth = (uint32_t*)take(sizeof(uint32_t) * (size_t)S * 4 * kRadix);
-    w.hist_tile = (uint32_t*)take(sizeof(uint32_t) * kMaxPasses * kRadix);
-    w.tile_counter = (uint32_t*)take(sizeof(uint32_t) * 8);
+    w.counters = (uint32_t*)take(sizeof(uint32_t) * 8);
     w.sort_count = (uint32_t*)take(sizeof(uint32_t) * 4);
+    w.tile_cnt = (uint32_t*)take(sizeof(uint32_t) * (size_t)S * w.tiles);
     w.status_depth_stride = depth_tiles * kRadix;
     w.status_depth = (uint32_t*)take(sizeof(uint32_t) * w.status_depth_stride * 4);
-    w.status_tile_stride = max_pair_tiles * kRadix;
-    w.status_tile = (uint32_t*)take(sizeof(uint32_t) * w.status_tile_stride * w.tile_passes);
+    w.status_emit = (uint32_t*)take(sizeof(uint32_t) * emit_chunks * w.tiles);
     w.zero_bytes = off;
-    w.tile_sums = (uint32_t*)take(sizeof(uint32_t) * n_scan_tiles);
+    w.tile_start = (uint32_t*)take(sizeof(uint32_t) * (size_t)S * w.tiles);
     for (int i = 0; i < 2; i++) w.dkeys[i] = (uint32_t*)take(sizeof(uint32_t) * count);
     for (int i = 0; i < 2; i++) w.perm[i] = (uint32_t*)take(sizeof(uint32_t) * count);
-    for (int i = 0; i < 2; i++) w.tkeys[i] = (uint32_t*)take(sizeof(uint32_t) * capacity);
-    w.tvals = (uint32_t*)take(sizeof(uint32_t) * capacity);
     w.total = off;
     return w;
 }
 
-// value buffer that pass p of the tile sort READS (p = tile_passes: the final result).  The two
-// buffers alternate and the LAST pass must write the caller's d_sorted_vals, which fixes where the
-// emission has to put the unsorted values.
-static inline uint32_t* tile_vals_buffer(const BinningWs& w, uint32_t* d_sorted_vals, int p) {
-    return ((w.tile_passes - p) & 1) ? w.tvals : d_sorted_vals;
-}
-
-static int set_onesweep_attr() {
-    static bool attr_set = false;
-    if (!attr_set) {
+static int set_kernel_attrs(int tiles) {
+    static bool rs_set = false;
+    if (!rs_set) {
         OMFS_CUDA(cudaFuncSetAttribute(rs_onesweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)sizeof(RsSmem)));
-        attr_set = true;
+        rs_set = true;
+    }
+    static int es_bytes = 0;
+    const int need = (int)emit_scatter_smem(tiles);
+    if (need > es_bytes) {
+        OMFS_CUDA(cudaFuncSetAttribute(emit_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, need));
+        es_bytes = need;
     }
     return OMFS_OK;
 }
@@ -492,7 +645,7 @@ int binning_depth_sort(int S, int N, int width, int height, size_t capacity, con
                        void* d_workspace, cudaStream_t stream) {
     BinningWs w = carve(d_workspace, S, N, width, height, capacity);
     OMFS_CUDA(cudaMemsetAsync(d_workspace, 0, w.zero_bytes, stream));
-    int rc = set_onesweep_attr();
+    int rc = set_kernel_attrs(w.tiles);
     if (rc) return rc;
     // the depth exponent byte (bits 24..31) is nearly constant inside a warp's 32 keys
     rs_histogram_kernel<<<dim3(8, S), 256, 0, stream>>>(d_depth_keys, nullptr, (uint32_t)N, 4, 0x8u, w.hist_depth);
@@ -505,7 +658,7 @@ int binning_depth_sort(int S, int N, int width, int height, size_t capacity, con
         uint32_t* vout = w.perm[(p + 1) & 1];
         rs_onesweep_kernel<<<kNumSMs * 4, kRsThreads, sizeof(RsSmem), stream>>>(
             kin, vin, kout, vout, nullptr, (uint32_t)N, (uint32_t)S, 8 * p, w.hist_depth + p * kRadix, 4 * kRadix,
-            w.tile_counter + p, w.status_depth + (size_t)p * w.status_depth_stride);
+            w.counters + p, w.status_depth + (size_t)p * w.status_depth_stride);
         count_launch();
         kin = kout;
         vin = vout;
@@ -514,68 +667,57 @@ int binning_depth_sort(int S, int N, int width, int height, size_t capacity, con
     return OMFS_OK;
 }
 
-// ---- stage 2: offsets in depth order + emission of (tile id, Gaussian) pairs
-int binning_scan_emit(int S, int N, int width, int height, size_t capacity, const float* d_P0,
-                      const uint32_t* d_tiles_touched, uint32_t* d_sorted_vals, uint32_t* d_ranges,
-                      uint32_t* d_num_pairs, int* d_status_flag, unsigned long long* d_pair_accum,
-                      void* d_workspace, cudaStream_t stream) {
+// ---- stage 2: tile counts, their scan (= tile ranges, pair count)
+int binning_tile_ranges(int S, int N, int width, int height, size_t capacity, const float* d_P0,
+                        const uint32_t* d_tiles_touched, uint32_t* d_ranges, uint32_t* d_num_pairs,
+                        int* d_status_flag, unsigned long long* d_pair_accum, void* d_workspace,
+                        cudaStream_t stream) {
     BinningWs w = carve(d_workspace, S, N, width, height, capacity);
-    const long long count = (long long)S * N;
-    const int n_scan_tiles = ceil_div(count, kScanTile);
-    const long long tiles_total = (long long)S * ((width + kTile - 1) / kTile) * ((height + kTile - 1) / kTile);
-    if (d_ranges) OMFS_CUDA(cudaMemsetAsync(d_ranges, 0, sizeof(uint32_t) * 2 * (size_t)tiles_total, stream));
-    scan_tile_sums_kernel<<<n_scan_tiles, kScanThreads, 0, stream>>>(count, N, d_tiles_touched, w.perm[0],
-                                                                    w.tile_sums);
-    scan_sums_kernel<<<1, 1024, 0, stream>>>(n_scan_tiles, w.tile_sums, d_num_pairs, (unsigned long long)capacity,
-                                             d_status_flag, w.sort_count, d_pair_accum);
-    scan_emit_kernel<<<n_scan_tiles, kScanThreads, 0, stream>>>(count, N, width, height, d_tiles_touched, w.perm[0],
-                                                               w.tile_sums, (const float4*)d_P0, w.sort_count,
-                                                               w.tkeys[0], tile_vals_buffer(w, d_sorted_vals, 0));
-    count_launch(3);
-    OMFS_LAUNCH_CHECK();
-    return OMFS_OK;
-}
-
-// ---- stage 3: stable sort of the pairs by tile id.  Sorted values land in d_sorted_vals.
-int binning_tile_sort(int S, int N, int width, int height, size_t capacity, uint32_t* d_sorted_vals,
-                      void* d_workspace, const uint32_t** d_sorted_tiles_out, cudaStream_t stream) {
-    BinningWs w = carve(d_workspace, S, N, width, height, capacity);
-    const int passes = w.tile_passes;
-    int rc = set_onesweep_attr();
-    if (rc) return rc;
-    // every tile-id byte above the lowest is shared by long runs of consecutive pairs
-    rs_histogram_kernel<<<dim3(kNumSMs * 4, 1), 256, 0, stream>>>(w.tkeys[0], w.sort_count, 0u, passes, 0xEu,
-                                                                 w.hist_tile);
-    rs_scan_hist_kernel<<<passes, 256, 0, stream>>>(w.hist_tile);
-    count_launch(2);
-    for (int p = 0; p < passes; p++) {
-        rs_onesweep_kernel<<<kNumSMs * 4, kRsThreads, sizeof(RsSmem), stream>>>(
-            w.tkeys[p & 1], tile_vals_buffer(w, d_sorted_vals, p), w.tkeys[(p + 1) & 1],
-            tile_vals_buffer(w, d_sorted_vals, p + 1), w.sort_count, 0u, 1u, 8 * p, w.hist_tile + p * kRadix, 0u,
-            w.tile_counter + 4 + p, w.status_tile + (size_t)p * w.status_tile_stride);
-        count_launch();
+    if (w.tiles > 12288) {
+        set_error("binning: %d tiles per frame exceed the shared-memory histogram (max 12288)", w.tiles);
+        return OMFS_ERR_INVALID;
     }
+    tile_count_kernel<<<dim3(8, S), 256, sizeof(uint32_t) * w.tiles, stream>>>(N, width, height, w.tiles,
+                                                                              (const float4*)d_P0, d_tiles_touched,
+                                                                              w.tile_cnt);
+    tile_scan_kernel<<<1, 1024, 0, stream>>>(S * w.tiles, w.tile_cnt, w.tile_start, d_ranges, d_num_pairs,
+                                             (unsigned long long)capacity, d_status_flag, w.sort_count,
+                                             d_pair_accum);
+    count_launch(2);
     OMFS_LAUNCH_CHECK();
-    *d_sorted_tiles_out = w.tkeys[passes & 1];
     return OMFS_OK;
 }
 
-int binning_ranges(int S, int N, int width, int height, size_t capacity, const uint32_t* d_sorted_tiles,
-                   uint32_t* d_ranges, void* d_workspace, cudaStream_t stream) {
+// ---- stage 3: fused emission + counting sort by tile: Gaussian indices land at their final positions
+int binning_emit_scatter(int S, int N, int width, int height, size_t capacity, const float* d_P0,
+                         const uint32_t* d_tiles_touched, uint32_t* d_sorted_vals, void* d_workspace,
+                         cudaStream_t stream) {
     BinningWs w = carve(d_workspace, S, N, width, height, capacity);
-    tile_ranges_kernel<<<kNumSMs * 4, 256, 0, stream>>>(d_sorted_tiles, w.sort_count, d_ranges);
+    if (w.tiles > (1 << 22)) {
+        set_error("binning: too many tiles per frame (%d)", w.tiles);
+        return OMFS_ERR_INVALID;
+    }
+    int rc = set_kernel_attrs(w.tiles);
+    if (rc) return rc;
+    const size_t smem = emit_scatter_smem(w.tiles);
+    if (smem > 227 * 1024) {
+        set_error("binning: %d tiles per frame need %zu bytes of shared memory", w.tiles, smem);
+        return OMFS_ERR_INVALID;
+    }
+    emit_scatter_kernel<<<kNumSMs * 4, kEsThreads, smem, stream>>>(
+        S, N, width, height, w.tiles, w.tile_bits, w.perm[0], d_tiles_touched, (const float4*)d_P0, w.tile_start,
+        w.sort_count, w.counters + 4, w.status_emit, d_sorted_vals);
     count_launch();
     OMFS_LAUNCH_CHECK();
     return OMFS_OK;
 }
 
-int binning_rebuild_keys(int S, int N, int width, int height, size_t capacity, const uint32_t* d_tile_ids,
+int binning_rebuild_keys(int S, int N, int width, int height, size_t capacity, const uint32_t* d_ranges,
                          const uint32_t* d_vals, const float* d_P0, uint64_t* d_keys64, void* d_workspace,
                          cudaStream_t stream) {
     BinningWs w = carve(d_workspace, S, N, width, height, capacity);
-    const int tiles = ((width + kTile - 1) / kTile) * ((height + kTile - 1) / kTile);
-    rebuild_keys_kernel<<<kNumSMs * 4, 256, 0, stream>>>(N, tiles, d_tile_ids, d_vals, (const float4*)d_P0,
-                                                         w.sort_count, d_keys64);
+    rebuild_keys_kernel<<<kNumSMs * 8, 256, 0, stream>>>(N, w.tiles, (long long)S * w.tiles, d_ranges, d_vals,
+                                                         (const float4*)d_P0, d_keys64);
     count_launch();
     OMFS_LAUNCH_CHECK();
     return OMFS_OK;
@@ -595,9 +737,9 @@ extern "C" int omfs_binning_sort_bits(int S, int width, int height) { return 32 
 
 extern "C" int omfs_binning(int S, int N, int width, int height, size_t capacity, const float* d_P0,
                             const uint32_t* d_depth_keys, const uint32_t* d_tiles_touched,
-                            uint32_t* d_sorted_vals, uint64_t* d_sorted_keys, uint64_t* d_emitted_keys,
-                            uint32_t* d_emitted_vals, uint32_t* d_ranges, uint32_t* d_num_pairs, int* d_status_flag,
-                            void* d_workspace, size_t workspace_bytes, void* stream_) {
+                            uint32_t* d_sorted_vals, uint64_t* d_sorted_keys, uint32_t* d_ranges,
+                            uint32_t* d_num_pairs, int* d_status_flag, void* d_workspace, size_t workspace_bytes,
+                            void* stream_) {
     OMFS_REQUIRE(S > 0 && N > 0 && width > 0 && height > 0, "bad sizes");
     OMFS_REQUIRE(S <= 65535, "at most 65535 segments per call");
     OMFS_REQUIRE(capacity > 0 && capacity < (1ull << 30), "capacity must be in (0, 2^30)");
@@ -609,28 +751,16 @@ extern "C" int omfs_binning(int S, int N, int width, int height, size_t capacity
     OMFS_REQUIRE(workspace_bytes >= carve(nullptr, S, N, width, height, capacity).total,
                  "workspace too small (omfs_binning_workspace_bytes)");
     cudaStream_t stream = (cudaStream_t)stream_;
-    BinningWs w = carve(d_workspace, S, N, width, height, capacity);
     int rc = binning_depth_sort(S, N, width, height, capacity, d_depth_keys, d_workspace, stream);
     if (rc) return rc;
-    rc = binning_scan_emit(S, N, width, height, capacity, d_P0, d_tiles_touched, d_sorted_vals, d_ranges,
-                           d_num_pairs, d_status_flag, nullptr, d_workspace, stream);
+    rc = binning_tile_ranges(S, N, width, height, capacity, d_P0, d_tiles_touched, d_ranges, d_num_pairs,
+                             d_status_flag, nullptr, d_workspace, stream);
     if (rc) return rc;
-    if (d_emitted_keys) {
-        const uint32_t* ev = tile_vals_buffer(w, d_sorted_vals, 0);
-        rc = binning_rebuild_keys(S, N, width, height, capacity, w.tkeys[0], ev, d_P0, d_emitted_keys, d_workspace,
-                                  stream);
-        if (rc) return rc;
-        if (d_emitted_vals)
-            OMFS_CUDA(cudaMemcpyAsync(d_emitted_vals, ev, sizeof(uint32_t) * capacity, cudaMemcpyDeviceToDevice,
-                                      stream));
-    }
-    const uint32_t* sorted_tiles = nullptr;
-    rc = binning_tile_sort(S, N, width, height, capacity, d_sorted_vals, d_workspace, &sorted_tiles, stream);
-    if (rc) return rc;
-    rc = binning_ranges(S, N, width, height, capacity, sorted_tiles, d_ranges, d_workspace, stream);
+    rc = binning_emit_scatter(S, N, width, height, capacity, d_P0, d_tiles_touched, d_sorted_vals, d_workspace,
+                              stream);
     if (rc) return rc;
     if (d_sorted_keys)
-        rc = binning_rebuild_keys(S, N, width, height, capacity, sorted_tiles, d_sorted_vals, d_P0, d_sorted_keys,
+        rc = binning_rebuild_keys(S, N, width, height, capacity, d_ranges, d_sorted_vals, d_P0, d_sorted_keys,
                                   d_workspace, stream);
     return rc;
 }

@@ -157,7 +157,7 @@ struct omfs_session {
     int seg_table_fpb = -1, seg_table_views = -1;
 };
 
-enum Stage { kStFlame = 0, kStFaceFrames, kStBindPre, kStDepthSort, kStScanEmit, kStTileSort, kStRanges, kStComposite, kStCount };
+enum Stage { kStFlame = 0, kStFaceFrames, kStBindPre, kStDepthSort, kStTileRanges, kStEmitScatter, kStComposite, kStCount };
 
 static int upload(DevBuf& b, const void* h, size_t bytes, cudaStream_t st) {
     int rc = b.ensure(bytes);
@@ -442,20 +442,17 @@ static int render_core(omfs_session* s, int T, int n_views, const float* p_expr,
             if ((rc = mark(kStDepthSort))) return rc;
             if ((rc = binning_depth_sort(S, N, W, H, s->capacity, s->depth_keys.as<uint32_t>(), s->ws.p, st)))
                 return rc;
-            if ((rc = mark(kStScanEmit))) return rc;
-            if ((rc = binning_scan_emit(S, N, W, H, s->capacity, s->P0.as<float>(), s->tt.as<uint32_t>(),
-                                        s->vals.as<uint32_t>(), s->ranges.as<uint32_t>(), d_num_pairs, d_flag,
-                                        d_pair_accum, s->ws.p, st)))
+            if ((rc = mark(kStTileRanges))) return rc;
+            if ((rc = binning_tile_ranges(S, N, W, H, s->capacity, s->P0.as<float>(), s->tt.as<uint32_t>(),
+                                          s->ranges.as<uint32_t>(), d_num_pairs, d_flag, d_pair_accum, s->ws.p,
+                                          st)))
                 return rc;
-            if ((rc = mark(kStTileSort))) return rc;
-            const uint32_t* sorted_tiles = nullptr;
-            if ((rc = binning_tile_sort(S, N, W, H, s->capacity, s->vals.as<uint32_t>(), s->ws.p, &sorted_tiles, st)))
-                return rc;
-            if ((rc = mark(kStRanges))) return rc;
-            if ((rc = binning_ranges(S, N, W, H, s->capacity, sorted_tiles, s->ranges.as<uint32_t>(), s->ws.p, st)))
+            if ((rc = mark(kStEmitScatter))) return rc;
+            if ((rc = binning_emit_scatter(S, N, W, H, s->capacity, s->P0.as<float>(), s->tt.as<uint32_t>(),
+                                           s->vals.as<uint32_t>(), s->ws.p, st)))
                 return rc;
             if (s->cfg.debug_keys &&
-                (rc = binning_rebuild_keys(S, N, W, H, s->capacity, sorted_tiles, s->vals.as<uint32_t>(),
+                (rc = binning_rebuild_keys(S, N, W, H, s->capacity, s->ranges.as<uint32_t>(), s->vals.as<uint32_t>(),
                                            s->P0.as<float>(), s->keys64.as<uint64_t>(), s->ws.p, st)))
                 return rc;
             // the image buffer may still be draining to the host from two batches ago
@@ -628,7 +625,7 @@ extern "C" int omfs_session_tap(omfs_session* s, const char* name, void** d_ptr,
 
 // Per-stage device time, accumulated while profiling is on (it costs a host sync per batch, so the
 // headline throughput is measured with profiling off).  out_ms/out_calls: flame, face_frames,
-// bind_preprocess, depth_sort, scan+emit, tile_sort, ranges, composite.
+// bind_preprocess, depth_sort, tile_ranges, emit_scatter, composite.
 extern "C" int omfs_session_set_profiling(omfs_session* s, int on) {
     OMFS_REQUIRE(s, "null argument");
     s->profiling = on != 0;

@@ -45,15 +45,14 @@ inline void count_launch(int n = 1) { g_launches += (unsigned long long)n; }
 // binning stages (binning.cu), called separately by the session so that it can time them
 int binning_depth_sort(int S, int N, int width, int height, size_t capacity, const uint32_t* d_depth_keys,
                        void* d_workspace, cudaStream_t stream);
-int binning_scan_emit(int S, int N, int width, int height, size_t capacity, const float* d_P0,
-                      const uint32_t* d_tiles_touched, uint32_t* d_sorted_vals, uint32_t* d_ranges,
-                      uint32_t* d_num_pairs, int* d_status_flag, unsigned long long* d_pair_accum,
-                      void* d_workspace, cudaStream_t stream);
-int binning_tile_sort(int S, int N, int width, int height, size_t capacity, uint32_t* d_sorted_vals,
-                      void* d_workspace, const uint32_t** d_sorted_tiles_out, cudaStream_t stream);
-int binning_ranges(int S, int N, int width, int height, size_t capacity, const uint32_t* d_sorted_tiles,
-                   uint32_t* d_ranges, void* d_workspace, cudaStream_t stream);
-int binning_rebuild_keys(int S, int N, int width, int height, size_t capacity, const uint32_t* d_tile_ids,
+int binning_tile_ranges(int S, int N, int width, int height, size_t capacity, const float* d_P0,
+                        const uint32_t* d_tiles_touched, uint32_t* d_ranges, uint32_t* d_num_pairs,
+                        int* d_status_flag, unsigned long long* d_pair_accum, void* d_workspace,
+                        cudaStream_t stream);
+int binning_emit_scatter(int S, int N, int width, int height, size_t capacity, const float* d_P0,
+                         const uint32_t* d_tiles_touched, uint32_t* d_sorted_vals, void* d_workspace,
+                         cudaStream_t stream);
+int binning_rebuild_keys(int S, int N, int width, int height, size_t capacity, const uint32_t* d_ranges,
                          const uint32_t* d_vals, const float* d_P0, uint64_t* d_keys64, void* d_workspace,
                          cudaStream_t stream);
 

@@ -5,20 +5,18 @@
 // only approximate operation is ex2.approx (the oracle uses exp2f), which moves the image by ~1e-7.
 //
 // Structure
-//   * the tile's depth-sorted Gaussian list is consumed in chunks of 256: each thread gathers one
-//     Gaussian's 9 compositing floats (centre, pre-scaled conic, log2 opacity, colour) from the
-//     [S,N] float4 streams (L2-resident: every Gaussian is referenced by ~3.6 tiles) and stages
-//     them in shared memory; the per-pixel loop then reads them as warp-wide broadcasts;
-//   * a warp owns an 8x4 pixel block (not a 16x2 strip) and culls per block: each lane tests one
-//     staged Gaussian's alpha >= 1/255 footprint (a conservative box, cull_box below) against the
-//     block, a ballot gives the ~1/3 of the tile's Gaussians that can touch it, and only those are
-//     evaluated — the kernel is FP32-issue bound, so skipped (Gaussian, warp) pairs are the win;
-//   * early termination at three levels: per pixel (T < 1e-4), per warp (all 32 pixels done: the
-//     warp stops evaluating and only helps staging), per CTA (__syncthreads_count).
+//   * one warp = one CTA = one 8x4 pixel block; the tile's depth-sorted list is consumed 32 entries
+//     at a time with a lane-parallel footprint cull (extents precomputed by the preprocess kernel and
+//     carried in P2.w) and a ballot, so only the ~1/3 of the tile's Gaussians that can touch the
+//     block are evaluated — the kernel is FP32-issue bound, skipped (Gaussian, warp) pairs are the win;
+//   * no block barriers: a finished pixel block frees its slot at once (see the kernel comment);
+//   * early termination per pixel (T < 1e-4) and per warp (all 32 pixels saturated);
 //   * the optional uint8 HWC image (the save_image quantisation) is produced by the same kernel,
 //     so the frame sink costs no extra pass over HBM.
 // Roofline: 40 B per tile pair against ~256 pixel evaluations of ~10-20
 // instructions each: the FP32/SFU issue rate binds, not HBM; bench.py reports both.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "exact_math.cuh"
 
@@ -34,43 +32,41 @@ struct Ex2Dev {
     __device__ __forceinline__ float operator()(float x) const { return ex2_approx(x); }
 };
 
-constexpr int kChunk = 256;
-
-// Conservative footprint of one Gaussian for the per-warp cull.  A pixel at offset d from the centre
-// can only pass the `e >= log2(1/255)` test if  q(d) = -(ca dx^2 + cb dx dy + cc dy^2) <= Lq with
-// Lq = lo - log2(1/255); minimising q over dy gives dx^2 <= Lq * (-cc) / (ca*cc - cb^2/4) (and the
-// symmetric bound for dy).  The half-widths are inflated (x1.001 + 0.01 px), far more than the 1e-6
-// relative rounding of the kernel's own evaluation, so the cull never drops a contributing pixel:
-// results stay bit-identical to evaluating every (Gaussian, pixel) pair.
-__device__ __forceinline__ float4 cull_box(float gx, float gy, float ca, float cb, float cc, float lo) {
-    const float Lq = lo - kLog2Inv255;
-    const float D = ca * cc - 0.25f * cb * cb;
-    if (!(Lq >= 0.0f)) return make_float4(INFINITY, -INFINITY, INFINITY, -INFINITY);  // can never contribute
-    if (!(D > 0.0f)) return make_float4(-INFINITY, INFINITY, -INFINITY, INFINITY);    // degenerate: always test
-    const float inv = Lq / D;
-    const float bx = sqrtf(fmaxf(-cc * inv, 0.0f)) * 1.001f + 0.01f;
-    const float by = sqrtf(fmaxf(-ca * inv, 0.0f)) * 1.001f + 0.01f;
-    return make_float4(gx - bx, gx + bx, gy - by, gy + by);
+// One warp = one CTA = one 8x4 pixel block of a 16x16 tile (8 CTAs share a tile's list).  There is no
+// block barrier anywhere: a warp that saturates or runs out of Gaussians retires immediately and its
+// SM slot goes to another pixel block, which removes the barrier stalls (the top stall reason of the
+// 256-thread version: ncu smsp__average_warps_issue_stalled_barrier 7.1 per issue).
+//
+// Per round of 32 list entries: lane l fetches entry l (index, centre, colour + packed cull extents),
+// tests the Gaussian's alpha >= 1/255 footprint box against the warp's pixel block, and a ballot yields
+// the entries worth evaluating, still in depth order.  Only those lanes fetch the conic and publish
+// their 9 floats to the warp's shared-memory slots; every lane then evaluates the survivors with
+// broadcast reads.  The next round's gathers are issued before the current round is evaluated, so the
+// L2 latency of the dependent index -> record loads overlaps the arithmetic.
+__device__ __forceinline__ void unpack_extents(float w, float& bx, float& by) {
+    const uint32_t u = __float_as_uint(w);
+    const __half2 h = *reinterpret_cast<const __half2*>(&u);
+    bx = __low2float(h);
+    by = __high2float(h);
 }
 
-__global__ void __launch_bounds__(256) composite_kernel(int N, int width, int height, const float4* __restrict__ P0,
-                                                        const float4* __restrict__ P1,
-                                                        const float4* __restrict__ P2,
-                                                        const uint32_t* __restrict__ vals,
-                                                        const uint2* __restrict__ ranges, float bg0, float bg1,
-                                                        float bg2, float* __restrict__ image,
-                                                        uint8_t* __restrict__ image_u8) {
-    __shared__ float4 s_a[kChunk];     // gx gy ca cb
-    __shared__ float4 s_b[kChunk];     // cc lo r g
-    __shared__ float s_c[kChunk];      // b
-    __shared__ float4 s_box[kChunk];   // xmin xmax ymin ymax of the alpha >= 1/255 footprint
+__global__ void __launch_bounds__(32) composite_kernel(int N, int width, int height, const float4* __restrict__ P0,
+                                                       const float4* __restrict__ P1,
+                                                       const float4* __restrict__ P2,
+                                                       const uint32_t* __restrict__ vals,
+                                                       const uint2* __restrict__ ranges, float bg0, float bg1,
+                                                       float bg2, float* __restrict__ image,
+                                                       uint8_t* __restrict__ image_u8) {
+    __shared__ float4 s_a[32];  // gx gy ca cb
+    __shared__ float4 s_b[32];  // cc lo r g
+    __shared__ float s_c[32];   // b
 
     const int gxt = (width + kTile - 1) / kTile, gyt = (height + kTile - 1) / kTile;
-    const int tile = blockIdx.x, seg = blockIdx.y;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    // a warp owns an 8x4 pixel block of the tile
-    const int bx0 = (tile % gxt) * kTile + (warp & 1) * 8;
-    const int by0 = (tile / gxt) * kTile + (warp >> 1) * 4;
+    const int tile = blockIdx.x >> 3, sub = blockIdx.x & 7, seg = blockIdx.y;
+    const int lane = threadIdx.x;
+    const int bx0 = (tile % gxt) * kTile + (sub & 1) * 8;
+    const int by0 = (tile / gxt) * kTile + (sub >> 1) * 4;
+    if (bx0 >= width || by0 >= height) return;  // pixel block entirely outside the image
     const int px = bx0 + (lane & 7);
     const int py = by0 + (lane >> 3);
     const bool inside = px < width && py < height;
@@ -83,48 +79,60 @@ __global__ void __launch_bounds__(256) composite_kernel(int N, int width, int he
 
     float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
     bool done = !inside;
-    for (uint32_t base = range.x; base < range.y; base += kChunk) {
-        // barrier (protects the staging buffers) + CTA-level early out
-        if (__syncthreads_count(done) == 256) break;
-        const uint32_t idx = base + tid;
-        if (idx < range.y) {
-            const uint32_t g = __ldg(vals + idx);
-            const float4 a = ldg4(p0 + g), b = ldg4(p1 + g), c = ldg4(p2 + g);
-            s_a[tid] = make_float4(a.x, a.y, b.x, b.y);
-            s_b[tid] = make_float4(b.z, b.w, c.x, c.y);
-            s_c[tid] = c.z;
-            s_box[tid] = cull_box(a.x, a.y, b.x, b.y, b.z, b.w);
+
+    // software pipeline: (g, a, c) of the round being evaluated, (gn, an, cn) of the next one
+    uint32_t g = 0;
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), c = a;
+    if (range.x + lane < range.y) {
+        g = __ldg(vals + range.x + lane);
+        a = ldg4(p0 + g);
+        c = ldg4(p2 + g);
+    }
+    for (uint32_t base = range.x; base < range.y; base += 32) {
+        const bool have = base + lane < range.y;
+        uint32_t gn = 0;
+        float4 an = make_float4(0.f, 0.f, 0.f, 0.f), cn = an;
+        if (base + 32 + lane < range.y) {
+            gn = __ldg(vals + base + 32 + lane);
+            an = ldg4(p0 + gn);
+            cn = ldg4(p2 + gn);
         }
-        __syncthreads();
-        const int n = (int)min((uint32_t)kChunk, range.y - base);
-        if (__all_sync(0xffffffffu, done)) continue;  // warp-level: nothing left to shade here
-        // 32 Gaussians at a time: each lane tests ONE Gaussian's footprint against the warp's pixel
-        // block, the ballot is the list of Gaussians worth evaluating (still in depth order)
-        for (int sub = 0; sub < n; sub += 32) {
-            const int jj = sub + lane;
-            bool hit = false;
-            if (jj < n) {
-                const float4 bb = s_box[jj];
-                hit = (bb.y >= wx0) && (bb.x <= wx1) && (bb.w >= wy0) && (bb.z <= wy1);
+        bool hit = false;
+        if (have) {
+            float ex, ey;
+            unpack_extents(c.w, ex, ey);
+            hit = (a.x + ex >= wx0) && (a.x - ex <= wx1) && (a.y + ey >= wy0) && (a.y - ey <= wy1);
+        }
+        uint32_t mask = __ballot_sync(0xffffffffu, hit);
+        if (mask) {
+            if (hit) {
+                const float4 b = ldg4(p1 + g);
+                s_a[lane] = make_float4(a.x, a.y, b.x, b.y);
+                s_b[lane] = make_float4(b.z, b.w, c.x, c.y);
+                s_c[lane] = c.z;
             }
-            uint32_t mask = __ballot_sync(0xffffffffu, hit);
+            __syncwarp();
             bool any_stop = false;
             while (mask) {
-                const int j = sub + __ffs(mask) - 1;
+                const int j = __ffs(mask) - 1;
                 mask &= mask - 1;
                 if (!done) {
-                    const float4 a = s_a[j];
-                    const float4 b = s_b[j];
-                    const int r = ex_blend(a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w, s_c[j], pxf, pyf, T, C0, C1, C2,
-                                           Ex2Dev());
+                    const float4 sa = s_a[j];
+                    const float4 sb = s_b[j];
+                    const int r = ex_blend(sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w, s_c[j], pxf, pyf, T, C0,
+                                           C1, C2, Ex2Dev());
                     if (r == 2) {
                         done = true;
                         any_stop = true;
                     }
                 }
             }
+            __syncwarp();
             if (__any_sync(0xffffffffu, any_stop) && __all_sync(0xffffffffu, done)) break;
         }
+        g = gn;
+        a = an;
+        c = cn;
     }
     if (inside) {
         const float o0 = fmaf(T, bg0, C0), o1 = fmaf(T, bg1, C1), o2 = fmaf(T, bg2, C2);
@@ -173,8 +181,9 @@ extern "C" int omfs_composite(int S, int N, int width, int height, const float* 
     OMFS_REQUIRE(d_image || d_image_u8, "no output requested");
     if (S == 0) return OMFS_OK;
     const int tiles = ((width + kTile - 1) / kTile) * ((height + kTile - 1) / kTile);
-    dim3 grid(tiles, S);
-    composite_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(N, width, height, (const float4*)d_P0,
+    OMFS_REQUIRE((long long)tiles * 8 < (1ll << 31), "too many tiles");
+    dim3 grid(tiles * 8, S);
+    composite_kernel<<<grid, 32, 0, (cudaStream_t)stream>>>(N, width, height, (const float4*)d_P0,
                                                              (const float4*)d_P1, (const float4*)d_P2,
                                                              d_sorted_vals, (const uint2*)d_ranges, bg3[0], bg3[1],
                                                              bg3[2], d_image, d_image_u8);

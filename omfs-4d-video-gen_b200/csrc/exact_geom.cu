@@ -9,10 +9,37 @@
 //     Gaussians that survive culling;
 //   * the per-frame face records (5 float4 per face, ~0.8 MB per frame) are gathered through the
 //     read-only path and stay L2-resident across the segments of a batch.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #include "exact_math.cuh"
 
 namespace omfs {
+
+// Conservative half-extents (pixels) of the region where a Gaussian can pass the compositing test
+// `power2 + lo >= log2(1/255)`, packed as two round-UP halves into P2.w.  With
+// q(d) = -(ca dx^2 + cb dx dy + cc dy^2) and Lq = lo - log2(1/255), minimising q over dy gives
+// dx^2 <= Lq * (-cc) / (ca*cc - cb^2/4) (symmetrically for dy).  The extents are inflated (x1.002 +
+// 0.02 px, then rounded up to half precision), far more than the 1e-6 relative rounding of the
+// compositing arithmetic: the per-warp cull that consumes them can only skip pixels that would have
+// been skipped anyway.  P2.w is an acceleration hint, NOT part of the parity surface (the oracle
+// leaves it 0); a value of +inf means "always test", -inf "never contributes".
+__device__ __forceinline__ float pack_cull_extents(float ca, float cb, float cc, float lo) {
+    const float Lq = lo - kLog2Inv255;
+    const float D = ca * cc - 0.25f * cb * cb;
+    float bx, by;
+    if (!(Lq >= 0.0f)) {
+        bx = by = -INFINITY;
+    } else if (!(D > 0.0f)) {
+        bx = by = INFINITY;
+    } else {
+        const float inv = Lq / D;
+        bx = sqrtf(fmaxf(-cc * inv, 0.0f)) * 1.002f + 0.02f;
+        by = sqrtf(fmaxf(-ca * inv, 0.0f)) * 1.002f + 0.02f;
+    }
+    const __half2 h = __halves2half2(__float2half_ru(bx), __float2half_ru(by));
+    return __uint_as_float(*reinterpret_cast<const uint32_t*>(&h));
+}
 
 // ---------------------------------------------------------------------------------------- U4
 __global__ void __launch_bounds__(256) face_frames_kernel(int T, int V, int F, const float* __restrict__ verts,
@@ -103,7 +130,7 @@ __global__ void __launch_bounds__(256) bind_preprocess_kernel(
     }
     P0[oi] = make_float4(o.px, o.py, o.depth, __int_as_float(o.radius));
     P1[oi] = make_float4(o.ca, o.cb, o.cc, s.w);
-    P2[oi] = make_float4(rgb[0], rgb[1], rgb[2], 0.f);
+    P2[oi] = make_float4(rgb[0], rgb[1], rgb[2], pack_cull_extents(o.ca, o.cb, o.cc, s.w));
     tiles_touched[oi] = o.tiles;
     if (depth_keys) depth_keys[oi] = __float_as_uint(o.depth);  // sort key of the depth sort (binning.cu)
 }

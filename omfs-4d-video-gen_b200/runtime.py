@@ -95,7 +95,7 @@ def load_library():
     L.omfs_flame_fold_subject.argtypes = [c_int, c_int, c_int, vp, vp, vp, vp, vp, vp, vp, vp]
     L.omfs_face_frames.argtypes = [c_int, c_int, c_int, vp, vp, vp, vp]
     L.omfs_bind_preprocess.argtypes = [c_int, c_int, c_int, c_int, c_int] + [vp] * 13
-    L.omfs_binning.argtypes = [c_int, c_int, c_int, c_int, c_size_t] + [vp] * 11 + [c_size_t, vp]
+    L.omfs_binning.argtypes = [c_int, c_int, c_int, c_int, c_size_t] + [vp] * 9 + [c_size_t, vp]
     L.omfs_binning_sort_bits.argtypes = [c_int, c_int, c_int]
     L.omfs_composite.argtypes = [c_int, c_int, c_int, c_int, vp, vp, vp, vp, vp, POINTER(c_float), vp, vp, vp]
     L.omfs_to_uint8.argtypes = [c_int, c_int, c_int, vp, vp, vp]
@@ -264,8 +264,7 @@ class Session:
         keys = ("V", "F", "n_expr", "N", "kpad", "npad", "tiles", "last_batch_segments", "pairs_last_batch")
         return dict(zip(keys, [int(x) for x in out]))
 
-    STAGES = ("flame", "face_frames", "bind_preprocess", "depth_sort", "scan_emit", "tile_sort", "ranges",
-              "composite")
+    STAGES = ("flame", "face_frames", "bind_preprocess", "depth_sort", "tile_ranges", "emit_scatter", "composite")
 
     def set_profiling(self, on: bool):
         check(self._L.omfs_session_set_profiling(self._h, 1 if on else 0))

@@ -69,7 +69,7 @@ def test_full_chain_small(rt, small_scene, gemm_impl):
     assert np.array_equal(bits(sess.tap_array("ff", (T, F, 20), np.float32)), bits(ref.ff))
     assert np.array_equal(bits(sess.tap_array("P0", (T, N, 4), np.float32)), bits(ref.pre.P0))
     assert np.array_equal(bits(sess.tap_array("P1", (T, N, 4), np.float32)), bits(ref.pre.P1))
-    assert np.array_equal(bits(sess.tap_array("P2", (T, N, 4), np.float32)), bits(ref.pre.P2))
+    assert np.array_equal(bits(sess.tap_array("P2", (T, N, 4), np.float32)[..., :3]), bits(ref.pre.P2[..., :3]))  # .w = cull hint
     assert np.array_equal(sess.tap_array("tiles_touched", (T, N), np.uint32), ref.pre.tiles_touched)
     R = ref.binned.n_pairs
     assert sess.dims()["pairs_last_batch"] == R == sess.stats()["pairs"]
@@ -124,31 +124,22 @@ def test_level1_stages_and_unsorted_keys(rt, small_scene):
     ws_bytes = L.omfs_binning_workspace_bytes(S, N, W, H, cap)
     d_ws = DA((ws_bytes,), np.uint8)
     d_vals, d_keys = DA((cap,), np.uint32), DA((cap,), np.uint64)
-    d_ek, d_ev = DA((cap,), np.uint64), DA((cap,), np.uint32)
     d_cnt = DA((4,), np.uint32)
     d_cnt.zero()
     flag_ptr = d_cnt.ptr + 4
     tiles = ((W + 15) // 16) * ((H + 15) // 16)
     d_ranges = DA((S * tiles, 2), np.uint32)
-    rt.check(L.omfs_binning(S, N, W, H, cap, d_P[0].ptr, d_dk.ptr, d_tt.ptr, d_vals.ptr, d_keys.ptr, d_ek.ptr,
-                            d_ev.ptr, d_ranges.ptr, d_cnt.ptr, flag_ptr, d_ws.ptr, ws_bytes, None))
+    rt.check(L.omfs_binning(S, N, W, H, cap, d_P[0].ptr, d_dk.ptr, d_tt.ptr, d_vals.ptr, d_keys.ptr,
+                            d_ranges.ptr, d_cnt.ptr, flag_ptr, d_ws.ptr, ws_bytes, None))
     R = ref.binned.n_pairs
     assert int(d_cnt.numpy()[0]) == R and int(d_cnt.numpy()[1]) == 0
     assert L.omfs_binning_sort_bits(S, W, H) == ref.binned.sort_bits
-    # the list as EMITTED: the same multiset of (key, value) pairs as the oracle's index-order
-    # emission, here in (segment, depth, index) order
-    ek, ev = d_ek.numpy()[:R], d_ev.numpy()[:R]
-    o1 = np.lexsort((ev, ek))
-    o2 = np.lexsort((ref.binned.values, ref.binned.keys))
-    assert np.array_equal(ek[o1], ref.binned.keys[o2]) and np.array_equal(ev[o1], ref.binned.values[o2])
-    seg_of = (ek >> np.uint64(32)).astype(np.int64) // tiles
-    depth_of = (ek & np.uint64(0xFFFFFFFF)).astype(np.int64)
-    order_key = (seg_of << 49) + (depth_of << 17) + ev.astype(np.int64)     # N < 2^17 here
-    assert np.all(np.diff(order_key) >= 0)
-    # the sorted list: bit-exact keys, values and ranges
+    # the sorted list: bit-exact keys, values and ranges.  (The multiset of emitted pairs is implied:
+    # the oracle's sorted list IS its emitted list, stably sorted.)
     assert np.array_equal(d_keys.numpy()[:R], ref.binned.sorted_keys)
     assert np.array_equal(d_vals.numpy()[:R], ref.binned.sorted_values)
     assert np.array_equal(d_ranges.numpy(), ref.binned.ranges)
+    assert np.array_equal(np.sort(ref.binned.keys), ref.binned.sorted_keys)
 
     d_img = DA((S, 3, H, W), np.float32)
     d_u8 = DA((S, H, W, 3), np.uint8)
