@@ -110,6 +110,8 @@ __global__ void __launch_bounds__(256) tile_count_kernel(int N, int width, int h
 
 // one CTA: exclusive scan of the S*tiles counters -> tile_start (final position of each tile's first
 // pair), the tile ranges (U9; untouched tiles stay (0,0)), the pair count and the overflow flag.
+// 8 counters per thread per round (8192 per round), so a 60-segment batch takes 8 rounds.
+constexpr int kTsItems = 8;
 __global__ void __launch_bounds__(1024) tile_scan_kernel(int n_tiles_total, const uint32_t* __restrict__ cnt,
                                                          uint32_t* __restrict__ tile_start,
                                                          uint32_t* __restrict__ ranges,
@@ -122,10 +124,16 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(int n_tiles_total, cons
     if (threadIdx.x == 0) s_carry = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int base = 0; base < n_tiles_total; base += 1024) {
-        const int i = base + threadIdx.x;
-        const uint32_t v = (i < n_tiles_total) ? cnt[i] : 0u;
-        const uint32_t inc = warp_incl_scan(v);
+    for (int base = 0; base < n_tiles_total; base += 1024 * kTsItems) {
+        const int first = base + threadIdx.x * kTsItems;
+        uint32_t v[kTsItems];
+        uint32_t acc = 0;
+#pragma unroll
+        for (int k = 0; k < kTsItems; k++) {
+            v[k] = (first + k < n_tiles_total) ? cnt[first + k] : 0u;
+            acc += v[k];
+        }
+        const uint32_t inc = warp_incl_scan(acc);
         if (lane == 31) s_warp[warp] = inc;
         __syncthreads();
         if (warp == 0) {
@@ -134,14 +142,19 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(int n_tiles_total, cons
             s_warp[lane] = winc - w;
         }
         __syncthreads();
-        const uint32_t excl = s_carry + s_warp[warp] + inc - v;
-        if (i < n_tiles_total) {
-            tile_start[i] = excl;
-            ranges[2 * i] = v ? excl : 0u;
-            ranges[2 * i + 1] = v ? excl + v : 0u;
+        uint32_t run = s_carry + s_warp[warp] + inc - acc;
+#pragma unroll
+        for (int k = 0; k < kTsItems; k++) {
+            const int i = first + k;
+            if (i < n_tiles_total) {
+                tile_start[i] = run;
+                ranges[2 * i] = v[k] ? run : 0u;
+                ranges[2 * i + 1] = v[k] ? run + v[k] : 0u;
+            }
+            run += v[k];
         }
         __syncthreads();
-        if (threadIdx.x == 1023) s_carry = excl + v;
+        if (threadIdx.x == 1023) s_carry = run;
         __syncthreads();
     }
     const bool overflow = (unsigned long long)s_carry > capacity;
@@ -176,8 +189,10 @@ static inline size_t emit_scatter_smem(int tiles) {
     return sizeof(uint32_t) * (kEsWarps * kEsWin + kEsChunk + tiles) + sizeof(uint16_t) * kEsWarps * tp + 64;
 }
 
+template <int TILE_BITS>
 __global__ void __launch_bounds__(kEsThreads) emit_scatter_kernel(
-    int S, int N, int width, int height, int tiles, int tile_bits, const uint32_t* __restrict__ perm,
+    int S, int N, int width, int height, int tiles, const uint32_t* __restrict__ perm_a,
+    const uint32_t* __restrict__ perm_b, const uint32_t* __restrict__ perm_select,
     const uint32_t* __restrict__ tt, const float4* __restrict__ P0, const uint32_t* __restrict__ tile_start,
     const uint32_t* __restrict__ sort_count, uint32_t* __restrict__ chunk_counter,
     volatile uint32_t* __restrict__ status /*[chunks][tiles]*/, uint32_t* __restrict__ vals_out) {
@@ -191,6 +206,8 @@ __global__ void __launch_bounds__(kEsThreads) emit_scatter_kernel(
     __shared__ uint32_t s_chunk;
 
     if (*sort_count == 0) return;  // empty batch, or overflow (flagged by tile_scan_kernel)
+    // the depth sort ends in perm_a, or in perm_b when its last pass was skipped as trivial
+    const uint32_t* __restrict__ perm = (*perm_select) ? perm_b : perm_a;
     const int gx = (width + kTile - 1) / kTile, gy = (height + kTile - 1) / kTile;
     const int cps = (N + kEsChunk - 1) / kEsChunk;  // chunks per segment
     const uint32_t n_chunks = (uint32_t)cps * (uint32_t)S;
@@ -329,7 +346,8 @@ __global__ void __launch_bounds__(kEsThreads) emit_scatter_kernel(
                             atomicAdd(reinterpret_cast<uint32_t*>(wc) + (t >> 1), 1u << (16 * (t & 1u)));
                     } else {
                         uint32_t peers = __ballot_sync(0xffffffffu, valid);
-                        for (int b = 0; b < tile_bits; b++) {
+#pragma unroll
+                        for (int b = 0; b < TILE_BITS; b++) {
                             const bool bit = (t >> b) & 1u;
                             const uint32_t bal = __ballot_sync(0xffffffffu, bit);
                             peers &= bit ? bal : ~bal;
@@ -394,11 +412,15 @@ __global__ void __launch_bounds__(256) rs_histogram_kernel(const uint32_t* __res
     }
 }
 
-// exclusive scan of each (segment, pass) histogram: counts -> digit start offsets.  grid = n_seg*passes
-__global__ void __launch_bounds__(256) rs_scan_hist_kernel(uint32_t* __restrict__ hist) {
+// exclusive scan of each (segment, pass) histogram: counts -> digit start offsets.  grid = n_seg*passes.
+// If `nontrivial` is given, blocks of pass `watch_pass` raise it when their segment's keys do not all
+// share one digit: a pass whose digit is constant in every segment is the identity and gets skipped.
+__global__ void __launch_bounds__(256) rs_scan_hist_kernel(uint32_t* __restrict__ hist, int passes, int watch_pass,
+                                                           uint32_t seg_len, uint32_t* __restrict__ nontrivial) {
     __shared__ uint32_t s_warp[8];
     uint32_t* h = hist + (size_t)blockIdx.x * kRadix;
     const uint32_t v = h[threadIdx.x];
+    if (nontrivial && (int)(blockIdx.x % passes) == watch_pass && v != 0u && v != seg_len) atomicOr(nontrivial, 1u);
     uint32_t total;
     h[threadIdx.x] = block_excl_scan_256(v, s_warp, total);
 }
@@ -434,9 +456,16 @@ __global__ void __launch_bounds__(kRsThreads, 4) rs_onesweep_kernel(
     const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ keys_out,
     uint32_t* __restrict__ vals_out, const uint32_t* __restrict__ count_ptr, uint32_t seg_len, uint32_t n_seg,
     int shift, const uint32_t* __restrict__ digit_start, uint32_t digit_stride,
-    uint32_t* __restrict__ tile_counter, volatile uint32_t* __restrict__ status /*[tiles][256] this pass*/) {
+    uint32_t* __restrict__ tile_counter, volatile uint32_t* __restrict__ status /*[tiles][256] this pass*/,
+    const uint32_t* __restrict__ run_if_set /*NULL: always run*/, uint32_t* __restrict__ skipped_flag) {
     extern __shared__ __align__(16) unsigned char rs_smem_raw[];
     RsSmem& sm = *reinterpret_cast<RsSmem*>(rs_smem_raw);
+    if (run_if_set && *run_if_set == 0u) {
+        // this pass's digit is constant in every segment: the pass is the identity permutation.  Tell the
+        // consumer that the result stayed in the input buffers.
+        if (blockIdx.x == 0 && threadIdx.x == 0) *skipped_flag = 1u;
+        return;
+    }
     if (count_ptr) seg_len = *count_ptr;
     const uint32_t tiles_per_seg = (seg_len + kRsTile - 1) / kRsTile;
     const uint32_t n_tiles = tiles_per_seg * n_seg;
@@ -634,13 +663,16 @@ static int set_kernel_attrs(int tiles) {
     static int es_bytes = 0;
     const int need = (int)emit_scatter_smem(tiles);
     if (need > es_bytes) {
-        OMFS_CUDA(cudaFuncSetAttribute(emit_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, need));
+        OMFS_CUDA(cudaFuncSetAttribute(emit_scatter_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, need));
+        OMFS_CUDA(cudaFuncSetAttribute(emit_scatter_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, need));
+        OMFS_CUDA(cudaFuncSetAttribute(emit_scatter_kernel<22>, cudaFuncAttributeMaxDynamicSharedMemorySize, need));
         es_bytes = need;
     }
     return OMFS_OK;
 }
 
-// ---- stage 1: depth sort of the Gaussians of every segment.  4 passes: the result is in perm[0].
+// ---- stage 1: depth sort of the Gaussians of every segment.  4 passes: the result is in perm[0]
+// (or in perm[1] with counters[6] set, when the exponent-byte pass was the identity and got skipped).
 int binning_depth_sort(int S, int N, int width, int height, size_t capacity, const uint32_t* d_depth_keys,
                        void* d_workspace, cudaStream_t stream) {
     BinningWs w = carve(d_workspace, S, N, width, height, capacity);
@@ -649,7 +681,8 @@ int binning_depth_sort(int S, int N, int width, int height, size_t capacity, con
     if (rc) return rc;
     // the depth exponent byte (bits 24..31) is nearly constant inside a warp's 32 keys
     rs_histogram_kernel<<<dim3(8, S), 256, 0, stream>>>(d_depth_keys, nullptr, (uint32_t)N, 4, 0x8u, w.hist_depth);
-    rs_scan_hist_kernel<<<S * 4, 256, 0, stream>>>(w.hist_depth);
+    // counters[5] = "top-byte pass is not trivial", counters[6] = "top-byte pass was skipped"
+    rs_scan_hist_kernel<<<S * 4, 256, 0, stream>>>(w.hist_depth, 4, 3, (uint32_t)N, w.counters + 5);
     count_launch(2);
     const uint32_t* kin = d_depth_keys;
     const uint32_t* vin = nullptr;  // identity
@@ -658,7 +691,8 @@ int binning_depth_sort(int S, int N, int width, int height, size_t capacity, con
         uint32_t* vout = w.perm[(p + 1) & 1];
         rs_onesweep_kernel<<<kNumSMs * 4, kRsThreads, sizeof(RsSmem), stream>>>(
             kin, vin, kout, vout, nullptr, (uint32_t)N, (uint32_t)S, 8 * p, w.hist_depth + p * kRadix, 4 * kRadix,
-            w.counters + p, w.status_depth + (size_t)p * w.status_depth_stride);
+            w.counters + p, w.status_depth + (size_t)p * w.status_depth_stride, p == 3 ? w.counters + 5 : nullptr,
+            w.counters + 6);
         count_launch();
         kin = kout;
         vin = vout;
@@ -677,7 +711,7 @@ int binning_tile_ranges(int S, int N, int width, int height, size_t capacity, co
         set_error("binning: %d tiles per frame exceed the shared-memory histogram (max 12288)", w.tiles);
         return OMFS_ERR_INVALID;
     }
-    tile_count_kernel<<<dim3(8, S), 256, sizeof(uint32_t) * w.tiles, stream>>>(N, width, height, w.tiles,
+    tile_count_kernel<<<dim3(32, S), 256, sizeof(uint32_t) * w.tiles, stream>>>(N, width, height, w.tiles,
                                                                               (const float4*)d_P0, d_tiles_touched,
                                                                               w.tile_cnt);
     tile_scan_kernel<<<1, 1024, 0, stream>>>(S * w.tiles, w.tile_cnt, w.tile_start, d_ranges, d_num_pairs,
@@ -704,9 +738,13 @@ int binning_emit_scatter(int S, int N, int width, int height, size_t capacity, c
         set_error("binning: %d tiles per frame need %zu bytes of shared memory", w.tiles, smem);
         return OMFS_ERR_INVALID;
     }
-    emit_scatter_kernel<<<kNumSMs * 4, kEsThreads, smem, stream>>>(
-        S, N, width, height, w.tiles, w.tile_bits, w.perm[0], d_tiles_touched, (const float4*)d_P0, w.tile_start,
-        w.sort_count, w.counters + 4, w.status_emit, d_sorted_vals);
+    // ballots per pair = bits of the tile id inside a frame: 10 at 512^2, 12 at 1024^2
+    auto kern = w.tile_bits <= 10 ? emit_scatter_kernel<10> : (w.tile_bits <= 12 ? emit_scatter_kernel<12>
+                                                                                 : emit_scatter_kernel<22>);
+    kern<<<kNumSMs * 4, kEsThreads, smem, stream>>>(S, N, width, height, w.tiles, w.perm[0], w.perm[1],
+                                                    w.counters + 6, d_tiles_touched, (const float4*)d_P0,
+                                                    w.tile_start, w.sort_count, w.counters + 4, w.status_emit,
+                                                    d_sorted_vals);
     count_launch();
     OMFS_LAUNCH_CHECK();
     return OMFS_OK;
