@@ -57,13 +57,14 @@ __global__ void __launch_bounds__(32) composite_kernel(int N, int width, int hei
                                                        const uint2* __restrict__ ranges, float bg0, float bg1,
                                                        float bg2, float* __restrict__ image,
                                                        uint8_t* __restrict__ image_u8) {
-    __shared__ float4 s_a[32];  // gx gy ca cb
-    __shared__ float4 s_b[32];  // cc lo r g
-    __shared__ float s_c[32];   // b
+    // survivors of the current round, COMPACTED in depth order: 3 x float4 per entry
+    // [gx gy ca cb | cc lo r g | b - - -], so the evaluation loop walks one pointer
+    __shared__ float4 s_rec[32 * 3];
 
     const int gxt = (width + kTile - 1) / kTile, gyt = (height + kTile - 1) / kTile;
     const int tile = blockIdx.x >> 3, sub = blockIdx.x & 7, seg = blockIdx.y;
     const int lane = threadIdx.x;
+    const uint32_t lanemask_lt = (1u << lane) - 1u;
     const int bx0 = (tile % gxt) * kTile + (sub & 1) * 8;
     const int by0 = (tile / gxt) * kTile + (sub >> 1) * 4;
     if (bx0 >= width || by0 >= height) return;  // pixel block entirely outside the image
@@ -103,32 +104,32 @@ __global__ void __launch_bounds__(32) composite_kernel(int N, int width, int hei
             unpack_extents(c.w, ex, ey);
             hit = (a.x + ex >= wx0) && (a.x - ex <= wx1) && (a.y + ey >= wy0) && (a.y - ey <= wy1);
         }
-        uint32_t mask = __ballot_sync(0xffffffffu, hit);
+        const uint32_t mask = __ballot_sync(0xffffffffu, hit);
         if (mask) {
             if (hit) {
                 const float4 b = ldg4(p1 + g);
-                s_a[lane] = make_float4(a.x, a.y, b.x, b.y);
-                s_b[lane] = make_float4(b.z, b.w, c.x, c.y);
-                s_c[lane] = c.z;
+                float4* dst = s_rec + 3 * __popc(mask & lanemask_lt);
+                dst[0] = make_float4(a.x, a.y, b.x, b.y);
+                dst[1] = make_float4(b.z, b.w, c.x, c.y);
+                dst[2] = make_float4(c.z, 0.f, 0.f, 0.f);
             }
             __syncwarp();
-            bool any_stop = false;
-            while (mask) {
-                const int j = __ffs(mask) - 1;
-                mask &= mask - 1;
-                if (!done) {
-                    const float4 sa = s_a[j];
-                    const float4 sb = s_b[j];
-                    const int r = ex_blend(sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w, s_c[j], pxf, pyf, T, C0,
+            if (!done) {
+                const int cnt = __popc(mask);
+                const float4* rec = s_rec;
+                for (int j = 0; j < cnt; j++, rec += 3) {
+                    const float4 sa = rec[0];
+                    const float4 sb = rec[1];
+                    const int r = ex_blend(sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w, rec[2].x, pxf, pyf, T, C0,
                                            C1, C2, Ex2Dev());
                     if (r == 2) {
                         done = true;
-                        any_stop = true;
+                        break;
                     }
                 }
             }
             __syncwarp();
-            if (__any_sync(0xffffffffu, any_stop) && __all_sync(0xffffffffu, done)) break;
+            if (__all_sync(0xffffffffu, done)) break;
         }
         g = gn;
         a = an;

@@ -298,9 +298,8 @@ OMFS_HD int ex_blend(float gx, float gy, float ca, float cb, float cc, float lo,
     float pw = t2 * dx;
     const float t4 = cc * dy;
     pw = fmaf(t4, dy, pw);
-    if (pw > 0.0f) return 0;
     const float e = pw + lo;
-    if (e < kLog2Inv255) return 0;
+    if ((pw > 0.0f) | (e < kLog2Inv255)) return 0;  // one combined predicate, no short-circuit branch
     const float alpha = fminf(0.99f, exp2_fn(e));
     const float testT = T * (1.0f - alpha);
     if (testT < 0.0001f) return 2;
