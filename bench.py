@@ -334,11 +334,21 @@ def main():
                             "alg_MB_per_frame": alg[name] / 1e6, "achieved_GBs": gbs, "frac_of_hbm": gbs / hbm,
                             "share_of_step": v["ms"] / total_ms}
         dom = max(stages, key=lambda k: stages[k]["share_of_step"])
+        # measured DRAM traffic of the dominant kernel from the committed ncu --set full capture, rescaled
+        # to this run's frames per launch (null if that kernel was not captured)
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+        if os.path.exists(tpath):
+            t = json.load(open(tpath)).get(dom)
+            if t:
+                traffic = t["dram_bytes_per_launch"] * stages[dom]["frames_per_launch"] / t["frames_per_launch"]
         roofline = {"kernel": dom, "bound": "hbm", "achieved": stages[dom]["achieved_GBs"], "peak": hbm,
-                    "unit": "GB/s", "frac": stages[dom]["achieved_GBs"] / hbm, "traffic": None,
+                    "unit": "GB/s", "frac": stages[dom]["achieved_GBs"] / hbm, "traffic": traffic,
                     "peak_source": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs)",
-                    "note": "algorithmic bytes (SURVEY 8d) / CUDA-event time of the stage; compositing is "
-                            "FP32/SFU-issue bound, see profiles/"}
+                    "note": "algorithmic bytes per launch (SURVEY 8d: 40 B x tile pairs + 12 B x pixels, x frames per "
+                            "launch) / in-situ CUDA-event time of the stage.  The compositing kernel is FP32-issue "
+                            "bound, not HBM bound (ncu: issue slots 70 % busy, DRAM 3 % of peak, "
+                            "profiles/r1_ncu_summary.md), so its HBM fraction is low by construction"}
         # tensor-pipe figure for the blendshape GEMM: 2*T*K3*npad flops per launch group
         flops_gemm = 2.0 * 3 * d["kpad"] * d["npad"]
         cpu = None

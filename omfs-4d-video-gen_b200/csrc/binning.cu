@@ -126,13 +126,21 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(int n_tiles_total, cons
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     for (int base = 0; base < n_tiles_total; base += 1024 * kTsItems) {
         const int first = base + threadIdx.x * kTsItems;
+        const bool full = first + kTsItems <= n_tiles_total;
         uint32_t v[kTsItems];
         uint32_t acc = 0;
+        if (full) {
+            // this CTA is alone on its SM: 16-byte accesses keep every request fully coalesced
+            const uint4 a = *reinterpret_cast<const uint4*>(cnt + first);
+            const uint4 b = *reinterpret_cast<const uint4*>(cnt + first + 4);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+            v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        } else {
 #pragma unroll
-        for (int k = 0; k < kTsItems; k++) {
-            v[k] = (first + k < n_tiles_total) ? cnt[first + k] : 0u;
-            acc += v[k];
+            for (int k = 0; k < kTsItems; k++) v[k] = (first + k < n_tiles_total) ? cnt[first + k] : 0u;
         }
+#pragma unroll
+        for (int k = 0; k < kTsItems; k++) acc += v[k];
         const uint32_t inc = warp_incl_scan(acc);
         if (lane == 31) s_warp[warp] = inc;
         __syncthreads();
@@ -143,15 +151,29 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(int n_tiles_total, cons
         }
         __syncthreads();
         uint32_t run = s_carry + s_warp[warp] + inc - acc;
+        uint32_t st[kTsItems], r0[kTsItems], r1[kTsItems];
 #pragma unroll
         for (int k = 0; k < kTsItems; k++) {
-            const int i = first + k;
-            if (i < n_tiles_total) {
-                tile_start[i] = run;
-                ranges[2 * i] = v[k] ? run : 0u;
-                ranges[2 * i + 1] = v[k] ? run + v[k] : 0u;
-            }
+            st[k] = run;
+            r0[k] = v[k] ? run : 0u;
+            r1[k] = v[k] ? run + v[k] : 0u;
             run += v[k];
+        }
+        if (full) {
+            uint4* ts = reinterpret_cast<uint4*>(tile_start + first);
+            ts[0] = make_uint4(st[0], st[1], st[2], st[3]);
+            ts[1] = make_uint4(st[4], st[5], st[6], st[7]);
+            uint4* rg = reinterpret_cast<uint4*>(ranges + 2 * (size_t)first);
+#pragma unroll
+            for (int k = 0; k < 4; k++) rg[k] = make_uint4(r0[2 * k], r1[2 * k], r0[2 * k + 1], r1[2 * k + 1]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < kTsItems; k++)
+                if (first + k < n_tiles_total) {
+                    tile_start[first + k] = st[k];
+                    ranges[2 * (first + k)] = r0[k];
+                    ranges[2 * (first + k) + 1] = r1[k];
+                }
         }
         __syncthreads();
         if (threadIdx.x == 1023) s_carry = run;
