@@ -245,9 +245,11 @@ __global__ void __launch_bounds__(kEsThreads) emit_scatter_kernel(
             for (int i = threadIdx.x; i < kEsWarps * tp / 2; i += kEsThreads) z[i] = 0;
         }
         __syncthreads();
-        const uint32_t chunk = s_chunk;
-        if (chunk >= n_chunks) break;
-        const int seg = (int)(chunk / cps), lc = (int)(chunk % cps);
+        const uint32_t work = s_chunk;
+        if (work >= n_chunks) break;
+        // chunk-major order across the segments keeps the look-back short (see rs_onesweep_kernel)
+        const int lc = (int)(work / (uint32_t)S), seg = (int)(work % (uint32_t)S);
+        const uint32_t chunk = (uint32_t)seg * (uint32_t)cps + (uint32_t)lc;  // status slot; predecessor = chunk - 1
         const int g0 = lc * kEsChunk;
         const int n_g = min(kEsChunk, N - g0);
         const size_t seg_off = (size_t)seg * N;
@@ -500,9 +502,13 @@ __global__ void __launch_bounds__(kRsThreads, 4) rs_onesweep_kernel(
         if (threadIdx.x == 0) sm.tile_id = atomicAdd(tile_counter, 1u);
         for (int i = threadIdx.x; i < kRsWarps * kRadix; i += kRsThreads) (&sm.warp_hist[0][0])[i] = 0;
         __syncthreads();
-        const uint32_t tile = sm.tile_id;
-        if (tile >= n_tiles) break;
-        const uint32_t seg = tile / tiles_per_seg, ltile = tile - seg * tiles_per_seg;
+        const uint32_t work = sm.tile_id;
+        if (work >= n_tiles) break;
+        // work items are ordered tile-major across the segments (tile 0 of every segment, then tile 1 ...):
+        // the CTAs in flight spread over all segments, so a tile's predecessors have usually published their
+        // inclusive prefix already and the look-back stays short
+        const uint32_t ltile = work / n_seg, seg = work - ltile * n_seg;
+        const uint32_t tile = seg * tiles_per_seg + ltile;  // status slot; the predecessor is tile - 1
         const size_t seg_off = (size_t)seg * seg_len;
         const uint32_t tile_base = ltile * kRsTile;  // inside the segment
         // warp w owns keys [tile_base + w*512, +512); item i of lane l is element i*32 + l of that
