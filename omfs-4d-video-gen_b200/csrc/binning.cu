@@ -289,104 +289,119 @@ __global__ void __launch_bounds__(kEsThreads) emit_scatter_kernel(
         const uint32_t my_lo = min(total_pairs, (uint32_t)warp * per_warp);
         const uint32_t my_n = min(total_pairs, (uint32_t)(warp + 1) * per_warp) - my_lo;
 
-        for (int sweep = 0; sweep < 2; sweep++) {
-            if (sweep == 1) {
-                // ---- per tile: offsets of the warps inside the chunk, chunk aggregate, look-back
-                __syncthreads();
-                for (int t = threadIdx.x; t < tiles; t += kEsThreads) {
-                    uint32_t off = 0;
+        // ---- pass A: per-warp, per-tile counts.  Order is irrelevant for counting, so every thread walks
+        // its own Gaussians' rectangles and bumps the counter of the warp that OWNS each pair.
 #pragma unroll
-                    for (int w = 0; w < kEsWarps; w++) {
-                        const uint32_t c = s_wcnt[w * tp + t];
-                        s_wcnt[w * tp + t] = (uint16_t)off;
-                        off += c;
-                    }
-                    volatile uint32_t* my_status = status + (size_t)chunk * tiles;
-                    my_status[t] = (lc == 0 ? kFlagPrefix : kFlagAgg) | off;
-                    uint32_t excl = 0;
-                    if (lc > 0) {
-                        uint32_t look = chunk - 1;
-                        uint32_t spins = 0;
-                        while (true) {
-                            if (++spins > (1u << 28)) __trap();  // a lost predecessor is a bug: fail, do not hang
-                            const uint32_t sv = status[(size_t)look * tiles + t];
-                            const uint32_t flag = sv & kFlagMask;
-                            if (flag == kFlagPrefix) {
-                                excl += sv & kValMask;
-                                break;
-                            }
-                            if (flag == kFlagAgg) {
-                                excl += sv & kValMask;
-                                look--;
-                            }
-                        }
-                        my_status[t] = kFlagPrefix | ((excl + off) & kValMask);
-                    }
-                    s_base[t] = __ldg(tile_start + (size_t)seg * tiles + t) + excl;
+        for (int q = 0; q < kEsGpt; q++) {
+            if (cnt[q] == 0) continue;
+            uint32_t j = my_off;
+#pragma unroll
+            for (int qq = 0; qq < kEsGpt; qq++)
+                if (qq < q) j += cnt[qq];
+            uint32_t owner = j / per_warp;
+            uint32_t wi = j - owner * per_warp;
+            int cx = 0, cy = 0;
+            for (uint32_t k = 0; k < cnt[q]; k++) {
+                const uint32_t tile = (uint32_t)((rminy[q] + cy) * gx + rminx[q] + cx);
+                atomicAdd(reinterpret_cast<uint32_t*>(s_wcnt + owner * tp) + (tile >> 1), 1u << (16 * (tile & 1u)));
+                if (++cx == rw[q]) {
+                    cx = 0;
+                    cy++;
+                }
+                if (++wi == per_warp) {
+                    wi = 0;
+                    owner++;
                 }
             }
-            for (uint32_t win = 0; win < n_win; win++) {
-                __syncthreads();  // the pair windows are free (and, for sweep 1, s_base / s_wcnt are final)
-                // ---- expand the pairs that fall into the current window of their owning warp
+        }
+        __syncthreads();
+        // ---- per tile: offsets of the warps inside the chunk, chunk aggregate, look-back
+        for (int t = threadIdx.x; t < tiles; t += kEsThreads) {
+            uint32_t off = 0;
 #pragma unroll
-                for (int q = 0; q < kEsGpt; q++) {
-                    if (cnt[q] == 0) continue;
-                    uint32_t j = my_off;
-#pragma unroll
-                    for (int qq = 0; qq < kEsGpt; qq++)
-                        if (qq < q) j += cnt[qq];
-                    uint32_t owner = j / per_warp;
-                    uint32_t wi = j - owner * per_warp;
-                    int cx = 0, cy = 0;
-                    const uint32_t li = (uint32_t)(threadIdx.x * kEsGpt + q);
-                    for (uint32_t k = 0; k < cnt[q]; k++) {
-                        if ((wi >> kEsWinShift) == win) {
-                            const uint32_t tile = (uint32_t)((rminy[q] + cy) * gx + rminx[q] + cx);
-                            s_pair[owner * kEsWin + (wi & (kEsWin - 1))] = (tile << 10) | li;
-                        }
-                        if (++cx == rw[q]) {
-                            cx = 0;
-                            cy++;
-                        }
-                        if (++wi == per_warp) {
-                            wi = 0;
-                            owner++;
-                        }
+            for (int w = 0; w < kEsWarps; w++) {
+                const uint32_t c = s_wcnt[w * tp + t];
+                s_wcnt[w * tp + t] = (uint16_t)off;
+                off += c;
+            }
+            volatile uint32_t* my_status = status + (size_t)chunk * tiles;
+            my_status[t] = (lc == 0 ? kFlagPrefix : kFlagAgg) | off;
+            uint32_t excl = 0;
+            if (lc > 0) {
+                uint32_t look = chunk - 1;
+                uint32_t spins = 0;
+                while (true) {
+                    if (++spins > (1u << 28)) __trap();  // a lost predecessor is a bug: fail, do not hang
+                    const uint32_t sv = status[(size_t)look * tiles + t];
+                    const uint32_t flag = sv & kFlagMask;
+                    if (flag == kFlagPrefix) {
+                        excl += sv & kValMask;
+                        break;
+                    }
+                    if (flag == kFlagAgg) {
+                        excl += sv & kValMask;
+                        look--;
                     }
                 }
-                __syncthreads();
-                // ---- my warp's window, 32 pairs per step, in pair order
-                const uint32_t w_lo = win * kEsWin;
-                const uint32_t w_n = (my_n > w_lo) ? min((uint32_t)kEsWin, my_n - w_lo) : 0u;
-                const uint32_t* wp = s_pair + warp * kEsWin;
-                uint16_t* wc = s_wcnt + warp * tp;
-                for (uint32_t s0 = 0; s0 < w_n; s0 += 32) {
-                    const bool valid = s0 + lane < w_n;
-                    const uint32_t pr = valid ? wp[s0 + lane] : 0u;
-                    const uint32_t t = pr >> 10;
-                    if (sweep == 0) {
-                        // counting only: order does not matter, a packed 16-bit shared atomic does it
-                        if (valid)
-                            atomicAdd(reinterpret_cast<uint32_t*>(wc) + (t >> 1), 1u << (16 * (t & 1u)));
-                    } else {
-                        uint32_t peers = __ballot_sync(0xffffffffu, valid);
+                my_status[t] = kFlagPrefix | ((excl + off) & kValMask);
+            }
+            s_base[t] = __ldg(tile_start + (size_t)seg * tiles + t) + excl;
+        }
+        // ---- pass B: expand the pairs IN ORDER into the owning warp's window, rank, scatter
+        for (uint32_t win = 0; win < n_win; win++) {
+            __syncthreads();  // windows are free; for win 0 also: s_base / s_wcnt are final
 #pragma unroll
-                        for (int b = 0; b < TILE_BITS; b++) {
-                            const bool bit = (t >> b) & 1u;
-                            const uint32_t bal = __ballot_sync(0xffffffffu, bit);
-                            peers &= bit ? bal : ~bal;
-                        }
-                        const int leader = __ffs(peers) - 1;
-                        uint32_t pre = 0;
-                        if (valid && lane == leader) {
-                            pre = wc[t];
-                            wc[t] = (uint16_t)(pre + __popc(peers));
-                        }
-                        pre = __shfl_sync(0xffffffffu, pre, leader & 31);
-                        if (valid) vals_out[s_base[t] + pre + __popc(peers & lanemask_lt)] = s_gidx[pr & 1023u];
-                        __syncwarp();
+            for (int q = 0; q < kEsGpt; q++) {
+                if (cnt[q] == 0) continue;
+                uint32_t j = my_off;
+#pragma unroll
+                for (int qq = 0; qq < kEsGpt; qq++)
+                    if (qq < q) j += cnt[qq];
+                uint32_t owner = j / per_warp;
+                uint32_t wi = j - owner * per_warp;
+                int cx = 0, cy = 0;
+                const uint32_t li = (uint32_t)(threadIdx.x * kEsGpt + q);
+                for (uint32_t k = 0; k < cnt[q]; k++) {
+                    if ((wi >> kEsWinShift) == win) {
+                        const uint32_t tile = (uint32_t)((rminy[q] + cy) * gx + rminx[q] + cx);
+                        s_pair[owner * kEsWin + (wi & (kEsWin - 1))] = (tile << 10) | li;
+                    }
+                    if (++cx == rw[q]) {
+                        cx = 0;
+                        cy++;
+                    }
+                    if (++wi == per_warp) {
+                        wi = 0;
+                        owner++;
                     }
                 }
+            }
+            __syncthreads();
+            // my warp's window, 32 pairs per step, in pair order
+            const uint32_t w_lo = win * kEsWin;
+            const uint32_t w_n = (my_n > w_lo) ? min((uint32_t)kEsWin, my_n - w_lo) : 0u;
+            const uint32_t* wp = s_pair + warp * kEsWin;
+            uint16_t* wc = s_wcnt + warp * tp;
+            for (uint32_t s0 = 0; s0 < w_n; s0 += 32) {
+                const bool valid = s0 + lane < w_n;
+                const uint32_t pr = valid ? wp[s0 + lane] : 0u;
+                const uint32_t t = pr >> 10;
+                uint32_t peers = __ballot_sync(0xffffffffu, valid);
+#pragma unroll
+                for (int b = 0; b < TILE_BITS; b++) {
+                    const bool bit = (t >> b) & 1u;
+                    const uint32_t bal = __ballot_sync(0xffffffffu, bit);
+                    peers &= bit ? bal : ~bal;
+                }
+                const int leader = __ffs(peers) - 1;
+                uint32_t pre = 0;
+                if (valid && lane == leader) {
+                    pre = wc[t];
+                    wc[t] = (uint16_t)(pre + __popc(peers));
+                }
+                pre = __shfl_sync(0xffffffffu, pre, leader & 31);
+                if (valid) vals_out[s_base[t] + pre + __popc(peers & lanemask_lt)] = s_gidx[pr & 1023u];
+                __syncwarp();
             }
         }
         __syncthreads();

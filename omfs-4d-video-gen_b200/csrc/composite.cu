@@ -5,7 +5,7 @@
 // only approximate operation is ex2.approx (the oracle uses exp2f), which moves the image by ~1e-7.
 //
 // Structure
-//   * one warp = one CTA = one 8x4 pixel block; the tile's depth-sorted list is consumed 32 entries
+//   * one warp = one 8x4 pixel block (4 independent warps per CTA); the tile's depth-sorted list is consumed 32 entries
 //     at a time with a lane-parallel footprint cull (extents precomputed by the preprocess kernel and
 //     carried in P2.w) and a ballot, so only the ~1/3 of the tile's Gaussians that can touch the
 //     block are evaluated — the kernel is FP32-issue bound, skipped (Gaussian, warp) pairs are the win;
@@ -32,10 +32,11 @@ struct Ex2Dev {
     __device__ __forceinline__ float operator()(float x) const { return ex2_approx(x); }
 };
 
-// One warp = one CTA = one 8x4 pixel block of a 16x16 tile (8 CTAs share a tile's list).  There is no
-// block barrier anywhere: a warp that saturates or runs out of Gaussians retires immediately and its
-// SM slot goes to another pixel block, which removes the barrier stalls (the top stall reason of the
-// 256-thread version: ncu smsp__average_warps_issue_stalled_barrier 7.1 per issue).
+// One warp = one 8x4 pixel block of a 16x16 tile; a CTA is just kCompWarps such warps of the same tile
+// packed together (the hardware caps CTAs per SM at 32, packing lifts the resident warp count to the
+// register limit).  The warps never synchronise with each other: there is no block barrier anywhere, a
+// warp that saturates or runs out of Gaussians stops at once, which removes the barrier stalls (the top
+// stall reason of the 256-thread tile-per-CTA version: ncu ..._issue_stalled_barrier 7.1 per issue).
 //
 // Per round of 32 list entries: lane l fetches entry l (index, centre, colour + packed cull extents),
 // tests the Gaussian's alpha >= 1/255 footprint box against the warp's pixel block, and a ballot yields
@@ -50,7 +51,9 @@ __device__ __forceinline__ void unpack_extents(float w, float& bx, float& by) {
     by = __high2float(h);
 }
 
-__global__ void __launch_bounds__(32) composite_kernel(int N, int width, int height, const float4* __restrict__ P0,
+constexpr int kCompWarps = 4;  // independent pixel-block warps per CTA (the hardware caps CTAs per SM at 32)
+
+__global__ void __launch_bounds__(32 * kCompWarps) composite_kernel(int N, int width, int height, const float4* __restrict__ P0,
                                                        const float4* __restrict__ P1,
                                                        const float4* __restrict__ P2,
                                                        const uint32_t* __restrict__ vals,
@@ -59,11 +62,13 @@ __global__ void __launch_bounds__(32) composite_kernel(int N, int width, int hei
                                                        uint8_t* __restrict__ image_u8) {
     // survivors of the current round, COMPACTED in depth order: 3 x float4 per entry
     // [gx gy ca cb | cc lo r g | b - - -], so the evaluation loop walks one pointer
-    __shared__ float4 s_rec[32 * 3];
+    __shared__ float4 s_rec_all[kCompWarps][32 * 3];
+    float4* s_rec = s_rec_all[threadIdx.x >> 5];
 
     const int gxt = (width + kTile - 1) / kTile, gyt = (height + kTile - 1) / kTile;
-    const int tile = blockIdx.x >> 3, sub = blockIdx.x & 7, seg = blockIdx.y;
-    const int lane = threadIdx.x;
+    const int unit = blockIdx.x * kCompWarps + (threadIdx.x >> 5);  // (tile, pixel block) work unit of this warp
+    const int tile = unit >> 3, sub = unit & 7, seg = blockIdx.y;
+    const int lane = threadIdx.x & 31;
     const uint32_t lanemask_lt = (1u << lane) - 1u;
     const int bx0 = (tile % gxt) * kTile + (sub & 1) * 8;
     const int by0 = (tile / gxt) * kTile + (sub >> 1) * 4;
@@ -183,8 +188,8 @@ extern "C" int omfs_composite(int S, int N, int width, int height, const float* 
     if (S == 0) return OMFS_OK;
     const int tiles = ((width + kTile - 1) / kTile) * ((height + kTile - 1) / kTile);
     OMFS_REQUIRE((long long)tiles * 8 < (1ll << 31), "too many tiles");
-    dim3 grid(tiles * 8, S);
-    composite_kernel<<<grid, 32, 0, (cudaStream_t)stream>>>(N, width, height, (const float4*)d_P0,
+    dim3 grid(tiles * 8 / kCompWarps, S);
+    composite_kernel<<<grid, 32 * kCompWarps, 0, (cudaStream_t)stream>>>(N, width, height, (const float4*)d_P0,
                                                              (const float4*)d_P1, (const float4*)d_P2,
                                                              d_sorted_vals, (const uint2*)d_ranges, bg3[0], bg3[1],
                                                              bg3[2], d_image, d_image_u8);
