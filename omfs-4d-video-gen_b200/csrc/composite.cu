@@ -44,6 +44,15 @@ struct Ex2Dev {
 // their 9 floats to the warp's shared-memory slots; every lane then evaluates the survivors with
 // broadcast reads.  The next round's gathers are issued before the current round is evaluated, so the
 // L2 latency of the dependent index -> record loads overlaps the arithmetic.
+//
+// The kernel is issue-bound (ncu: issue slots 70 % busy, FMA pipe 31 %, DRAM 3 %), so the evaluation is
+// written to spend as few issue slots per (Gaussian, pixel block) as possible:
+//   * survivors are stored in PAIRS, structure-of-arrays, so the 8 operations of the power term run as
+//     packed f32x2 instructions (FADD2/FMUL2/FFMA2 of sm_100: two IEEE-rounded binary32 results per
+//     issue slot — the sequence per element is exactly exact_math.cuh::ex_blend's);
+//   * a skipped Gaussian gets alpha = 0 (then T*(1-0) == T and fma(c,0,C) == C bit for bit), so there is
+//     no per-entry divergence (no BSSY/BSYNC); a saturated pixel parks its transmittance in Tbg and goes
+//     on with T = 0; saturation is detected by one compare + vote per pair (see blend_pair).
 __device__ __forceinline__ void unpack_extents(float w, float& bx, float& by) {
     const uint32_t u = __float_as_uint(w);
     const __half2 h = *reinterpret_cast<const __half2*>(&u);
@@ -51,7 +60,67 @@ __device__ __forceinline__ void unpack_extents(float w, float& bx, float& by) {
     by = __high2float(h);
 }
 
-constexpr int kCompWarps = 4;  // independent pixel-block warps per CTA (the hardware caps CTAs per SM at 32)
+constexpr int kCompWarps = 4;   // independent pixel-block warps per CTA (the hardware caps CTAs per SM at 32)
+constexpr int kPairSlots = 16;  // 32 survivors per round = 16 pairs
+// one pair slot = 5 float4: [gx0 gx1 gy0 gy1] [ca0 ca1 cb0 cb1] [cc0 cc1 lo0 lo1] [r0 g0 b0 -] [r1 g1 b1 -]
+constexpr int kPairFloats = 20;
+
+// alpha of one Gaussian at one pixel: min(0.99, 2^e), or 0 when ex_blend would skip it.
+// keep = (e >= log2(1/255)) && (pw <= 0) is the complement of ex_blend's skip test (no NaNs reach this
+// point); spelled in PTX so the two compares chain into ONE predicate and one select.
+__device__ __forceinline__ float alpha_of(float pw, float e) {
+    float alpha = fminf(0.99f, ex2_approx(e));
+    asm("{\n\t.reg .pred p, q;\n\t"
+        "setp.le.f32 q, %1, 0f00000000;\n\t"
+        "setp.ge.and.f32 p, %2, %3, q;\n\t"
+        "selp.f32 %0, %0, 0f00000000, p;\n\t}"
+        : "+f"(alpha)
+        : "f"(pw), "f"(e), "f"(kLog2Inv255));
+    return alpha;
+}
+
+// The exact per-Gaussian step with the saturation rule (same arithmetic as ex_blend).  Only reached for
+// the few pairs in which some pixel of the warp saturates.
+__device__ __forceinline__ void blend_step_stop(float alpha, float r, float g, float b, float& T, float& Tbg,
+                                                bool& live, float& C0, float& C1, float& C2) {
+    const float testT = T * (1.0f - alpha);
+    const bool stop = live && (testT < 0.0001f);
+    float w = alpha * T;
+    w = stop ? 0.0f : w;  // the saturating Gaussian is NOT blended
+    Tbg = stop ? T : Tbg;  // ... and the pixel keeps the transmittance it had before it
+    T = stop ? 0.0f : testT;
+    live = live && !stop;
+    C0 = fmaf(r, w, C0);
+    C1 = fmaf(g, w, C1);
+    C2 = fmaf(b, w, C2);
+}
+
+// Two consecutive Gaussians onto one pixel.  `live` is false once the pixel has saturated; from then on
+// T == 0, so alpha * T == 0 and nothing more is blended.  Saturation happens ONCE per pixel, so the pair
+// is first evaluated as if nobody saturates (no selects: the kernel is bound by issue slots and by the
+// ALU pipe that executes selects, compares and min/max); one compare + vote per PAIR detects the rare
+// case, which is then redone with the exact rule.  T2 = T*(1-a0)*(1-a1) <= T*(1-a0), so testing T2 covers
+// both steps.
+__device__ __forceinline__ void blend_pair(float a0, float a1, const float4& c0, const float4& c1, float& T,
+                                           float& Tbg, bool& live, float& C0, float& C1, float& C2) {
+    const float T1 = T * (1.0f - a0);
+    const float T2 = T1 * (1.0f - a1);
+    const bool sat = live && (T2 < 0.0001f);
+    if (__builtin_expect(__any_sync(0xffffffffu, sat), 0)) {
+        blend_step_stop(a0, c0.x, c0.y, c0.z, T, Tbg, live, C0, C1, C2);
+        blend_step_stop(a1, c1.x, c1.y, c1.z, T, Tbg, live, C0, C1, C2);
+        asm volatile("" ::: "memory");  // keep this a real (warp-uniform) branch, not a chain of selects
+    } else {
+        const float w0 = a0 * T, w1 = a1 * T1;
+        C0 = fmaf(c0.x, w0, C0);
+        C1 = fmaf(c0.y, w0, C1);
+        C2 = fmaf(c0.z, w0, C2);
+        C0 = fmaf(c1.x, w1, C0);
+        C1 = fmaf(c1.y, w1, C1);
+        C2 = fmaf(c1.z, w1, C2);
+        T = T2;
+    }
+}
 
 __global__ void __launch_bounds__(32 * kCompWarps) composite_kernel(int N, int width, int height, const float4* __restrict__ P0,
                                                        const float4* __restrict__ P1,
@@ -60,10 +129,10 @@ __global__ void __launch_bounds__(32 * kCompWarps) composite_kernel(int N, int w
                                                        const uint2* __restrict__ ranges, float bg0, float bg1,
                                                        float bg2, float* __restrict__ image,
                                                        uint8_t* __restrict__ image_u8) {
-    // survivors of the current round, COMPACTED in depth order: 3 x float4 per entry
-    // [gx gy ca cb | cc lo r g | b - - -], so the evaluation loop walks one pointer
-    __shared__ float4 s_rec_all[kCompWarps][32 * 3];
+    // survivors of the current round, COMPACTED in depth order and stored as pairs (see kPairFloats)
+    __shared__ float4 s_rec_all[kCompWarps][kPairSlots * 5];
     float4* s_rec = s_rec_all[threadIdx.x >> 5];
+    float* s_f = reinterpret_cast<float*>(s_rec);
 
     const int gxt = (width + kTile - 1) / kTile, gyt = (height + kTile - 1) / kTile;
     const int unit = blockIdx.x * kCompWarps + (threadIdx.x >> 5);  // (tile, pixel block) work unit of this warp
@@ -76,72 +145,111 @@ __global__ void __launch_bounds__(32 * kCompWarps) composite_kernel(int N, int w
     const int px = bx0 + (lane & 7);
     const int py = by0 + (lane >> 3);
     const bool inside = px < width && py < height;
-    const float pxf = (float)px, pyf = (float)py;
+    const float2 npx = make_float2(-(float)px, -(float)px), npy = make_float2(-(float)py, -(float)py);
     const float wx0 = (float)bx0, wx1 = (float)(bx0 + 7), wy0 = (float)by0, wy1 = (float)(by0 + 3);
     const uint2 range = ranges[(size_t)seg * (gxt * gyt) + tile];
     const float4* p0 = P0 + (size_t)seg * N;
     const float4* p1 = P1 + (size_t)seg * N;
     const float4* p2 = P2 + (size_t)seg * N;
 
-    float T = 1.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
-    bool done = !inside;
+    // the odd slot of a round with an odd survivor count is evaluated with whatever it holds, made
+    // harmless by lo = -inf: everything else in it must be finite, so start from zeros
+    for (int i = lane; i < kPairSlots * 5; i += 32) s_rec[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncwarp();
 
-    // software pipeline: (g, a, c) of the round being evaluated, (gn, an, cn) of the next one
-    uint32_t g = 0;
-    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), c = a;
-    if (range.x + lane < range.y) {
-        g = __ldg(vals + range.x + lane);
-        a = ldg4(p0 + g);
-        c = ldg4(p2 + g);
-    }
-    for (uint32_t base = range.x; base < range.y; base += 32) {
-        const bool have = base + lane < range.y;
-        uint32_t gn = 0;
-        float4 an = make_float4(0.f, 0.f, 0.f, 0.f), cn = an;
-        if (base + 32 + lane < range.y) {
-            gn = __ldg(vals + base + 32 + lane);
-            an = ldg4(p0 + gn);
-            cn = ldg4(p2 + gn);
-        }
-        bool hit = false;
-        if (have) {
-            float ex, ey;
-            unpack_extents(c.w, ex, ey);
-            hit = (a.x + ex >= wx0) && (a.x - ex <= wx1) && (a.y + ey >= wy0) && (a.y - ey <= wy1);
-        }
-        const uint32_t mask = __ballot_sync(0xffffffffu, hit);
-        if (mask) {
+    float T = inside ? 1.0f : 0.0f, Tbg = 0.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
+    bool live = inside;
+
+    // Software pipeline, three rounds deep, so that no load is consumed in the iteration that issued it
+    // (index -> record -> conic are DEPENDENT gathers, each an L2 round trip):
+    //   iteration r:  publish round r (its conic was requested one iteration ago)
+    //                 cull round r+1 (its records were requested one iteration ago), request the survivors' conics
+    //                 request the records of round r+2 (its indices were requested one iteration ago)
+    //                 request the indices of round r+3
+    //                 evaluate round r from shared memory
+    // Entries past the end of the list read Gaussian 0 of the segment (harmless) and never hit.
+    const int len = (int)(range.y - range.x);
+    const uint32_t* vp = vals + range.x + lane;
+    auto fetch_index = [&](int round) -> uint32_t { return (round * 32 + lane < len) ? __ldg(vp + round * 32) : 0u; };
+    auto cull = [&](const float4& a, const float4& c, int round) -> bool {
+        float ex, ey;
+        unpack_extents(c.w, ex, ey);
+        return (round * 32 + lane < len) & (a.x + ex >= wx0) & (a.x - ex <= wx1) & (a.y + ey >= wy0) & (a.y - ey <= wy1);
+    };
+    const int rounds = (len + 31) >> 5;
+    if (rounds > 0) {
+        // prologue
+        uint32_t g1 = fetch_index(0);
+        uint32_t g2 = fetch_index(1);
+        uint32_t g3 = fetch_index(2);
+        float4 a1 = ldg4(p0 + g1), c1 = ldg4(p2 + g1);
+        float4 a2 = ldg4(p0 + g2), c2 = ldg4(p2 + g2);
+        bool hit = cull(a1, c1, 0);
+        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (hit) b = ldg4(p1 + g1);
+        uint32_t mask = __ballot_sync(0xffffffffu, hit);
+        float ax = a1.x, ay = a1.y, cr = c1.x, cg = c1.y, cb_ = c1.z;
+        // now: round 0 = (ax, ay, b, cr..), hit/mask;  (a2, c2) = records of round 1;  g2 -> unused after, g3 = indices of round 2
+        for (int r = 0; r < rounds; r++) {
+            // 1. publish round r
+            const int cnt = __popc(mask);
             if (hit) {
-                const float4 b = ldg4(p1 + g);
-                float4* dst = s_rec + 3 * __popc(mask & lanemask_lt);
-                dst[0] = make_float4(a.x, a.y, b.x, b.y);
-                dst[1] = make_float4(b.z, b.w, c.x, c.y);
-                dst[2] = make_float4(c.z, 0.f, 0.f, 0.f);
+                const int s = __popc(mask & lanemask_lt);
+                const int h = s & 1;
+                float* d = s_f + (s >> 1) * kPairFloats + h;
+                d[0] = ax;
+                d[2] = ay;
+                d[4] = b.x;
+                d[6] = b.y;
+                d[8] = b.z;
+                d[10] = b.w;
+                *reinterpret_cast<float4*>(s_f + (s >> 1) * kPairFloats + 12 + 4 * h) = make_float4(cr, cg, cb_, 0.f);
+                if (s == cnt - 1 && h == 0) d[11] = __int_as_float(0xff800000);  // odd count: mute the partner
+            }
+            // 2. cull round r+1 and request its survivors' conics
+            const bool hitn = cull(a2, c2, r + 1);
+            float4 bn = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (hitn) bn = ldg4(p1 + g2);
+            const uint32_t maskn = __ballot_sync(0xffffffffu, hitn);
+            const float axn = a2.x, ayn = a2.y, crn = c2.x, cgn = c2.y, cbn = c2.z;
+            // 3. request the records of round r+2 and the indices of round r+3
+            g2 = g3;
+            a2 = ldg4(p0 + g3);
+            c2 = ldg4(p2 + g3);
+            g3 = fetch_index(r + 3);
+            __syncwarp();
+            // 4. evaluate round r
+            const int npairs = (cnt + 1) >> 1;
+            const float4* rec = s_rec;
+#pragma unroll 2
+            for (int j = 0; j < npairs; j++, rec += 5) {
+                const float4 q0 = rec[0], q1 = rec[1], q2 = rec[2];
+                const float2 dx = __fadd2_rn(make_float2(q0.x, q0.y), npx);
+                const float2 dy = __fadd2_rn(make_float2(q0.z, q0.w), npy);
+                const float2 t1 = __fmul2_rn(make_float2(q1.x, q1.y), dx);
+                const float2 t2 = __ffma2_rn(make_float2(q1.z, q1.w), dy, t1);
+                float2 pw = __fmul2_rn(t2, dx);
+                const float2 t4 = __fmul2_rn(make_float2(q2.x, q2.y), dy);
+                pw = __ffma2_rn(t4, dy, pw);
+                const float2 e = __fadd2_rn(pw, make_float2(q2.z, q2.w));
+                blend_pair(alpha_of(pw.x, e.x), alpha_of(pw.y, e.y), rec[3], rec[4], T, Tbg, live, C0, C1, C2);
             }
             __syncwarp();
-            if (!done) {
-                const int cnt = __popc(mask);
-                const float4* rec = s_rec;
-                for (int j = 0; j < cnt; j++, rec += 3) {
-                    const float4 sa = rec[0];
-                    const float4 sb = rec[1];
-                    const int r = ex_blend(sa.x, sa.y, sa.z, sa.w, sb.x, sb.y, sb.z, sb.w, rec[2].x, pxf, pyf, T, C0,
-                                           C1, C2, Ex2Dev());
-                    if (r == 2) {
-                        done = true;
-                        break;
-                    }
-                }
-            }
-            __syncwarp();
-            if (__all_sync(0xffffffffu, done)) break;
+            if (cnt && __all_sync(0xffffffffu, !live)) break;
+            // 5. rotate
+            hit = hitn;
+            mask = maskn;
+            b = bn;
+            ax = axn;
+            ay = ayn;
+            cr = crn;
+            cg = cgn;
+            cb_ = cbn;
         }
-        g = gn;
-        a = an;
-        c = cn;
     }
     if (inside) {
-        const float o0 = fmaf(T, bg0, C0), o1 = fmaf(T, bg1, C1), o2 = fmaf(T, bg2, C2);
+        const float Tf = live ? T : Tbg;
+        const float o0 = fmaf(Tf, bg0, C0), o1 = fmaf(Tf, bg1, C1), o2 = fmaf(Tf, bg2, C2);
         const size_t hw = (size_t)width * height;
         const size_t pix = (size_t)py * width + px;
         if (image) {
