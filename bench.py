@@ -168,6 +168,9 @@ def main():
     ap.add_argument("--cpu-frames", type=int, default=300, help="frames of the cpu_baseline sample")
     ap.add_argument("--ref-frames", type=int, default=60, help="frames per step of --impl reference")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-gather", action="store_true", help="diagnosis only: skip the frame gather (flagged in config)")
+    ap.add_argument("--gather", default="p2p", choices=("p2p", "nccl"),
+                    help="frame exchange: copy-engine peer-to-peer pushes into rank 0 (default) or one NCCL gather")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -209,17 +212,55 @@ def main():
     d_cam = dev_t(cam.pack()[None])
     d_ptrs = {k: v.data_ptr() for k, v in d_in.items()}
     d_ptrs["cams"] = d_cam.data_ptr()
-    frames_u8 = torch.empty((T, HEIGHT, WIDTH, 3), dtype=torch.uint8, device=dev)
-    gathered = torch.empty((world, T, HEIGHT, WIDTH, 3), dtype=torch.uint8, device=dev) if (world > 1 and rank == 0) else None
-    # a dedicated stream: the kernels, the NCCL gather and the timing events all go through it
+    # finished frames: double-buffered so that the gather of step i overlaps the rendering of step i+1
+    frames_bufs = [torch.empty((T, HEIGHT, WIDTH, 3), dtype=torch.uint8, device=dev) for _ in range(2 if world > 1 else 1)]
+    frames_u8 = frames_bufs[0]
+    gathered = None
+    peer_gather = None
+    slot_bytes = T * HEIGHT * WIDTH * 3
+    if world > 1 and args.gather == "nccl":
+        gathered = torch.empty((world, T, HEIGHT, WIDTH, 3), dtype=torch.uint8, device=dev) if rank == 0 else None
+    elif world > 1:
+        from omfs_b200 import sharding
+
+        def exchange(obj):
+            out = [None] * world
+            dist.all_gather_object(out, obj)
+            return out
+
+        peer_gather = sharding.PeerFrameGather(slot_bytes, rank, world, exchange)
+    # a dedicated stream: the kernels and the timing events go through it; the NCCL gather runs on a second
+    # stream, ordered by events (rendered -> gather may start; gathered -> the buffer may be overwritten)
     stream = torch.cuda.Stream(device=dev)
+    comm_stream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(stream)
+    ev_rendered = [torch.cuda.Event() for _ in frames_bufs]
+    ev_gathered = [torch.cuda.Event() for _ in frames_bufs]
+    step_no = [0]
 
     def step_device():
-        sess.render_device(d_ptrs, T, 1, d_out_u8=frames_u8.data_ptr(), stream=stream.cuda_stream)
+        b = step_no[0] % len(frames_bufs)
+        step_no[0] += 1
         if world > 1:
+            stream.wait_event(ev_gathered[b])
+        sess.render_device(d_ptrs, T, 1, d_out_u8=frames_bufs[b].data_ptr(), stream=stream.cuda_stream)
+        if world > 1 and not args.no_gather:
             # the only collective of the path: finished frames to rank 0 over NVLink
-            dist.gather(frames_u8, list(gathered.unbind(0)) if rank == 0 else None, dst=0)
+            ev_rendered[b].record(stream)
+            comm_stream.wait_event(ev_rendered[b])
+            if peer_gather is not None:
+                # every rank pushes its block into its slot of rank 0's buffer: sender-side copy engine
+                peer_gather.push(frames_bufs[b].data_ptr(), slot_bytes, comm_stream.cuda_stream)
+                ev_gathered[b].record(comm_stream)
+            else:
+                with torch.cuda.stream(comm_stream):
+                    dist.gather(frames_bufs[b], list(gathered.unbind(0)) if rank == 0 else None, dst=0)
+                    ev_gathered[b].record(comm_stream)
+
+    def drain():
+        # the timed region ends only when every step's frames have arrived on rank 0
+        if world > 1:
+            stream.wait_stream(comm_stream)
 
     def barrier():
         if world > 1:
@@ -228,6 +269,7 @@ def main():
 
     for _ in range(args.warmup):
         step_device()
+    drain()
     barrier()
     sess.sync()
     launches0 = runtime.launch_count()
@@ -239,6 +281,7 @@ def main():
     e0.record(stream)
     for _ in range(args.steps):
         step_device()
+    drain()
     e1.record(stream)
     barrier()
     ms = e0.elapsed_time(e1)
@@ -249,6 +292,11 @@ def main():
     if world > 1:
         dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     ms_max = float(t_ms.item())
+    ms_ranks = [ms]
+    if world > 1:
+        all_ms = [torch.zeros(1, dtype=torch.float64, device=dev) for _ in range(world)]
+        dist.all_gather(all_ms, torch.tensor([ms], dtype=torch.float64, device=dev))
+        ms_ranks = [float(x.item()) for x in all_ms]
     value = world * T * args.steps / (ms_max / 1e3)
 
     # ---- end to end through the host-buffer C-ABI call (pinned host memory both ways)
@@ -369,10 +417,16 @@ def main():
                        "l2": "per-batch working set (P0-P2 %.0f MB + keys/values %.0f MB) exceeds the 126 MB L2; "
                              "frame-invariant avatar streams (24 MB) stay L2-resident by design" % (
                                  48e-6 * args.batch * N_GAUSS, 24e-6 * R * args.batch),
-                       "gather": "NCCL gather of uint8 frames to rank 0 inside the timed region" if world > 1 else "none"},
+                       "gather": ("none" if world == 1 else
+                                  ("copy-engine peer-to-peer pushes (CUDA IPC, NVLink)" if args.gather == "p2p" else "NCCL gather") +
+                                  " of every step's uint8 frames into rank 0 inside the timed region, on a second stream: step i's "
+                                  "exchange overlaps step i+1's rendering; every rank waits for its last push before its end event "
+                                  "and the time is the max over ranks")},
+            **({"diagnosis": "--no-gather: NOT a valid multi-GPU number"} if args.no_gather and world > 1 else {}),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": e2e_steps, "note": "omfs_session_render_host: pinned host params in, uint8 frames out"},
             "gpu_launches": int(launches),
+            "ms_per_step_by_rank": [m / args.steps for m in ms_ranks],
             "clocks": clocks,
             "roofline": roofline,
             "stages": stages,
@@ -381,6 +435,8 @@ def main():
         }
         print(json.dumps(line), flush=True)
     barrier()
+    if peer_gather is not None:
+        peer_gather.close()
     sess.close()
     if world > 1:
         dist.destroy_process_group()

@@ -235,6 +235,22 @@ int omfs_memcpy_d2h(void* h_dst, const void* d_src, size_t bytes); /* synchronis
 int omfs_device_sync(void);
 unsigned long long omfs_launch_count(void);    /* kernels launched by this library so far */
 
+/* ------------------------------------------------------------------------------------------
+ * Frame exchange between the GPUs of one box (the path's only exchange step; the
+ * reference is single-GPU, 02_Visual_Engine/app.py:194-196).  One process per GPU.  The root
+ * allocates its receive buffer with omfs_device_alloc and exports it; every other rank opens the
+ * handle once and pushes its finished frames with omfs_push_frames: a peer-to-peer copy over
+ * NVLink executed by the SENDER's copy engine on the given stream — no SM is taken from the
+ * rendering kernels on either side.  Completion is ordered by the stream (record an event or
+ * synchronise after the push); the root learns of it through the caller's barrier.
+ * ---------------------------------------------------------------------------------------- */
+#define OMFS_IPC_HANDLE_BYTES 64
+int omfs_ipc_export(void* d_ptr /* from omfs_device_alloc */, void* h_handle /*[OMFS_IPC_HANDLE_BYTES]*/);
+int omfs_ipc_open(const void* h_handle, void** d_ptr);   /* in ANOTHER process than the exporter */
+int omfs_ipc_close(void* d_ptr);
+int omfs_push_frames(void* d_dst /* local or opened peer memory */, const void* d_src, size_t bytes,
+                     void* stream);
+
 /* Level-1 extras used by the parity tests and by omfs_session_set_subject. */
 int omfs_flame_fold_subject(int V, int n_shape, int npad, const float* d_template, const float* d_shapedirs,
                             const float* d_shape, const float* d_static, const float* d_plan, const float* d_jreg,

@@ -94,6 +94,36 @@ extern "C" int omfs_device_sync(void) {
     return OMFS_OK;
 }
 
+// ---- frame exchange (include/omfs_b200.h): CUDA IPC + copy-engine peer-to-peer pushes
+static_assert(sizeof(cudaIpcMemHandle_t) == OMFS_IPC_HANDLE_BYTES, "IPC handle size");
+extern "C" int omfs_ipc_export(void* d_ptr, void* h_handle) {
+    OMFS_REQUIRE(d_ptr && h_handle, "null pointer");
+    cudaIpcMemHandle_t h;
+    OMFS_CUDA(cudaIpcGetMemHandle(&h, d_ptr));
+    memcpy(h_handle, &h, sizeof(h));
+    return OMFS_OK;
+}
+extern "C" int omfs_ipc_open(const void* h_handle, void** d_ptr) {
+    OMFS_REQUIRE(d_ptr && h_handle, "null pointer");
+    cudaIpcMemHandle_t h;
+    memcpy(&h, h_handle, sizeof(h));
+    OMFS_CUDA(cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return OMFS_OK;
+}
+extern "C" int omfs_ipc_close(void* d_ptr) {
+    OMFS_REQUIRE(d_ptr, "null pointer");
+    OMFS_CUDA(cudaIpcCloseMemHandle(d_ptr));
+    return OMFS_OK;
+}
+extern "C" int omfs_push_frames(void* d_dst, const void* d_src, size_t bytes, void* stream) {
+    OMFS_REQUIRE(d_dst && d_src, "null pointer");
+    if (bytes == 0) return OMFS_OK;
+    // cudaMemcpyDefault: UVA resolves local vs peer; a device-to-device copy is run by the copy engine of
+    // the device that owns `stream`, i.e. the sender pushes
+    OMFS_CUDA(cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDefault, (cudaStream_t)stream));
+    return OMFS_OK;
+}
+
 // --------------------------------------------------------------------------------------------
 struct DevBuf {
     void* p = nullptr;

@@ -60,6 +60,9 @@ __device__ __forceinline__ void unpack_extents(float w, float& bx, float& by) {
     by = __high2float(h);
 }
 
+#ifndef OMFS_COMPOSITE_PX
+#define OMFS_COMPOSITE_PX 2  // pixels per lane (see composite_kernel)
+#endif
 constexpr int kCompWarps = 4;   // independent pixel-block warps per CTA (the hardware caps CTAs per SM at 32)
 constexpr int kPairSlots = 16;  // 32 survivors per round = 16 pairs
 // one pair slot = 5 float4: [gx0 gx1 gy0 gy1] [ca0 ca1 cb0 cb1] [cc0 cc1 lo0 lo1] [r0 g0 b0 -] [r1 g1 b1 -]
@@ -79,49 +82,72 @@ __device__ __forceinline__ float alpha_of(float pw, float e) {
     return alpha;
 }
 
+// state of one pixel.  `live` is false once the pixel has saturated; from then on T == 0, so
+// alpha * T == 0 and nothing more is blended; Tbg keeps the transmittance it saturated with.
+struct Pixel {
+    float T, Tbg, C0, C1, C2;
+    bool live;
+};
+
 // The exact per-Gaussian step with the saturation rule (same arithmetic as ex_blend).  Only reached for
 // the few pairs in which some pixel of the warp saturates.
-__device__ __forceinline__ void blend_step_stop(float alpha, float r, float g, float b, float& T, float& Tbg,
-                                                bool& live, float& C0, float& C1, float& C2) {
-    const float testT = T * (1.0f - alpha);
-    const bool stop = live && (testT < 0.0001f);
-    float w = alpha * T;
-    w = stop ? 0.0f : w;  // the saturating Gaussian is NOT blended
-    Tbg = stop ? T : Tbg;  // ... and the pixel keeps the transmittance it had before it
-    T = stop ? 0.0f : testT;
-    live = live && !stop;
-    C0 = fmaf(r, w, C0);
-    C1 = fmaf(g, w, C1);
-    C2 = fmaf(b, w, C2);
+__device__ __forceinline__ void blend_step_stop(float alpha, const float4& c, Pixel& p) {
+    const float testT = p.T * (1.0f - alpha);
+    const bool stop = p.live && (testT < 0.0001f);
+    float w = alpha * p.T;
+    w = stop ? 0.0f : w;        // the saturating Gaussian is NOT blended
+    p.Tbg = stop ? p.T : p.Tbg;  // ... and the pixel keeps the transmittance it had before it
+    p.T = stop ? 0.0f : testT;
+    p.live = p.live && !stop;
+    p.C0 = fmaf(c.x, w, p.C0);
+    p.C1 = fmaf(c.y, w, p.C1);
+    p.C2 = fmaf(c.z, w, p.C2);
 }
 
-// Two consecutive Gaussians onto one pixel.  `live` is false once the pixel has saturated; from then on
-// T == 0, so alpha * T == 0 and nothing more is blended.  Saturation happens ONCE per pixel, so the pair
-// is first evaluated as if nobody saturates (no selects: the kernel is bound by issue slots and by the
-// ALU pipe that executes selects, compares and min/max); one compare + vote per PAIR detects the rare
-// case, which is then redone with the exact rule.  T2 = T*(1-a0)*(1-a1) <= T*(1-a0), so testing T2 covers
-// both steps.
-__device__ __forceinline__ void blend_pair(float a0, float a1, const float4& c0, const float4& c1, float& T,
-                                           float& Tbg, bool& live, float& C0, float& C1, float& C2) {
-    const float T1 = T * (1.0f - a0);
-    const float T2 = T1 * (1.0f - a1);
-    const bool sat = live && (T2 < 0.0001f);
+// Two consecutive Gaussians (alphas a0[k], a1[k]) onto the PX pixels of a lane.  Saturation happens ONCE
+// per pixel, so the pair is first evaluated as if nobody saturates (no selects: the kernel is bound by
+// issue slots and by the ALU pipe that executes selects, compares and min/max); one compare per pixel +
+// one vote per PAIR detects the rare case, which is then redone with the exact rule.
+// T2 = T*(1-a0)*(1-a1) <= T*(1-a0), so testing T2 covers both steps.
+template <int PX>
+__device__ __forceinline__ void blend_pair(const float (&a0)[PX], const float (&a1)[PX], const float4& c0,
+                                           const float4& c1, Pixel (&px)[PX]) {
+    float T1[PX], T2[PX];
+    bool sat = false;
+#pragma unroll
+    for (int k = 0; k < PX; k++) {
+        T1[k] = px[k].T * (1.0f - a0[k]);
+        T2[k] = T1[k] * (1.0f - a1[k]);
+        sat = sat || (px[k].live && (T2[k] < 0.0001f));
+    }
     if (__builtin_expect(__any_sync(0xffffffffu, sat), 0)) {
-        blend_step_stop(a0, c0.x, c0.y, c0.z, T, Tbg, live, C0, C1, C2);
-        blend_step_stop(a1, c1.x, c1.y, c1.z, T, Tbg, live, C0, C1, C2);
+#pragma unroll
+        for (int k = 0; k < PX; k++) {
+            blend_step_stop(a0[k], c0, px[k]);
+            blend_step_stop(a1[k], c1, px[k]);
+        }
         asm volatile("" ::: "memory");  // keep this a real (warp-uniform) branch, not a chain of selects
     } else {
-        const float w0 = a0 * T, w1 = a1 * T1;
-        C0 = fmaf(c0.x, w0, C0);
-        C1 = fmaf(c0.y, w0, C1);
-        C2 = fmaf(c0.z, w0, C2);
-        C0 = fmaf(c1.x, w1, C0);
-        C1 = fmaf(c1.y, w1, C1);
-        C2 = fmaf(c1.z, w1, C2);
-        T = T2;
+#pragma unroll
+        for (int k = 0; k < PX; k++) {
+            const float w0 = a0[k] * px[k].T, w1 = a1[k] * T1[k];
+            px[k].C0 = fmaf(c0.x, w0, px[k].C0);
+            px[k].C1 = fmaf(c0.y, w0, px[k].C1);
+            px[k].C2 = fmaf(c0.z, w0, px[k].C2);
+            px[k].C0 = fmaf(c1.x, w1, px[k].C0);
+            px[k].C1 = fmaf(c1.y, w1, px[k].C1);
+            px[k].C2 = fmaf(c1.z, w1, px[k].C2);
+            px[k].T = T2[k];
+        }
     }
 }
 
+// PX = pixels per lane.  A warp owns an 8 x (4*PX) pixel block of its tile: lane l holds the pixels
+// (x, y + 4k), k < PX.  PX = 2 halves the number of warps that walk a tile's list (per-entry gathers and
+// cull) and the shared-memory broadcasts per pixel evaluated — the L1/shared data pipe is the unit this
+// kernel saturates first (ncu l1tex__data_pipe_lsu_wavefronts 90 % with PX = 1) — at the price of a
+// coarser footprint cull.
+template <int PX>
 __global__ void __launch_bounds__(32 * kCompWarps) composite_kernel(int N, int width, int height, const float4* __restrict__ P0,
                                                        const float4* __restrict__ P1,
                                                        const float4* __restrict__ P2,
@@ -129,6 +155,8 @@ __global__ void __launch_bounds__(32 * kCompWarps) composite_kernel(int N, int w
                                                        const uint2* __restrict__ ranges, float bg0, float bg1,
                                                        float bg2, float* __restrict__ image,
                                                        uint8_t* __restrict__ image_u8) {
+    constexpr int kBlocksPerTile = 8 / PX;  // pixel blocks (warps) per 16x16 tile
+    constexpr int kBlockH = 4 * PX;
     // survivors of the current round, COMPACTED in depth order and stored as pairs (see kPairFloats)
     __shared__ float4 s_rec_all[kCompWarps][kPairSlots * 5];
     float4* s_rec = s_rec_all[threadIdx.x >> 5];
@@ -136,17 +164,26 @@ __global__ void __launch_bounds__(32 * kCompWarps) composite_kernel(int N, int w
 
     const int gxt = (width + kTile - 1) / kTile, gyt = (height + kTile - 1) / kTile;
     const int unit = blockIdx.x * kCompWarps + (threadIdx.x >> 5);  // (tile, pixel block) work unit of this warp
-    const int tile = unit >> 3, sub = unit & 7, seg = blockIdx.y;
+    const int tile = unit / kBlocksPerTile, sub = unit % kBlocksPerTile, seg = blockIdx.y;
     const int lane = threadIdx.x & 31;
     const uint32_t lanemask_lt = (1u << lane) - 1u;
     const int bx0 = (tile % gxt) * kTile + (sub & 1) * 8;
-    const int by0 = (tile / gxt) * kTile + (sub >> 1) * 4;
+    const int by0 = (tile / gxt) * kTile + (sub >> 1) * kBlockH;
     if (bx0 >= width || by0 >= height) return;  // pixel block entirely outside the image
-    const int px = bx0 + (lane & 7);
-    const int py = by0 + (lane >> 3);
-    const bool inside = px < width && py < height;
-    const float2 npx = make_float2(-(float)px, -(float)px), npy = make_float2(-(float)py, -(float)py);
-    const float wx0 = (float)bx0, wx1 = (float)(bx0 + 7), wy0 = (float)by0, wy1 = (float)(by0 + 3);
+    const int pxi = bx0 + (lane & 7);
+    const int pyi = by0 + (lane >> 3);
+    const float2 npx = make_float2(-(float)pxi, -(float)pxi);
+    float2 npy[PX];
+    Pixel px[PX];
+#pragma unroll
+    for (int k = 0; k < PX; k++) {
+        npy[k] = make_float2(-(float)(pyi + 4 * k), -(float)(pyi + 4 * k));
+        const bool inside = pxi < width && pyi + 4 * k < height;
+        px[k].T = inside ? 1.0f : 0.0f;
+        px[k].Tbg = px[k].C0 = px[k].C1 = px[k].C2 = 0.0f;
+        px[k].live = inside;
+    }
+    const float wx0 = (float)bx0, wx1 = (float)(bx0 + 7), wy0 = (float)by0, wy1 = (float)(by0 + kBlockH - 1);
     const uint2 range = ranges[(size_t)seg * (gxt * gyt) + tile];
     const float4* p0 = P0 + (size_t)seg * N;
     const float4* p1 = P1 + (size_t)seg * N;
@@ -156,9 +193,6 @@ __global__ void __launch_bounds__(32 * kCompWarps) composite_kernel(int N, int w
     // harmless by lo = -inf: everything else in it must be finite, so start from zeros
     for (int i = lane; i < kPairSlots * 5; i += 32) s_rec[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncwarp();
-
-    float T = inside ? 1.0f : 0.0f, Tbg = 0.0f, C0 = 0.f, C1 = 0.f, C2 = 0.f;
-    bool live = inside;
 
     // Software pipeline, three rounds deep, so that no load is consumed in the iteration that issued it
     // (index -> record -> conic are DEPENDENT gathers, each an L2 round trip):
@@ -189,7 +223,7 @@ __global__ void __launch_bounds__(32 * kCompWarps) composite_kernel(int N, int w
         if (hit) b = ldg4(p1 + g1);
         uint32_t mask = __ballot_sync(0xffffffffu, hit);
         float ax = a1.x, ay = a1.y, cr = c1.x, cg = c1.y, cb_ = c1.z;
-        // now: round 0 = (ax, ay, b, cr..), hit/mask;  (a2, c2) = records of round 1;  g2 -> unused after, g3 = indices of round 2
+        // now: round 0 = (ax, ay, b, cr..), hit/mask;  (a2, c2) = records of round 1 (indices g2);  g3 = indices of round 2
         for (int r = 0; r < rounds; r++) {
             // 1. publish round r
             const int cnt = __popc(mask);
@@ -225,17 +259,26 @@ __global__ void __launch_bounds__(32 * kCompWarps) composite_kernel(int N, int w
             for (int j = 0; j < npairs; j++, rec += 5) {
                 const float4 q0 = rec[0], q1 = rec[1], q2 = rec[2];
                 const float2 dx = __fadd2_rn(make_float2(q0.x, q0.y), npx);
-                const float2 dy = __fadd2_rn(make_float2(q0.z, q0.w), npy);
                 const float2 t1 = __fmul2_rn(make_float2(q1.x, q1.y), dx);
-                const float2 t2 = __ffma2_rn(make_float2(q1.z, q1.w), dy, t1);
-                float2 pw = __fmul2_rn(t2, dx);
-                const float2 t4 = __fmul2_rn(make_float2(q2.x, q2.y), dy);
-                pw = __ffma2_rn(t4, dy, pw);
-                const float2 e = __fadd2_rn(pw, make_float2(q2.z, q2.w));
-                blend_pair(alpha_of(pw.x, e.x), alpha_of(pw.y, e.y), rec[3], rec[4], T, Tbg, live, C0, C1, C2);
+                float al0[PX], al1[PX];
+#pragma unroll
+                for (int k = 0; k < PX; k++) {
+                    const float2 dy = __fadd2_rn(make_float2(q0.z, q0.w), npy[k]);
+                    const float2 t2 = __ffma2_rn(make_float2(q1.z, q1.w), dy, t1);
+                    float2 pw = __fmul2_rn(t2, dx);
+                    const float2 t4 = __fmul2_rn(make_float2(q2.x, q2.y), dy);
+                    pw = __ffma2_rn(t4, dy, pw);
+                    const float2 e = __fadd2_rn(pw, make_float2(q2.z, q2.w));
+                    al0[k] = alpha_of(pw.x, e.x);
+                    al1[k] = alpha_of(pw.y, e.y);
+                }
+                blend_pair<PX>(al0, al1, rec[3], rec[4], px);
             }
             __syncwarp();
-            if (cnt && __all_sync(0xffffffffu, !live)) break;
+            bool any_live = false;
+#pragma unroll
+            for (int k = 0; k < PX; k++) any_live = any_live || px[k].live;
+            if (cnt && __all_sync(0xffffffffu, !any_live)) break;
             // 5. rotate
             hit = hitn;
             mask = maskn;
@@ -247,22 +290,26 @@ __global__ void __launch_bounds__(32 * kCompWarps) composite_kernel(int N, int w
             cb_ = cbn;
         }
     }
-    if (inside) {
-        const float Tf = live ? T : Tbg;
-        const float o0 = fmaf(Tf, bg0, C0), o1 = fmaf(Tf, bg1, C1), o2 = fmaf(Tf, bg2, C2);
-        const size_t hw = (size_t)width * height;
-        const size_t pix = (size_t)py * width + px;
-        if (image) {
-            float* img = image + (size_t)seg * 3 * hw;
-            img[pix] = o0;
-            img[hw + pix] = o1;
-            img[2 * hw + pix] = o2;
-        }
-        if (image_u8) {
-            uint8_t* o = image_u8 + ((size_t)seg * hw + pix) * 3;
-            o[0] = (uint8_t)fminf(fmaxf(o0 * 255.0f + 0.5f, 0.0f), 255.0f);
-            o[1] = (uint8_t)fminf(fmaxf(o1 * 255.0f + 0.5f, 0.0f), 255.0f);
-            o[2] = (uint8_t)fminf(fmaxf(o2 * 255.0f + 0.5f, 0.0f), 255.0f);
+    const size_t hw = (size_t)width * height;
+#pragma unroll
+    for (int k = 0; k < PX; k++) {
+        const int py = pyi + 4 * k;
+        if (pxi < width && py < height) {
+            const float Tf = px[k].live ? px[k].T : px[k].Tbg;
+            const float o0 = fmaf(Tf, bg0, px[k].C0), o1 = fmaf(Tf, bg1, px[k].C1), o2 = fmaf(Tf, bg2, px[k].C2);
+            const size_t pix = (size_t)py * width + pxi;
+            if (image) {
+                float* img = image + (size_t)seg * 3 * hw;
+                img[pix] = o0;
+                img[hw + pix] = o1;
+                img[2 * hw + pix] = o2;
+            }
+            if (image_u8) {
+                uint8_t* o = image_u8 + ((size_t)seg * hw + pix) * 3;
+                o[0] = (uint8_t)fminf(fmaxf(o0 * 255.0f + 0.5f, 0.0f), 255.0f);
+                o[1] = (uint8_t)fminf(fmaxf(o1 * 255.0f + 0.5f, 0.0f), 255.0f);
+                o[2] = (uint8_t)fminf(fmaxf(o2 * 255.0f + 0.5f, 0.0f), 255.0f);
+            }
         }
     }
 }
@@ -296,8 +343,9 @@ extern "C" int omfs_composite(int S, int N, int width, int height, const float* 
     if (S == 0) return OMFS_OK;
     const int tiles = ((width + kTile - 1) / kTile) * ((height + kTile - 1) / kTile);
     OMFS_REQUIRE((long long)tiles * 8 < (1ll << 31), "too many tiles");
-    dim3 grid(tiles * 8 / kCompWarps, S);
-    composite_kernel<<<grid, 32 * kCompWarps, 0, (cudaStream_t)stream>>>(N, width, height, (const float4*)d_P0,
+    constexpr int kPx = OMFS_COMPOSITE_PX;
+    dim3 grid(tiles * (8 / kPx) / kCompWarps, S);
+    composite_kernel<kPx><<<grid, 32 * kCompWarps, 0, (cudaStream_t)stream>>>(N, width, height, (const float4*)d_P0,
                                                              (const float4*)d_P1, (const float4*)d_P2,
                                                              d_sorted_vals, (const uint2*)d_ranges, bg3[0], bg3[1],
                                                              bg3[2], d_image, d_image_u8);

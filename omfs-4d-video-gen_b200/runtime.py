@@ -101,6 +101,10 @@ def load_library():
     L.omfs_to_uint8.argtypes = [c_int, c_int, c_int, vp, vp, vp]
     L.omfs_displace_points.argtypes = [c_int, vp, POINTER(c_double), POINTER(c_double), vp, c_int, vp, vp, vp, vp]
     L.omfs_device_check.argtypes = [c_int]
+    L.omfs_ipc_export.argtypes = [c_void_p, c_void_p]
+    L.omfs_ipc_open.argtypes = [c_void_p, POINTER(c_void_p)]
+    L.omfs_ipc_close.argtypes = [c_void_p]
+    L.omfs_push_frames.argtypes = [c_void_p, c_void_p, c_size_t, c_void_p]
     _lib = L
     return L
 
@@ -342,3 +346,29 @@ class DeviceArray:
             self.free()
         except Exception:
             pass
+
+
+IPC_HANDLE_BYTES = 64
+
+
+def ipc_export(d_ptr: int) -> bytes:
+    """CUDA IPC handle of a buffer from omfs_device_alloc (DeviceArray), to be opened by another process."""
+    buf = ctypes.create_string_buffer(IPC_HANDLE_BYTES)
+    check(load_library().omfs_ipc_export(c_void_p(d_ptr), buf))
+    return buf.raw
+
+
+def ipc_open(handle: bytes) -> int:
+    out = c_void_p()
+    buf = ctypes.create_string_buffer(handle, IPC_HANDLE_BYTES)
+    check(load_library().omfs_ipc_open(buf, ctypes.byref(out)))
+    return int(out.value)
+
+
+def ipc_close(d_ptr: int) -> None:
+    check(load_library().omfs_ipc_close(c_void_p(d_ptr)))
+
+
+def push_frames(d_dst: int, d_src: int, nbytes: int, stream: int = 0) -> None:
+    """Copy-engine device-to-device copy (local or to opened peer memory) on `stream`."""
+    check(load_library().omfs_push_frames(c_void_p(d_dst), c_void_p(d_src), nbytes, c_void_p(stream)))

@@ -1,8 +1,14 @@
 """Frame / view / plan sharding across the GPUs of one box.
 
 Every (plan, view, frame) triple is independent given the replicated model, so ranks never exchange
-data on the path; the only collective is the final gather of finished uint8 frames to rank 0
-(NCCL over NVLink on GPUs, gloo in the CPU tests).
+data on the path; the only exchange is the gather of finished uint8 frames on rank 0.  Two forms:
+
+* `gather_frames` — one collective (NCCL on GPUs, gloo in the CPU tests);
+* `PeerFrameGather` — the B200 form: rank 0 exports its receive buffer over CUDA IPC and every rank
+  pushes its block straight into its slot with a copy-engine peer-to-peer copy over NVLink
+  (`omfs_push_frames`).  No SM is taken from the rendering kernels, so the exchange of one clip
+  overlaps the rendering of the next; NCCL's send/recv kernels reached 127 GB/s into rank 0 at 8 GPUs
+  and did not overlap (gpurun_out/diag_8_*.json, profiles/).
 """
 from __future__ import annotations
 
@@ -38,3 +44,49 @@ def gather_frames(local_u8, n_total: int, rank: int, world: int, dst: int = 0):
         return torch.cat(parts, dim=0)[:n_total]
     dist.gather(pad, None, dst=dst)
     return None
+
+
+class PeerFrameGather:
+    """Finished frames of every rank -> one [world, slot_bytes] device buffer on rank `dst`.
+
+    `exchange(objs)` must all-gather small picklable objects across ranks (torch.distributed's
+    all_gather_object bound to the process group, or any other out-of-band channel); it is used once,
+    to hand the root's IPC handle to the peers.  `push(src_ptr, nbytes, stream)` enqueues this rank's
+    copy on `stream` (ordered after the rendering by the caller's events); the data is complete on the
+    root once every rank has synchronised that stream and the ranks have met at a barrier.
+    """
+
+    def __init__(self, slot_bytes: int, rank: int, world: int, exchange, dst: int = 0):
+        from . import runtime
+        self.rt = runtime
+        self.rank, self.world, self.dst, self.slot_bytes = rank, world, dst, slot_bytes
+        self.buffer = None      # DeviceArray on the root
+        self.base = 0           # device pointer of the root's buffer as seen from this process
+        handle = None
+        if rank == dst:
+            self.buffer = runtime.DeviceArray((world, slot_bytes), np.uint8)
+            self.base = self.buffer.ptr
+            handle = runtime.ipc_export(self.base)
+        handles = exchange(handle)
+        if rank != dst:
+            self.base = runtime.ipc_open(handles[dst])
+
+    def slot_ptr(self, rank: int | None = None) -> int:
+        return self.base + (self.rank if rank is None else rank) * self.slot_bytes
+
+    def push(self, src_ptr: int, nbytes: int, stream: int = 0) -> None:
+        if nbytes > self.slot_bytes:
+            raise ValueError("frame block larger than its slot")
+        self.rt.push_frames(self.slot_ptr(), src_ptr, nbytes, stream)
+
+    def numpy(self) -> np.ndarray:
+        """Root only: the gathered buffer [world, slot_bytes] (synchronises the device)."""
+        return self.buffer.numpy()
+
+    def close(self) -> None:
+        if self.rank != self.dst and self.base:
+            self.rt.ipc_close(self.base)
+            self.base = 0
+        if self.buffer is not None:
+            self.buffer.free()
+            self.buffer = None
