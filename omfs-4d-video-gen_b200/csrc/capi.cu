@@ -160,7 +160,12 @@ struct omfs_session {
     size_t capacity = 0;
     int geo_chunk = 512;  // frames per FLAME launch group
     cudaStream_t stream = nullptr, copy_stream = nullptr;
-    cudaEvent_t ev_done[2]{}, ev_copied[2]{};
+    // compositing of batch b runs on comp_stream (lowest priority) while the caller's stream already
+    // prepares batch b+1 (geometry, binning): ev_front = "batch's lists are ready", ev_comp = "batch's
+    // buffers may be overwritten"
+    cudaStream_t comp_stream = nullptr;
+    cudaEvent_t ev_done[2]{}, ev_copied[2]{}, ev_front[2]{}, ev_comp[2]{};
+    bool ev_comp_pending[2]{};
     bool subject_set = false;
     // model (resident)
     DevBuf template_, shapedirs, bt, jreg, weights, faces, xyzb, scale_lo, rot, sh, base;
@@ -171,7 +176,9 @@ struct omfs_session {
     // per geometry chunk
     DevBuf acoef, rmats, vp, verts;
     // per batch
-    DevBuf ff, P0, P1, P2, tt, depth_keys, vals, keys64, ranges, counters, ws, image[2], image_u8[2];
+    // (P0, P1, P2, vals, ranges are what compositing reads: double-buffered for the two-stream pipeline)
+    DevBuf ff, P0[2], P1[2], P2[2], tt, depth_keys, vals[2], keys64, ranges[2], counters, ws, image[2], image_u8[2];
+    int last_set = 0;
     size_t ws_bytes = 0;
     int last_sorted_buffer = 0, last_image_buffer = 0, last_batch_segments = 0;
     uint64_t stats[4]{};
@@ -210,18 +217,23 @@ extern "C" void omfs_session_destroy(omfs_session* s) {
     cudaSetDevice(s->cfg.device);
     if (s->stream) cudaStreamSynchronize(s->stream);
     if (s->copy_stream) cudaStreamSynchronize(s->copy_stream);
+    if (s->comp_stream) cudaStreamSynchronize(s->comp_stream);
     DevBuf* all[] = {&s->template_, &s->shapedirs, &s->bt, &s->jreg, &s->weights, &s->faces, &s->xyzb,
                      &s->scale_lo, &s->rot, &s->sh, &s->base, &s->shape, &s->static_off, &s->plan_off,
                      &s->expr, &s->rotation, &s->neck, &s->jaw, &s->eyes, &s->transl, &s->dyn, &s->jdyn,
-                     &s->cams, &s->seg_frame, &s->acoef, &s->rmats, &s->vp, &s->verts, &s->ff, &s->P0, &s->P1,
-                     &s->P2, &s->tt, &s->depth_keys, &s->vals, &s->keys64, &s->ranges,
+                     &s->cams, &s->seg_frame, &s->acoef, &s->rmats, &s->vp, &s->verts, &s->ff, &s->P0[0], &s->P1[0],
+                     &s->P2[0], &s->P0[1], &s->P1[1], &s->P2[1], &s->tt, &s->depth_keys, &s->vals[0], &s->vals[1],
+                     &s->keys64, &s->ranges[0], &s->ranges[1],
                      &s->counters, &s->ws, &s->image[0], &s->image[1], &s->image_u8[0], &s->image_u8[1]};
     for (DevBuf* b : all) b->release();
     for (int i = 0; i < 2; i++) {
         if (s->ev_done[i]) cudaEventDestroy(s->ev_done[i]);
         if (s->ev_copied[i]) cudaEventDestroy(s->ev_copied[i]);
+        if (s->ev_front[i]) cudaEventDestroy(s->ev_front[i]);
+        if (s->ev_comp[i]) cudaEventDestroy(s->ev_comp[i]);
     }
     for (cudaEvent_t e : s->prof_pool) cudaEventDestroy(e);
+    if (s->comp_stream) cudaStreamDestroy(s->comp_stream);
     if (s->stream) cudaStreamDestroy(s->stream);
     if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
     delete s;
@@ -269,9 +281,18 @@ extern "C" int omfs_session_create(const omfs_model_desc* m, const omfs_session_
     } while (0)
     TRY_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     TRY_CUDA(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+    {
+        // lowest priority: when both streams have CTAs to place, the next batch's front end goes first and
+        // the (issue-bound) compositing grid fills whatever is left
+        int prio_least = 0, prio_greatest = 0;
+        TRY_CUDA(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+        TRY_CUDA(cudaStreamCreateWithPriority(&s->comp_stream, cudaStreamNonBlocking, prio_least));
+    }
     for (int i = 0; i < 2; i++) {
         TRY_CUDA(cudaEventCreateWithFlags(&s->ev_done[i], cudaEventDisableTiming));
         TRY_CUDA(cudaEventCreateWithFlags(&s->ev_copied[i], cudaEventDisableTiming));
+        TRY_CUDA(cudaEventCreateWithFlags(&s->ev_front[i], cudaEventDisableTiming));
+        TRY_CUDA(cudaEventCreateWithFlags(&s->ev_comp[i], cudaEventDisableTiming));
     }
     cudaStream_t st = s->stream;
     TRY(upload(s->template_, m->v_template, sizeof(float) * V3, st));
@@ -324,14 +345,16 @@ extern "C" int omfs_session_create(const omfs_model_desc* m, const omfs_session_
     const size_t Sb = (size_t)cfg->max_batch;
     const size_t hw = (size_t)cfg->width * cfg->height;
     TRY(s->ff.ensure(sizeof(float) * kFF * Sb * s->F));
-    TRY(s->P0.ensure(sizeof(float) * 4 * Sb * N));
-    TRY(s->P1.ensure(sizeof(float) * 4 * Sb * N));
-    TRY(s->P2.ensure(sizeof(float) * 4 * Sb * N));
+    for (int i = 0; i < 2; i++) {
+        TRY(s->P0[i].ensure(sizeof(float) * 4 * Sb * N));
+        TRY(s->P1[i].ensure(sizeof(float) * 4 * Sb * N));
+        TRY(s->P2[i].ensure(sizeof(float) * 4 * Sb * N));
+        TRY(s->vals[i].ensure(sizeof(uint32_t) * s->capacity));
+        TRY(s->ranges[i].ensure(sizeof(uint32_t) * 2 * Sb * s->tiles));
+    }
     TRY(s->tt.ensure(sizeof(uint32_t) * Sb * N));
     TRY(s->depth_keys.ensure(sizeof(uint32_t) * Sb * N));
-    TRY(s->vals.ensure(sizeof(uint32_t) * s->capacity));
     if (cfg->debug_keys) TRY(s->keys64.ensure(sizeof(uint64_t) * s->capacity));
-    TRY(s->ranges.ensure(sizeof(uint32_t) * 2 * Sb * s->tiles));
     TRY(s->counters.ensure(256));
     TRY_CUDA(cudaMemsetAsync(s->counters.p, 0, 256, st));
     s->ws_bytes = omfs_binning_workspace_bytes((int)Sb, N, cfg->width, cfg->height, s->capacity);
@@ -415,6 +438,7 @@ static int render_core(omfs_session* s, int T, int n_views, const float* p_expr,
 
     unsigned long long* d_pair_accum = reinterpret_cast<unsigned long long*>(s->counters.as<unsigned char>() + 16);
     const bool prof = s->profiling;
+    const bool pipelined = !prof && s->cfg.max_batch > 0;
     size_t prof_used = 0;
     s->prof_stage.clear();
     // stage timing: mark(stage) records an event that closes the previous stage and opens `stage`
@@ -458,6 +482,16 @@ static int render_core(omfs_session* s, int T, int n_views, const float* p_expr,
             const int bT = std::min(fpb, gT - b0);
             const int S = bT * n_views;
             const int ib = batch_index & 1;
+            // the buffer set `ib` is free once the compositing of two batches ago has read it
+            if (s->ev_comp_pending[ib]) {
+                OMFS_CUDA(cudaStreamWaitEvent(st, s->ev_comp[ib], 0));
+                s->ev_comp_pending[ib] = false;
+            }
+            float* P0 = s->P0[ib].as<float>();
+            float* P1 = s->P1[ib].as<float>();
+            float* P2 = s->P2[ib].as<float>();
+            uint32_t* vals = s->vals[ib].as<uint32_t>();
+            uint32_t* ranges = s->ranges[ib].as<uint32_t>();
             if ((rc = mark(kStFaceFrames))) return rc;
             if ((rc = omfs_face_frames(bT, V, F, s->verts.as<float>() + (size_t)b0 * V * 3, s->faces.as<int32_t>(),
                                        s->ff.as<float>(), st)))
@@ -465,28 +499,32 @@ static int render_core(omfs_session* s, int T, int n_views, const float* p_expr,
             if ((rc = mark(kStBindPre))) return rc;
             if ((rc = omfs_bind_preprocess(S, N, F, W, H, s->ff.as<float>(), s->seg_frame.as<int32_t>(),
                                            s->cams.as<float>(), s->xyzb.as<float>(), s->scale_lo.as<float>(),
-                                           s->rot.as<float>(), s->sh.as<float>(), s->P0.as<float>(),
-                                           s->P1.as<float>(), s->P2.as<float>(), s->tt.as<uint32_t>(),
+                                           s->rot.as<float>(), s->sh.as<float>(), P0, P1, P2, s->tt.as<uint32_t>(),
                                            s->depth_keys.as<uint32_t>(), st)))
                 return rc;
             if ((rc = mark(kStDepthSort))) return rc;
             if ((rc = binning_depth_sort(S, N, W, H, s->capacity, s->depth_keys.as<uint32_t>(), s->ws.p, st)))
                 return rc;
             if ((rc = mark(kStTileRanges))) return rc;
-            if ((rc = binning_tile_ranges(S, N, W, H, s->capacity, s->P0.as<float>(), s->tt.as<uint32_t>(),
-                                          s->ranges.as<uint32_t>(), d_num_pairs, d_flag, d_pair_accum, s->ws.p,
-                                          st)))
+            if ((rc = binning_tile_ranges(S, N, W, H, s->capacity, P0, s->tt.as<uint32_t>(), ranges, d_num_pairs,
+                                          d_flag, d_pair_accum, s->ws.p, st)))
                 return rc;
             if ((rc = mark(kStEmitScatter))) return rc;
-            if ((rc = binning_emit_scatter(S, N, W, H, s->capacity, s->P0.as<float>(), s->tt.as<uint32_t>(),
-                                           s->vals.as<uint32_t>(), s->ws.p, st)))
+            if ((rc = binning_emit_scatter(S, N, W, H, s->capacity, P0, s->tt.as<uint32_t>(), vals, s->ws.p, st)))
                 return rc;
             if (s->cfg.debug_keys &&
-                (rc = binning_rebuild_keys(S, N, W, H, s->capacity, s->ranges.as<uint32_t>(), s->vals.as<uint32_t>(),
-                                           s->P0.as<float>(), s->keys64.as<uint64_t>(), s->ws.p, st)))
+                (rc = binning_rebuild_keys(S, N, W, H, s->capacity, ranges, vals, P0, s->keys64.as<uint64_t>(),
+                                           s->ws.p, st)))
                 return rc;
+            // ---- compositing: on its own stream unless stage timing is on (then everything stays in order
+            // on the caller's stream so that the event intervals mean one stage each)
+            cudaStream_t cst = pipelined ? s->comp_stream : st;
+            if (pipelined) {
+                OMFS_CUDA(cudaEventRecord(s->ev_front[ib], st));
+                OMFS_CUDA(cudaStreamWaitEvent(cst, s->ev_front[ib], 0));
+            }
             // the image buffer may still be draining to the host from two batches ago
-            if (batch_index >= 2 && out_on_host) OMFS_CUDA(cudaStreamWaitEvent(st, s->ev_copied[ib], 0));
+            if (batch_index >= 2 && out_on_host) OMFS_CUDA(cudaStreamWaitEvent(cst, s->ev_copied[ib], 0));
             float* img = s->image[ib].as<float>();
             uint8_t* img8 = s->image_u8[ib].as<uint8_t>();
             const size_t seg0 = (size_t)(g0 + b0) * n_views;
@@ -495,15 +533,17 @@ static int render_core(omfs_session* s, int T, int n_views, const float* p_expr,
             uint8_t* dst_8 = direct ? (out_u8 ? out_u8 + seg0 * 3 * hw : nullptr) : (out_u8 ? img8 : nullptr);
             if (!dst_f && !dst_8) dst_f = img;  // nothing requested: still render (debug taps)
             if ((rc = mark(kStComposite))) return rc;
-            if ((rc = omfs_composite(S, N, W, H, s->P0.as<float>(), s->P1.as<float>(), s->P2.as<float>(),
-                                     s->vals.as<uint32_t>(), s->ranges.as<uint32_t>(), s->cfg.bg, dst_f, dst_8,
-                                     st)))
-                return rc;
+            if ((rc = omfs_composite(S, N, W, H, P0, P1, P2, vals, ranges, s->cfg.bg, dst_f, dst_8, cst))) return rc;
             if ((rc = mark(-1))) return rc;
+            if (pipelined) {
+                OMFS_CUDA(cudaEventRecord(s->ev_comp[ib], cst));
+                s->ev_comp_pending[ib] = true;
+            }
             s->last_image_buffer = ib;
+            s->last_set = ib;
             s->last_batch_segments = S;
             if (out_on_host) {
-                OMFS_CUDA(cudaEventRecord(s->ev_done[ib], st));
+                OMFS_CUDA(cudaEventRecord(s->ev_done[ib], cst));
                 OMFS_CUDA(cudaStreamWaitEvent(s->copy_stream, s->ev_done[ib], 0));
                 if (out_u8)
                     OMFS_CUDA(cudaMemcpyAsync(out_u8 + seg0 * 3 * hw, img8, (size_t)S * 3 * hw,
@@ -516,6 +556,12 @@ static int render_core(omfs_session* s, int T, int n_views, const float* p_expr,
             batch_index++;
         }
     }
+    // everything this call launched is complete when the caller's stream is: join the compositing stream
+    for (int ib = 0; ib < 2; ib++)
+        if (s->ev_comp_pending[ib]) {
+            OMFS_CUDA(cudaStreamWaitEvent(st, s->ev_comp[ib], 0));
+            s->ev_comp_pending[ib] = false;
+        }
     s->stats[1] = g_launches - launches0;
     s->stats[2] = (uint64_t)batch_index;
     return OMFS_OK;
@@ -633,10 +679,10 @@ extern "C" int omfs_session_tap(omfs_session* s, const char* name, void** d_ptr,
         DevBuf* b;
     };
     DevBuf* sorted_k = &s->keys64;
-    DevBuf* sorted_v = &s->vals;
-    Tap taps[] = {{"verts", &s->verts}, {"ff", &s->ff}, {"P0", &s->P0}, {"P1", &s->P1}, {"P2", &s->P2},
+    DevBuf* sorted_v = &s->vals[s->last_set];
+    Tap taps[] = {{"verts", &s->verts}, {"ff", &s->ff}, {"P0", &s->P0[s->last_set]}, {"P1", &s->P1[s->last_set]}, {"P2", &s->P2[s->last_set]},
                   {"tiles_touched", &s->tt}, {"depth_keys", &s->depth_keys}, {"keys", sorted_k}, {"vals", sorted_v},
-                  {"ranges", &s->ranges}, {"image", &s->image[s->last_image_buffer]},
+                  {"ranges", &s->ranges[s->last_set]}, {"image", &s->image[s->last_image_buffer]},
                   {"image_u8", &s->image_u8[s->last_image_buffer]}, {"vp", &s->vp}, {"acoef", &s->acoef},
                   {"base", &s->base}, {"counters", &s->counters}, {"rmats", &s->rmats}};
     for (const Tap& t : taps)

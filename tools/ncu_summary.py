@@ -48,6 +48,9 @@ WANT = [
     ("sm__inst_executed_pipe_tensor.avg.pct_of_peak_sustained_active", "tensor inst %"),
     ("smsp__thread_inst_executed_per_inst_executed.ratio", "active threads per instruction"),
     ("lts__t_sector_hit_rate.pct", "L2 hit rate %"),
+    ("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed", "L1/shared data-pipe wavefronts % of peak"),
+    ("l1tex__data_pipe_lsu_wavefronts_mem_shared_op_ld.sum", "shared-load wavefronts"),
+    ("l1tex__t_output_wavefronts_pipe_lsu_mem_global_op_ld.sum", "global-load wavefronts"),
     ("smsp__inst_executed.sum", "warp instructions"),
 ]
 
