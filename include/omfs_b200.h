@@ -167,7 +167,8 @@ typedef struct omfs_session_config {
     int32_t device;
     int32_t gemm_impl;          /* 0 tensor core, 1 CUDA core */
     int32_t debug_keys;         /* also materialise the 64-bit sorted keys of each batch (parity taps) */
-    uint64_t pair_capacity;     /* tile pairs per batch; 0 = 24 * max_batch * n_gauss / 4 */
+    uint64_t pair_capacity;     /* tile pairs per batch; 0 = start at 6 * max_batch * n_gauss and let
+                                   omfs_session_render_host grow it when a batch overflows */
     float bg[3];
 } omfs_session_config;
 
@@ -214,6 +215,9 @@ int omfs_session_tap(omfs_session* s, const char* name, void** d_ptr, size_t* by
 
 /* Waits for the session's streams; returns OMFS_ERR_CAPACITY if any batch overflowed. */
 int omfs_session_sync(omfs_session* s);
+/* Grow the per-batch tile-pair capacity (never shrinks).  omfs_session_render_device cannot re-run a
+ * call by itself: on OMFS_ERR_CAPACITY from omfs_session_sync, reserve and render again. */
+int omfs_session_reserve_pairs(omfs_session* s, uint64_t capacity);
 void* omfs_session_stream(omfs_session* s);
 /* out9 = V, F, n_expr, N, kpad, npad, tiles, segments of the last batch, tile pairs of the last batch */
 int omfs_session_dims(omfs_session* s, int32_t* out9);

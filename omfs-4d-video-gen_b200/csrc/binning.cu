@@ -118,7 +118,8 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(int n_tiles_total, cons
                                                          uint32_t* __restrict__ num_pairs,
                                                          unsigned long long capacity, int* __restrict__ status_flag,
                                                          uint32_t* __restrict__ sort_count,
-                                                         unsigned long long* __restrict__ pair_accum) {
+                                                         unsigned long long* __restrict__ pair_accum,
+                                                         uint32_t* __restrict__ pair_max) {
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_carry;
     if (threadIdx.x == 0) s_carry = 0;
@@ -184,6 +185,7 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(int n_tiles_total, cons
         const uint32_t total = s_carry;
         *num_pairs = total;
         if (pair_accum) *pair_accum += total;  // running total over the batches of one render call
+        if (pair_max && total > *pair_max) *pair_max = total;  // largest batch: what the capacity must hold
         if (overflow) {
             // flag it and emit nothing; the caller re-runs with more capacity
             *status_flag = 1;
@@ -747,8 +749,8 @@ int binning_depth_sort(int S, int N, int width, int height, size_t capacity, con
 // ---- stage 2: tile counts, their scan (= tile ranges, pair count)
 int binning_tile_ranges(int S, int N, int width, int height, size_t capacity, const float* d_P0,
                         const uint32_t* d_tiles_touched, uint32_t* d_ranges, uint32_t* d_num_pairs,
-                        int* d_status_flag, unsigned long long* d_pair_accum, void* d_workspace,
-                        cudaStream_t stream) {
+                        int* d_status_flag, unsigned long long* d_pair_accum, uint32_t* d_pair_max,
+                        void* d_workspace, cudaStream_t stream) {
     BinningWs w = carve(d_workspace, S, N, width, height, capacity);
     if (w.tiles > 12288) {
         set_error("binning: %d tiles per frame exceed the shared-memory histogram (max 12288)", w.tiles);
@@ -759,7 +761,7 @@ int binning_tile_ranges(int S, int N, int width, int height, size_t capacity, co
                                                                               w.tile_cnt);
     tile_scan_kernel<<<1, 1024, 0, stream>>>(S * w.tiles, w.tile_cnt, w.tile_start, d_ranges, d_num_pairs,
                                              (unsigned long long)capacity, d_status_flag, w.sort_count,
-                                             d_pair_accum);
+                                             d_pair_accum, d_pair_max);
     count_launch(2);
     OMFS_LAUNCH_CHECK();
     return OMFS_OK;
@@ -835,7 +837,7 @@ extern "C" int omfs_binning(int S, int N, int width, int height, size_t capacity
     int rc = binning_depth_sort(S, N, width, height, capacity, d_depth_keys, d_workspace, stream);
     if (rc) return rc;
     rc = binning_tile_ranges(S, N, width, height, capacity, d_P0, d_tiles_touched, d_ranges, d_num_pairs,
-                             d_status_flag, nullptr, d_workspace, stream);
+                             d_status_flag, nullptr, nullptr, d_workspace, stream);
     if (rc) return rc;
     rc = binning_emit_scatter(S, N, width, height, capacity, d_P0, d_tiles_touched, d_sorted_vals, d_workspace,
                               stream);

@@ -188,7 +188,8 @@ struct omfs_session {
     std::vector<int> prof_stage;          // stage id each event OPENS (-1: closes the previous one only)
     double stage_ms[8]{};
     uint64_t stage_calls[8]{};
-    uint32_t last_pairs = 0;
+    uint32_t last_pairs = 0, max_batch_pairs = 0;
+    bool capacity_auto = true;   // pair_capacity == 0 at create: the host entry point grows it on overflow
     cudaStream_t user_stream = nullptr;   // stream of the last render_device call
     std::vector<int32_t> seg_frame_host;
     int seg_table_fpb = -1, seg_table_views = -1;
@@ -260,6 +261,7 @@ extern "C" int omfs_session_create(const omfs_model_desc* m, const omfs_session_
     s->npad = ((3 * s->V + 15) + 127) / 128 * 128;
     s->tiles = ((cfg->width + kTile - 1) / kTile) * ((cfg->height + kTile - 1) / kTile);
     s->capacity = cfg->pair_capacity ? (size_t)cfg->pair_capacity : (size_t)6 * cfg->max_batch * (size_t)s->N;
+    s->capacity_auto = cfg->pair_capacity == 0;
     if (s->capacity >= (1ull << 30)) s->capacity = (1ull << 30) - 1;
     const int V = s->V, V3 = 3 * V, N = s->N;
 #define TRY(x)                       \
@@ -437,6 +439,7 @@ static int render_core(omfs_session* s, int T, int n_views, const float* p_expr,
     OMFS_CUDA(cudaMemsetAsync(s->counters.p, 0, 256, st));
 
     unsigned long long* d_pair_accum = reinterpret_cast<unsigned long long*>(s->counters.as<unsigned char>() + 16);
+    uint32_t* d_pair_max = s->counters.as<uint32_t>() + 2;
     const bool prof = s->profiling;
     const bool pipelined = !prof && s->cfg.max_batch > 0;
     size_t prof_used = 0;
@@ -507,7 +510,7 @@ static int render_core(omfs_session* s, int T, int n_views, const float* p_expr,
                 return rc;
             if ((rc = mark(kStTileRanges))) return rc;
             if ((rc = binning_tile_ranges(S, N, W, H, s->capacity, P0, s->tt.as<uint32_t>(), ranges, d_num_pairs,
-                                          d_flag, d_pair_accum, s->ws.p, st)))
+                                          d_flag, d_pair_accum, d_pair_max, s->ws.p, st)))
                 return rc;
             if ((rc = mark(kStEmitScatter))) return rc;
             if ((rc = binning_emit_scatter(S, N, W, H, s->capacity, P0, s->tt.as<uint32_t>(), vals, s->ws.p, st)))
@@ -594,10 +597,31 @@ static int finish_stats(omfs_session* s) {
     s->stats[0] = total;  // tile pairs over the whole call
     s->stats[3] = h[1];
     s->last_pairs = h[0];
+    s->max_batch_pairs = h[2];
     if (h[1]) {
-        set_error("tile-pair list overflowed the session capacity (%zu); raise pair_capacity", s->capacity);
+        set_error("tile-pair list overflowed the session capacity (%zu; the largest batch needs %u): raise "
+                  "pair_capacity or call omfs_session_reserve_pairs",
+                  s->capacity, h[2]);
         return OMFS_ERR_CAPACITY;
     }
+    return OMFS_OK;
+}
+
+// Grow (never shrink) the per-batch tile-pair capacity: the sorted index lists and the binning workspace.
+extern "C" int omfs_session_reserve_pairs(omfs_session* s, uint64_t capacity) {
+    OMFS_REQUIRE(s, "null argument");
+    OMFS_REQUIRE(capacity > 0 && capacity < (1ull << 30), "capacity must be in (0, 2^30) pairs per batch");
+    OMFS_CUDA(cudaSetDevice(s->cfg.device));
+    if ((size_t)capacity <= s->capacity) return OMFS_OK;
+    OMFS_CUDA(cudaDeviceSynchronize());
+    int rc;
+    for (int i = 0; i < 2; i++)
+        if ((rc = s->vals[i].ensure(sizeof(uint32_t) * (size_t)capacity))) return rc;
+    if (s->cfg.debug_keys && (rc = s->keys64.ensure(sizeof(uint64_t) * (size_t)capacity))) return rc;
+    const size_t ws = omfs_binning_workspace_bytes(s->cfg.max_batch, s->N, s->cfg.width, s->cfg.height, (size_t)capacity);
+    if ((rc = s->ws.ensure(ws))) return rc;
+    s->ws_bytes = ws;
+    s->capacity = (size_t)capacity;
     return OMFS_OK;
 }
 
@@ -625,17 +649,27 @@ extern "C" int omfs_session_render_host(omfs_session* s, const omfs_frames_desc*
         return rc;
     DevBuf cams_in;
     if ((rc = upload(cams_in, fr->cams, sizeof(float) * kCam * fr->n_views, st))) return rc;
-    rc = render_core(s, T, fr->n_views, s->expr.as<float>(), s->rotation.as<float>(), s->neck.as<float>(),
-                     s->jaw.as<float>(), s->eyes.as<float>(), s->transl.as<float>(),
-                     fr->dynamic_offset ? s->dyn.as<float>() : nullptr, cams_in.as<float>(), h_out_u8, h_out_f32,
-                     true, st);
-    cudaError_t e1 = cudaStreamSynchronize(st);
-    cudaError_t e2 = cudaStreamSynchronize(s->copy_stream);
+    for (int attempt = 0;; attempt++) {
+        rc = render_core(s, T, fr->n_views, s->expr.as<float>(), s->rotation.as<float>(), s->neck.as<float>(),
+                         s->jaw.as<float>(), s->eyes.as<float>(), s->transl.as<float>(),
+                         fr->dynamic_offset ? s->dyn.as<float>() : nullptr, cams_in.as<float>(), h_out_u8,
+                         h_out_f32, true, st);
+        cudaError_t e1 = cudaStreamSynchronize(st);
+        cudaError_t e2 = cudaStreamSynchronize(s->copy_stream);
+        if (rc == OMFS_OK && e1 != cudaSuccess) rc = cuda_fail(e1, "stream sync", __FILE__, __LINE__);
+        if (rc == OMFS_OK && e2 != cudaSuccess) rc = cuda_fail(e2, "copy stream sync", __FILE__, __LINE__);
+        if (rc == OMFS_OK) rc = finish_stats(s);
+        // A session created with pair_capacity = 0 sizes itself: an overflowing batch emitted nothing, the
+        // scan still counted what it needs, so grow once to that (plus headroom) and render the call again.
+        if (rc == OMFS_ERR_CAPACITY && s->capacity_auto && attempt == 0 && s->max_batch_pairs > 0) {
+            uint64_t want = (uint64_t)s->max_batch_pairs + (uint64_t)s->max_batch_pairs / 8 + 4096;
+            if (want >= (1ull << 30)) want = (1ull << 30) - 1;
+            if (want > s->capacity && omfs_session_reserve_pairs(s, want) == OMFS_OK) continue;
+        }
+        break;
+    }
     cams_in.release();
-    if (rc) return rc;
-    if (e1 != cudaSuccess) return cuda_fail(e1, "stream sync", __FILE__, __LINE__);
-    if (e2 != cudaSuccess) return cuda_fail(e2, "copy stream sync", __FILE__, __LINE__);
-    return finish_stats(s);
+    return rc;
 }
 
 extern "C" int omfs_session_render_device(omfs_session* s, const omfs_frames_desc* fr, uint8_t* d_out_u8,

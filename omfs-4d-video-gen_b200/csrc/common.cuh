@@ -47,8 +47,8 @@ int binning_depth_sort(int S, int N, int width, int height, size_t capacity, con
                        void* d_workspace, cudaStream_t stream);
 int binning_tile_ranges(int S, int N, int width, int height, size_t capacity, const float* d_P0,
                         const uint32_t* d_tiles_touched, uint32_t* d_ranges, uint32_t* d_num_pairs,
-                        int* d_status_flag, unsigned long long* d_pair_accum, void* d_workspace,
-                        cudaStream_t stream);
+                        int* d_status_flag, unsigned long long* d_pair_accum, uint32_t* d_pair_max,
+                        void* d_workspace, cudaStream_t stream);
 int binning_emit_scatter(int S, int N, int width, int height, size_t capacity, const float* d_P0,
                          const uint32_t* d_tiles_touched, uint32_t* d_sorted_vals, void* d_workspace,
                          cudaStream_t stream);

@@ -76,6 +76,7 @@ def load_library():
     L.omfs_session_render_host.argtypes = [c_void_p, POINTER(FramesDesc), c_void_p, c_void_p]
     L.omfs_session_render_device.argtypes = [c_void_p, POINTER(FramesDesc), c_void_p, c_void_p, c_void_p]
     L.omfs_session_sync.argtypes = [c_void_p]
+    L.omfs_session_reserve_pairs.argtypes = [c_void_p, c_uint64]
     L.omfs_session_stats.argtypes = [c_void_p, POINTER(c_uint64)]
     L.omfs_session_tap.argtypes = [c_void_p, c_char_p, POINTER(c_void_p), POINTER(c_size_t)]
     L.omfs_session_dims.argtypes = [c_void_p, POINTER(c_int32)]
@@ -249,6 +250,10 @@ class Session:
                         d_params["translation"], d_params.get("dynamic_offset") or None, d_params["cams"])
         check(self._L.omfs_session_render_device(self._h, ctypes.byref(fd), d_out_u8 or None, d_out_f32 or None,
                                                  stream or None))
+
+    def reserve_pairs(self, capacity: int):
+        """Grow the per-batch tile-pair capacity (render_device callers, after an OMFS_ERR_CAPACITY)."""
+        check(self._L.omfs_session_reserve_pairs(self._h, int(capacity)))
 
     def sync(self):
         check(self._L.omfs_session_sync(self._h))

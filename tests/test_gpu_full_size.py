@@ -114,3 +114,113 @@ def test_linearity_of_blendshapes_full_size(full_scene):
     lin = a * v[0] + b * v[1] - (a + b - 1.0) * v[3]
     assert np.abs(v[2] - lin).max() <= 1e-6
     sess.close()
+
+
+def test_config4_multiview_1024_500k():
+    """configs[3]: 1024x1024, 16 ring views per frame, 500k Gaussians.  Two frames = 32 segments rendered in
+    16-segment batches (one frame's views per batch).  Oracle parity on sampled (frame, view) segments —
+    bit-exact tile counts / radii / depth keys, image within tolerance on the shared vertices — plus
+    the size-independent binning properties on the last batch (4096 tiles per frame: the 12-bit tile path)."""
+    import omfs_b200  # noqa: F401
+    import oracle
+    from omfs_b200 import avatar, cameras, runtime as rt, synthetic
+    W = H = 1024
+    N, n_views, T = 500_000, 16, 2
+    model, params, av, _ = synthetic.make_scene(n_gauss=N, n_frames=T, width=W, height=H)
+    baked = avatar.bake(av)
+    cams = cameras.ring_cameras(n_views, synthetic.camera_distance(W, H), (0, 0, 0), 0.3, W, H)
+    sess = rt.Session(model, baked, W, H, max_batch=n_views, debug_keys=True)
+    sess.set_subject(params.shape, params.static_offset)
+    u8, img = sess.render_host(params, cams, want_f32=True)
+    S = T * n_views
+    assert img.shape == (S, 3, H, W) and u8.shape == (S, H, W, 3)
+    verts = sess.tap_array("verts", (T, model.n_verts, 3), np.float32)
+    pairs = sess.stats()["pairs"]
+    assert 1e6 < pairs / S < 2e7
+    # ---- oracle parity on three (frame, view) segments: front, side, back of the ring
+    sample = [(0, 0), (1, 4), (1, 9)]
+    packed = [cams[v].pack() for _, v in sample]
+    seg_frame = np.array([f for f, _ in sample])
+    ref = oracle.render(model, params, baked, packed, W, H, seg_frame=seg_frame, verts=verts)
+    segs = [f * n_views + v for f, v in sample]
+    assert np.abs(img[segs] - ref.image).max() <= 2e-4
+    assert (oracle.to_uint8(ref.image) != u8[segs]).mean() < 1e-5
+    # last batch = frame 1, all 16 views: preprocess outputs bit-exact for the sampled views of that frame
+    P0 = sess.tap_array("P0", (n_views, N, 4), np.float32)
+    tt = sess.tap_array("tiles_touched", (n_views, N), np.uint32)
+    for k, (f, v) in enumerate(sample):
+        if f != 1:
+            continue
+        assert np.array_equal(P0[v].view(np.uint32), ref.pre.P0[k].view(np.uint32))
+        assert np.array_equal(tt[v], ref.pre.tiles_touched[k])
+    # ---- binning properties of the last batch
+    R = sess.dims()["pairs_last_batch"]
+    assert int(tt.sum()) == R
+    keys = sess.tap_array("keys", (R,), np.uint64)
+    vals = sess.tap_array("vals", (R,), np.uint32)
+    tiles = (W // 16) * (H // 16)
+    ranges = sess.tap_array("ranges", (n_views * tiles, 2), np.uint32).astype(np.int64)
+    assert np.all(keys[1:] >= keys[:-1])
+    lens = ranges[:, 1] - ranges[:, 0]
+    assert lens.min() >= 0 and int(lens.sum()) == R
+    tile_of = (keys >> np.uint64(32)).astype(np.int64)
+    assert np.array_equal(np.repeat(np.arange(n_views * tiles), lens), tile_of)
+    seg = tile_of // tiles
+    assert np.array_equal((keys & np.uint64(0xFFFFFFFF)).astype(np.uint32), P0[seg, vals, 2].view(np.uint32))
+    counts = np.bincount(seg * N + vals.astype(np.int64), minlength=n_views * N)
+    assert np.array_equal(counts.astype(np.uint32), tt.reshape(-1))
+    # ties in depth keep Gaussian-index order inside a tile (stable sort): check on the sampled back view
+    k = 2
+    rk = ref.binned
+    v = sample[k][1]
+    lo, hi = ranges[v * tiles:(v + 1) * tiles, 0], ranges[v * tiles:(v + 1) * tiles, 1]
+    ref_lens = (rk.ranges[2 * tiles:3 * tiles, 1].astype(np.int64) - rk.ranges[2 * tiles:3 * tiles, 0])
+    assert np.array_equal(hi - lo, ref_lens)
+    busiest = int(np.argmax(ref_lens))
+    got = vals[lo[busiest]:hi[busiest]]
+    want = rk.sorted_values[rk.ranges[2 * tiles + busiest, 0]:rk.ranges[2 * tiles + busiest, 1]]
+    assert np.array_equal(got, want)
+    sess.close()
+
+
+def test_config5_plan_sweep(full_scene):
+    """configs[4]: a sweep of BSSO setback/advancement plans over one clip.  Every plan is the reference's
+    scalar edit (render_surgery.py:40-42, 119-139) on the jaw pose; the frames of plan p rendered inside the
+    sweep must be bit-identical to rendering plan p alone, the zero plan must reproduce the unedited clip,
+    and sampled (plan, frame) pairs must match the oracle run on the edited parameters."""
+    import oracle
+    from oracle import reference_rows as rr
+    from omfs_b200 import render_surgery as rs, runtime as rt, synthetic
+    model, params, av, baked, cam = full_scene
+    W = H = 512
+    T = 6
+    clip = params.slice(0, T)
+    plans_mm = [-15.0, -7.5, 0.0, 4.0, 15.0]
+    sess = rt.Session(model, baked, W, H, max_batch=32)
+    sess.set_subject(clip.shape, clip.static_offset)
+    base_u8, _ = sess.render_host(clip, [cam])
+    outs = []
+    for mm in plans_mm:
+        rec = rs._edit_record(clip.as_dict(), 0.0, rs.compute_offset(mm, 1.0), None)
+        edited = synthetic.FrameParams.from_dict(rec, n_verts=model.n_verts)
+        u8, img = sess.render_host(edited, [cam], want_f32=True)
+        outs.append((edited, u8, img))
+    assert np.array_equal(outs[2][1], base_u8)                       # 0 mm plan = the unedited clip
+    assert not np.array_equal(outs[0][1], base_u8) and not np.array_equal(outs[4][1], base_u8)
+    # the reference's edit, restated by the oracle side, gives the same parameters
+    want = rr.modify_flame_params(clip.as_dict(), 0.0, rr.compute_offset(15.0, 1.0))
+    assert np.array_equal(np.asarray(want["jaw_pose"], np.float32), outs[4][0].jaw_pose)
+    # oracle parity for (plan 0, frame 1) and (plan 4, frame 5)
+    for p, f in ((0, 1), (4, 5)):
+        edited, u8, img = outs[p]
+        one = edited.slice(f, f + 1)
+        full = oracle.render(model, one, baked, [cam.pack()], W, H)
+        assert rr.psnr(img[f:f + 1] * 255.0, full.image * 255.0) > 50.0
+        assert np.abs(img[f:f + 1] - full.image).mean() < 1e-5
+    # a plan rendered alone in a fresh session is bit-identical to the same plan inside the sweep
+    alone = rt.Session(model, baked, W, H, max_batch=4)
+    alone.set_subject(clip.shape, clip.static_offset)
+    u8_alone, _ = alone.render_host(outs[0][0], [cam])
+    assert np.array_equal(u8_alone, outs[0][1])
+    alone.close()
+    sess.close()
