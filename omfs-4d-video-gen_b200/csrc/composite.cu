@@ -60,9 +60,6 @@ __device__ __forceinline__ void unpack_extents(float w, float& bx, float& by) {
     by = __high2float(h);
 }
 
-#ifndef OMFS_COMPOSITE_PX
-#define OMFS_COMPOSITE_PX 2  // pixels per lane (see composite_kernel)
-#endif
 constexpr int kCompWarps = 4;   // independent pixel-block warps per CTA (the hardware caps CTAs per SM at 32)
 constexpr int kPairSlots = 16;  // 32 survivors per round = 16 pairs
 // one pair slot = 5 float4: [gx0 gx1 gy0 gy1] [ca0 ca1 cb0 cb1] [cc0 cc1 lo0 lo1] [r0 g0 b0 -] [r1 g1 b1 -]
@@ -82,72 +79,68 @@ __device__ __forceinline__ float alpha_of(float pw, float e) {
     return alpha;
 }
 
-// state of one pixel.  `live` is false once the pixel has saturated; from then on T == 0, so
-// alpha * T == 0 and nothing more is blended; Tbg keeps the transmittance it saturated with.
-struct Pixel {
-    float T, Tbg, C0, C1, C2;
-    bool live;
+// State of the lane's two pixels (x, y) and (x, y + 4), packed so that the blend runs as f32x2 instructions
+// (one issue slot for both pixels).  A pixel that has saturated — or lies outside the image — holds
+// T = -0.0f: every product with it is -0, fma(c, -0, C) == C bit for bit, and as an UNSIGNED integer -0
+// never compares below 1e-4, so "still live" needs no separate flag or predicate.
+struct Pixels {
+    float2 T, Tbg, C0, C1, C2;
 };
+constexpr uint32_t kStopBits = 0x38d1b717u;  // 0.0001f; T < 0.0001f  <=>  bits(T) < kStopBits for T >= +0
+
+__device__ __forceinline__ bool stops(float testT) { return __float_as_uint(testT) < kStopBits; }
 
 // The exact per-Gaussian step with the saturation rule (same arithmetic as ex_blend).  Only reached for
 // the few pairs in which some pixel of the warp saturates.
-__device__ __forceinline__ void blend_step_stop(float alpha, const float4& c, Pixel& p) {
-    const float testT = p.T * (1.0f - alpha);
-    const bool stop = p.live && (testT < 0.0001f);
-    float w = alpha * p.T;
-    w = stop ? 0.0f : w;        // the saturating Gaussian is NOT blended
-    p.Tbg = stop ? p.T : p.Tbg;  // ... and the pixel keeps the transmittance it had before it
-    p.T = stop ? 0.0f : testT;
-    p.live = p.live && !stop;
-    p.C0 = fmaf(c.x, w, p.C0);
-    p.C1 = fmaf(c.y, w, p.C1);
-    p.C2 = fmaf(c.z, w, p.C2);
+__device__ __forceinline__ void blend_step_stop(float alpha, const float4& c, float& T, float& Tbg, float& C0,
+                                                float& C1, float& C2) {
+    const float testT = T * (1.0f - alpha);
+    const bool stop = stops(testT);  // never true for a parked pixel (testT == -0)
+    float w = alpha * T;
+    w = stop ? 0.0f : w;     // the saturating Gaussian is NOT blended
+    Tbg = stop ? T : Tbg;    // ... and the pixel keeps the transmittance it had before it
+    T = stop ? -0.0f : testT;
+    C0 = fmaf(c.x, w, C0);
+    C1 = fmaf(c.y, w, C1);
+    C2 = fmaf(c.z, w, C2);
 }
 
-// Two consecutive Gaussians (alphas a0[k], a1[k]) onto the PX pixels of a lane.  Saturation happens ONCE
-// per pixel, so the pair is first evaluated as if nobody saturates (no selects: the kernel is bound by
-// issue slots and by the ALU pipe that executes selects, compares and min/max); one compare per pixel +
-// one vote per PAIR detects the rare case, which is then redone with the exact rule.
-// T2 = T*(1-a0)*(1-a1) <= T*(1-a0), so testing T2 covers both steps.
-template <int PX>
-__device__ __forceinline__ void blend_pair(const float (&a0)[PX], const float (&a1)[PX], const float4& c0,
-                                           const float4& c1, Pixel (&px)[PX]) {
-    float T1[PX], T2[PX];
-    bool sat = false;
-#pragma unroll
-    for (int k = 0; k < PX; k++) {
-        T1[k] = px[k].T * (1.0f - a0[k]);
-        T2[k] = T1[k] * (1.0f - a1[k]);
-        sat = sat || (px[k].live && (T2[k] < 0.0001f));
-    }
+// Two consecutive Gaussians (alphas a0, a1 at the lane's two pixels) onto the two pixels.  Saturation
+// happens ONCE per pixel, so the pair is first evaluated as if nobody saturates (no selects: the kernel is
+// bound by issue slots); one integer compare per pixel + one vote per PAIR detects the rare case, which is
+// then redone with the exact rule.  T2 = T*(1-a0)*(1-a1) <= T*(1-a0), so testing T2 covers both steps.
+// Every packed instruction is two individually rounded binary32 operations: the per-pixel sequence is
+// exactly ex_blend's.
+__device__ __forceinline__ void blend_pair(const float2 a0, const float2 a1, const float4& c0, const float4& c1,
+                                           Pixels& p) {
+    const float2 one = make_float2(1.0f, 1.0f);
+    const float2 T1 = __fmul2_rn(p.T, __fadd2_rn(one, make_float2(-a0.x, -a0.y)));
+    const float2 T2 = __fmul2_rn(T1, __fadd2_rn(one, make_float2(-a1.x, -a1.y)));
+    const bool sat = stops(T2.x) || stops(T2.y);
     if (__builtin_expect(__any_sync(0xffffffffu, sat), 0)) {
-#pragma unroll
-        for (int k = 0; k < PX; k++) {
-            blend_step_stop(a0[k], c0, px[k]);
-            blend_step_stop(a1[k], c1, px[k]);
-        }
+        blend_step_stop(a0.x, c0, p.T.x, p.Tbg.x, p.C0.x, p.C1.x, p.C2.x);
+        blend_step_stop(a1.x, c1, p.T.x, p.Tbg.x, p.C0.x, p.C1.x, p.C2.x);
+        blend_step_stop(a0.y, c0, p.T.y, p.Tbg.y, p.C0.y, p.C1.y, p.C2.y);
+        blend_step_stop(a1.y, c1, p.T.y, p.Tbg.y, p.C0.y, p.C1.y, p.C2.y);
         asm volatile("" ::: "memory");  // keep this a real (warp-uniform) branch, not a chain of selects
     } else {
-#pragma unroll
-        for (int k = 0; k < PX; k++) {
-            const float w0 = a0[k] * px[k].T, w1 = a1[k] * T1[k];
-            px[k].C0 = fmaf(c0.x, w0, px[k].C0);
-            px[k].C1 = fmaf(c0.y, w0, px[k].C1);
-            px[k].C2 = fmaf(c0.z, w0, px[k].C2);
-            px[k].C0 = fmaf(c1.x, w1, px[k].C0);
-            px[k].C1 = fmaf(c1.y, w1, px[k].C1);
-            px[k].C2 = fmaf(c1.z, w1, px[k].C2);
-            px[k].T = T2[k];
-        }
+        const float2 w0 = __fmul2_rn(a0, p.T), w1 = __fmul2_rn(a1, T1);
+        p.C0 = __ffma2_rn(make_float2(c0.x, c0.x), w0, p.C0);
+        p.C1 = __ffma2_rn(make_float2(c0.y, c0.y), w0, p.C1);
+        p.C2 = __ffma2_rn(make_float2(c0.z, c0.z), w0, p.C2);
+        p.C0 = __ffma2_rn(make_float2(c1.x, c1.x), w1, p.C0);
+        p.C1 = __ffma2_rn(make_float2(c1.y, c1.y), w1, p.C1);
+        p.C2 = __ffma2_rn(make_float2(c1.z, c1.z), w1, p.C2);
+        p.T = T2;
     }
 }
 
-// PX = pixels per lane.  A warp owns an 8 x (4*PX) pixel block of its tile: lane l holds the pixels
-// (x, y + 4k), k < PX.  PX = 2 halves the number of warps that walk a tile's list (per-entry gathers and
-// cull) and the shared-memory broadcasts per pixel evaluated — the L1/shared data pipe is the unit this
-// kernel saturates first (ncu l1tex__data_pipe_lsu_wavefronts 90 % with PX = 1) — at the price of a
-// coarser footprint cull.
-template <int PX>
+// A warp owns an 8x8 pixel block of its tile: lane l holds the two pixels (x, y) and (x, y + 4).  Two pixels
+// per lane halve the number of warps that walk a tile's list (per-entry gathers and cull) and the
+// shared-memory broadcasts per pixel evaluated — the L1/shared data pipe is the unit the one-pixel-per-lane
+// version saturated first (ncu l1tex__data_pipe_lsu_wavefronts 90 %) — and let the blend run packed.
+constexpr int kBlocksPerTile = 4;  // 8x8 pixel blocks (warps) per 16x16 tile
+
 __global__ void __launch_bounds__(32 * kCompWarps) composite_kernel(int N, int width, int height, const float4* __restrict__ P0,
                                                        const float4* __restrict__ P1,
                                                        const float4* __restrict__ P2,
@@ -155,8 +148,6 @@ __global__ void __launch_bounds__(32 * kCompWarps) composite_kernel(int N, int w
                                                        const uint2* __restrict__ ranges, float bg0, float bg1,
                                                        float bg2, float* __restrict__ image,
                                                        uint8_t* __restrict__ image_u8) {
-    constexpr int kBlocksPerTile = 8 / PX;  // pixel blocks (warps) per 16x16 tile
-    constexpr int kBlockH = 4 * PX;
     // survivors of the current round, COMPACTED in depth order and stored as pairs (see kPairFloats)
     __shared__ float4 s_rec_all[kCompWarps][kPairSlots * 5];
     float4* s_rec = s_rec_all[threadIdx.x >> 5];
@@ -168,22 +159,17 @@ __global__ void __launch_bounds__(32 * kCompWarps) composite_kernel(int N, int w
     const int lane = threadIdx.x & 31;
     const uint32_t lanemask_lt = (1u << lane) - 1u;
     const int bx0 = (tile % gxt) * kTile + (sub & 1) * 8;
-    const int by0 = (tile / gxt) * kTile + (sub >> 1) * kBlockH;
+    const int by0 = (tile / gxt) * kTile + (sub >> 1) * 8;
     if (bx0 >= width || by0 >= height) return;  // pixel block entirely outside the image
     const int pxi = bx0 + (lane & 7);
     const int pyi = by0 + (lane >> 3);
     const float2 npx = make_float2(-(float)pxi, -(float)pxi);
-    float2 npy[PX];
-    Pixel px[PX];
-#pragma unroll
-    for (int k = 0; k < PX; k++) {
-        npy[k] = make_float2(-(float)(pyi + 4 * k), -(float)(pyi + 4 * k));
-        const bool inside = pxi < width && pyi + 4 * k < height;
-        px[k].T = inside ? 1.0f : 0.0f;
-        px[k].Tbg = px[k].C0 = px[k].C1 = px[k].C2 = 0.0f;
-        px[k].live = inside;
-    }
-    const float wx0 = (float)bx0, wx1 = (float)(bx0 + 7), wy0 = (float)by0, wy1 = (float)(by0 + kBlockH - 1);
+    const float2 npy0 = make_float2(-(float)pyi, -(float)pyi);
+    const float2 npy1 = make_float2(-(float)(pyi + 4), -(float)(pyi + 4));
+    Pixels px;
+    px.T = make_float2((pxi < width && pyi < height) ? 1.0f : -0.0f, (pxi < width && pyi + 4 < height) ? 1.0f : -0.0f);
+    px.Tbg = px.C0 = px.C1 = px.C2 = make_float2(0.0f, 0.0f);
+    const float wx0 = (float)bx0, wx1 = (float)(bx0 + 7), wy0 = (float)by0, wy1 = (float)(by0 + 7);
     const uint2 range = ranges[(size_t)seg * (gxt * gyt) + tile];
     const float4* p0 = P0 + (size_t)seg * N;
     const float4* p1 = P1 + (size_t)seg * N;
@@ -260,25 +246,26 @@ __global__ void __launch_bounds__(32 * kCompWarps) composite_kernel(int N, int w
                 const float4 q0 = rec[0], q1 = rec[1], q2 = rec[2];
                 const float2 dx = __fadd2_rn(make_float2(q0.x, q0.y), npx);
                 const float2 t1 = __fmul2_rn(make_float2(q1.x, q1.y), dx);
-                float al0[PX], al1[PX];
-#pragma unroll
-                for (int k = 0; k < PX; k++) {
-                    const float2 dy = __fadd2_rn(make_float2(q0.z, q0.w), npy[k]);
+                // power term of both Gaussians of the pair (packed) at the lane's pixel k
+                auto power = [&](const float2 npy, float2& pw, float2& e) {
+                    const float2 dy = __fadd2_rn(make_float2(q0.z, q0.w), npy);
                     const float2 t2 = __ffma2_rn(make_float2(q1.z, q1.w), dy, t1);
-                    float2 pw = __fmul2_rn(t2, dx);
+                    pw = __fmul2_rn(t2, dx);
                     const float2 t4 = __fmul2_rn(make_float2(q2.x, q2.y), dy);
                     pw = __ffma2_rn(t4, dy, pw);
-                    const float2 e = __fadd2_rn(pw, make_float2(q2.z, q2.w));
-                    al0[k] = alpha_of(pw.x, e.x);
-                    al1[k] = alpha_of(pw.y, e.y);
-                }
-                blend_pair<PX>(al0, al1, rec[3], rec[4], px);
+                    e = __fadd2_rn(pw, make_float2(q2.z, q2.w));
+                };
+                float2 pwa, ea, pwb, eb;
+                power(npy0, pwa, ea);
+                power(npy1, pwb, eb);
+                const float2 a0 = make_float2(alpha_of(pwa.x, ea.x), alpha_of(pwb.x, eb.x));  // Gaussian 0 at both pixels
+                const float2 a1 = make_float2(alpha_of(pwa.y, ea.y), alpha_of(pwb.y, eb.y));  // Gaussian 1
+                blend_pair(a0, a1, rec[3], rec[4], px);
             }
             __syncwarp();
-            bool any_live = false;
-#pragma unroll
-            for (int k = 0; k < PX; k++) any_live = any_live || px[k].live;
-            if (cnt && __all_sync(0xffffffffu, !any_live)) break;
+            // both pixels parked (sign bits set) in every lane: the block is finished
+            const bool done = (__float_as_uint(px.T.x) & __float_as_uint(px.T.y)) >> 31;
+            if (cnt && __all_sync(0xffffffffu, done)) break;
             // 5. rotate
             hit = hitn;
             mask = maskn;
@@ -291,12 +278,14 @@ __global__ void __launch_bounds__(32 * kCompWarps) composite_kernel(int N, int w
         }
     }
     const size_t hw = (size_t)width * height;
+    const float Ts[2] = {px.T.x, px.T.y}, Tb[2] = {px.Tbg.x, px.Tbg.y};
+    const float Cs[2][3] = {{px.C0.x, px.C1.x, px.C2.x}, {px.C0.y, px.C1.y, px.C2.y}};
 #pragma unroll
-    for (int k = 0; k < PX; k++) {
+    for (int k = 0; k < 2; k++) {
         const int py = pyi + 4 * k;
         if (pxi < width && py < height) {
-            const float Tf = px[k].live ? px[k].T : px[k].Tbg;
-            const float o0 = fmaf(Tf, bg0, px[k].C0), o1 = fmaf(Tf, bg1, px[k].C1), o2 = fmaf(Tf, bg2, px[k].C2);
+            const float Tf = (__float_as_uint(Ts[k]) >> 31) ? Tb[k] : Ts[k];  // parked: what it saturated with
+            const float o0 = fmaf(Tf, bg0, Cs[k][0]), o1 = fmaf(Tf, bg1, Cs[k][1]), o2 = fmaf(Tf, bg2, Cs[k][2]);
             const size_t pix = (size_t)py * width + pxi;
             if (image) {
                 float* img = image + (size_t)seg * 3 * hw;
@@ -343,9 +332,8 @@ extern "C" int omfs_composite(int S, int N, int width, int height, const float* 
     if (S == 0) return OMFS_OK;
     const int tiles = ((width + kTile - 1) / kTile) * ((height + kTile - 1) / kTile);
     OMFS_REQUIRE((long long)tiles * 8 < (1ll << 31), "too many tiles");
-    constexpr int kPx = OMFS_COMPOSITE_PX;
-    dim3 grid(tiles * (8 / kPx) / kCompWarps, S);
-    composite_kernel<kPx><<<grid, 32 * kCompWarps, 0, (cudaStream_t)stream>>>(N, width, height, (const float4*)d_P0,
+    dim3 grid(tiles * kBlocksPerTile / kCompWarps, S);
+    composite_kernel<<<grid, 32 * kCompWarps, 0, (cudaStream_t)stream>>>(N, width, height, (const float4*)d_P0,
                                                              (const float4*)d_P1, (const float4*)d_P2,
                                                              d_sorted_vals, (const uint2*)d_ranges, bg3[0], bg3[1],
                                                              bg3[2], d_image, d_image_u8);
