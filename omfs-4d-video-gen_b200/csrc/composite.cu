@@ -1,16 +1,16 @@
-// composite.cu — U10: front-to-back alpha compositing, one 16x16 pixel tile per CTA.
+// composite.cu — U10: front-to-back alpha compositing, one warp per 8x8 pixel block of a 16x16 tile.
 //
 // Arithmetic is the canonical sequence of exact_math.cuh::ex_blend (compiled with --fmad=false,
 // explicit fmaf only), so every skip / stop decision is bit-reproducible against the oracle; the
 // only approximate operation is ex2.approx (the oracle uses exp2f), which moves the image by ~1e-7.
 //
 // Structure
-//   * one warp = one 8x4 pixel block (4 independent warps per CTA); the tile's depth-sorted list is consumed 32 entries
+//   * one warp = one 8x8 pixel block, two pixels per lane; the tile's depth-sorted list is consumed 32 entries
 //     at a time with a lane-parallel footprint cull (extents precomputed by the preprocess kernel and
 //     carried in P2.w) and a ballot, so only the ~1/3 of the tile's Gaussians that can touch the
 //     block are evaluated — the kernel is FP32-issue bound, skipped (Gaussian, warp) pairs are the win;
 //   * no block barriers: a finished pixel block frees its slot at once (see the kernel comment);
-//   * early termination per pixel (T < 1e-4) and per warp (all 32 pixels saturated);
+//   * early termination per pixel (T < 1e-4) and per warp (all 64 pixels saturated);
 //   * the optional uint8 HWC image (the save_image quantisation) is produced by the same kernel,
 //     so the frame sink costs no extra pass over HBM.
 // Roofline: 40 B per tile pair against ~256 pixel evaluations of ~10-20
@@ -32,11 +32,12 @@ struct Ex2Dev {
     __device__ __forceinline__ float operator()(float x) const { return ex2_approx(x); }
 };
 
-// One warp = one 8x4 pixel block of a 16x16 tile; a CTA is just kCompWarps such warps of the same tile
-// packed together (the hardware caps CTAs per SM at 32, packing lifts the resident warp count to the
-// register limit).  The warps never synchronise with each other: there is no block barrier anywhere, a
-// warp that saturates or runs out of Gaussians stops at once, which removes the barrier stalls (the top
-// stall reason of the 256-thread tile-per-CTA version: ncu ..._issue_stalled_barrier 7.1 per issue).
+// One warp = one 8x8 pixel block of a 16x16 tile; a CTA is kCompWarps such warps (default 1: at 62
+// registers the 32-CTA-per-SM cap and the register file both allow 32 resident warps, and a one-warp CTA
+// frees its slot the moment its block is finished — measured 6.5 % faster than 4 warps per CTA).  The warps
+// never synchronise with each other: there is no block barrier anywhere, a warp that saturates or runs out
+// of Gaussians stops at once, which removes the barrier stalls (the top stall reason of the 256-thread
+// tile-per-CTA version: ncu ..._issue_stalled_barrier 7.1 per issue).
 //
 // Per round of 32 list entries: lane l fetches entry l (index, centre, colour + packed cull extents),
 // tests the Gaussian's alpha >= 1/255 footprint box against the warp's pixel block, and a ballot yields
@@ -45,14 +46,14 @@ struct Ex2Dev {
 // broadcast reads.  The next round's gathers are issued before the current round is evaluated, so the
 // L2 latency of the dependent index -> record loads overlaps the arithmetic.
 //
-// The kernel is issue-bound (ncu: issue slots 70 % busy, FMA pipe 31 %, DRAM 3 %), so the evaluation is
+// The kernel is issue-bound (ncu: issue slots 70 % busy, FMA pipe 49 %, DRAM 3 %), so the evaluation is
 // written to spend as few issue slots per (Gaussian, pixel block) as possible:
-//   * survivors are stored in PAIRS, structure-of-arrays, so the 8 operations of the power term run as
+//   * survivors are stored in PAIRS, structure-of-arrays, so the operations of the exponent run as
 //     packed f32x2 instructions (FADD2/FMUL2/FFMA2 of sm_100: two IEEE-rounded binary32 results per
 //     issue slot — the sequence per element is exactly exact_math.cuh::ex_blend's);
 //   * a skipped Gaussian gets alpha = 0 (then T*(1-0) == T and fma(c,0,C) == C bit for bit), so there is
 //     no per-entry divergence (no BSSY/BSYNC); a saturated pixel parks its transmittance in Tbg and goes
-//     on with T = 0; saturation is detected by one compare + vote per pair (see blend_pair).
+//     on with T = -0; saturation is detected by one compare + vote per pair (see blend_pair).
 __device__ __forceinline__ void unpack_extents(float w, float& bx, float& by) {
     const uint32_t u = __float_as_uint(w);
     const __half2 h = *reinterpret_cast<const __half2*>(&u);
@@ -60,22 +61,34 @@ __device__ __forceinline__ void unpack_extents(float w, float& bx, float& by) {
     by = __high2float(h);
 }
 
-constexpr int kCompWarps = 4;   // independent pixel-block warps per CTA (the hardware caps CTAs per SM at 32)
+#ifndef OMFS_COMP_WARPS
+#define OMFS_COMP_WARPS 1
+#endif
+#ifdef OMFS_COMP_MINCTAS
+#define OMFS_COMP_BOUNDS __launch_bounds__(32 * OMFS_COMP_WARPS, OMFS_COMP_MINCTAS)
+#else
+#define OMFS_COMP_BOUNDS __launch_bounds__(32 * OMFS_COMP_WARPS)
+#endif
+#ifndef OMFS_COMP_UNROLL
+#define OMFS_COMP_UNROLL 2
+#endif
+constexpr int kCompUnroll = OMFS_COMP_UNROLL;
+constexpr int kCompWarps = OMFS_COMP_WARPS;  // independent pixel-block warps per CTA (the hardware caps CTAs per SM at 32)
 constexpr int kPairSlots = 16;  // 32 survivors per round = 16 pairs
 // one pair slot = 5 float4: [gx0 gx1 gy0 gy1] [ca0 ca1 cb0 cb1] [cc0 cc1 lo0 lo1] [r0 g0 b0 -] [r1 g1 b1 -]
 constexpr int kPairFloats = 20;
 
 // alpha of one Gaussian at one pixel: min(0.99, 2^e), or 0 when ex_blend would skip it.
-// keep = (e >= log2(1/255)) && (pw <= 0) is the complement of ex_blend's skip test (no NaNs reach this
+// keep = (e >= log2(1/255)) && (e <= lo) is the complement of ex_blend's skip test (no NaNs reach this
 // point); spelled in PTX so the two compares chain into ONE predicate and one select.
-__device__ __forceinline__ float alpha_of(float pw, float e) {
+__device__ __forceinline__ float alpha_of(float e, float lo) {
     float alpha = fminf(0.99f, ex2_approx(e));
     asm("{\n\t.reg .pred p, q;\n\t"
-        "setp.le.f32 q, %1, 0f00000000;\n\t"
-        "setp.ge.and.f32 p, %2, %3, q;\n\t"
+        "setp.le.f32 q, %1, %2;\n\t"
+        "setp.ge.and.f32 p, %1, %3, q;\n\t"
         "selp.f32 %0, %0, 0f00000000, p;\n\t}"
         : "+f"(alpha)
-        : "f"(pw), "f"(e), "f"(kLog2Inv255));
+        : "f"(e), "f"(lo), "f"(kLog2Inv255));
     return alpha;
 }
 
@@ -141,7 +154,7 @@ __device__ __forceinline__ void blend_pair(const float2 a0, const float2 a1, con
 // version saturated first (ncu l1tex__data_pipe_lsu_wavefronts 90 %) — and let the blend run packed.
 constexpr int kBlocksPerTile = 4;  // 8x8 pixel blocks (warps) per 16x16 tile
 
-__global__ void __launch_bounds__(32 * kCompWarps) composite_kernel(int N, int width, int height, const float4* __restrict__ P0,
+__global__ void OMFS_COMP_BOUNDS composite_kernel(int N, int width, int height, const float4* __restrict__ P0,
                                                        const float4* __restrict__ P1,
                                                        const float4* __restrict__ P2,
                                                        const uint32_t* __restrict__ vals,
@@ -241,25 +254,24 @@ __global__ void __launch_bounds__(32 * kCompWarps) composite_kernel(int N, int w
             // 4. evaluate round r
             const int npairs = (cnt + 1) >> 1;
             const float4* rec = s_rec;
-#pragma unroll 2
+#pragma unroll kCompUnroll
             for (int j = 0; j < npairs; j++, rec += 5) {
                 const float4 q0 = rec[0], q1 = rec[1], q2 = rec[2];
+                // exact_math.cuh::ex_blend's sequence, both Gaussians of the pair per instruction.  The column
+                // terms (dx, c0 = lo + ca dx dx, v = cb dx) are shared by the lane's two pixels (same x).
+                const float2 lo = make_float2(q2.z, q2.w);
                 const float2 dx = __fadd2_rn(make_float2(q0.x, q0.y), npx);
-                const float2 t1 = __fmul2_rn(make_float2(q1.x, q1.y), dx);
-                // power term of both Gaussians of the pair (packed) at the lane's pixel k
-                auto power = [&](const float2 npy, float2& pw, float2& e) {
+                const float2 u = __fmul2_rn(make_float2(q1.x, q1.y), dx);
+                const float2 c0 = __ffma2_rn(u, dx, lo);
+                const float2 v = __fmul2_rn(make_float2(q1.z, q1.w), dx);
+                auto exponent = [&](const float2 npy) -> float2 {
                     const float2 dy = __fadd2_rn(make_float2(q0.z, q0.w), npy);
-                    const float2 t2 = __ffma2_rn(make_float2(q1.z, q1.w), dy, t1);
-                    pw = __fmul2_rn(t2, dx);
-                    const float2 t4 = __fmul2_rn(make_float2(q2.x, q2.y), dy);
-                    pw = __ffma2_rn(t4, dy, pw);
-                    e = __fadd2_rn(pw, make_float2(q2.z, q2.w));
+                    const float2 sd = __ffma2_rn(make_float2(q2.x, q2.y), dy, v);
+                    return __ffma2_rn(sd, dy, c0);
                 };
-                float2 pwa, ea, pwb, eb;
-                power(npy0, pwa, ea);
-                power(npy1, pwb, eb);
-                const float2 a0 = make_float2(alpha_of(pwa.x, ea.x), alpha_of(pwb.x, eb.x));  // Gaussian 0 at both pixels
-                const float2 a1 = make_float2(alpha_of(pwa.y, ea.y), alpha_of(pwb.y, eb.y));  // Gaussian 1
+                const float2 ea = exponent(npy0), eb = exponent(npy1);
+                const float2 a0 = make_float2(alpha_of(ea.x, lo.x), alpha_of(eb.x, lo.x));  // Gaussian 0 at both pixels
+                const float2 a1 = make_float2(alpha_of(ea.y, lo.y), alpha_of(eb.y, lo.y));  // Gaussian 1
                 blend_pair(a0, a1, rec[3], rec[4], px);
             }
             __syncwarp();

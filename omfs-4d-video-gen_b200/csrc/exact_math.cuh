@@ -289,17 +289,22 @@ OMFS_HD void ex_view_dir(float mx, float my, float mz, const float* cam, float& 
 
 // one pixel x one Gaussian of U10.  Returns 0 = skip, 1 = blended, 2 = pixel saturated (stop).
 // exp2 is the only non-reproducible operation (device: ex2.approx, oracle: exp2f).
+//
+// Canonical order of the exponent e = lo + ca dx^2 + cb dx dy + cc dy^2 (conic pre-scaled by log2 e,
+// lo = log2(opacity)): the terms that depend only on the pixel COLUMN, c0 = lo + (ca dx) dx and
+// v = cb dx, are formed first, then e = (cc dy + v) dy + c0 — two fused operations per pixel once the
+// column terms exist (the compositing kernel shares them between the pixels of one column).  The published
+// `power > 0` rejection (a rounding artefact of a negative-definite form) reads `e > lo` here.
 template <typename Exp2>
 OMFS_HD int ex_blend(float gx, float gy, float ca, float cb, float cc, float lo, float r, float g, float b,
                      float pxf, float pyf, float& T, float& C0, float& C1, float& C2, Exp2 exp2_fn) {
     const float dx = gx - pxf, dy = gy - pyf;
-    const float t1 = ca * dx;
-    const float t2 = fmaf(cb, dy, t1);
-    float pw = t2 * dx;
-    const float t4 = cc * dy;
-    pw = fmaf(t4, dy, pw);
-    const float e = pw + lo;
-    if ((pw > 0.0f) | (e < kLog2Inv255)) return 0;  // one combined predicate, no short-circuit branch
+    const float u = ca * dx;
+    const float c0 = fmaf(u, dx, lo);
+    const float v = cb * dx;
+    const float s = fmaf(cc, dy, v);
+    const float e = fmaf(s, dy, c0);
+    if ((e > lo) | (e < kLog2Inv255)) return 0;  // one combined predicate, no short-circuit branch
     const float alpha = fminf(0.99f, exp2_fn(e));
     const float testT = T * (1.0f - alpha);
     if (testT < 0.0001f) return 2;
