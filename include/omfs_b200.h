@@ -116,12 +116,16 @@ int omfs_binning(int S, int N, int width, int height, size_t capacity,
                  uint32_t* d_num_pairs, int* d_status_flag, void* d_workspace, size_t workspace_bytes,
                  void* stream);
 
-/* U10: front-to-back alpha compositing, one 16x16 tile per CTA.  d_image[S,3,H,W];
- * d_image_u8 (optional) [S,H,W,3] gets the save_image quantisation in the same kernel. */
+/* U10: front-to-back alpha compositing, one warp per 8x8 pixel block.  d_image[S,3,H,W];
+ * d_image_u8 (optional) [S,H,W,3] gets the save_image quantisation in the same kernel.
+ * d_tickets (optional): OMFS_COMPOSITE_TICKET_BYTES of device memory, zero before its first use and not
+ * shared by launches that may run concurrently; the kernel leaves it zeroed.  With it the launch is one
+ * resident wave of persistent warps drawing work units from the counter; without it, one CTA per unit. */
+#define OMFS_COMPOSITE_TICKET_BYTES 16
 int omfs_composite(int S, int N, int width, int height,
                    const float* d_P0, const float* d_P1, const float* d_P2,
                    const uint32_t* d_sorted_vals, const uint32_t* d_ranges, const float* bg3,
-                   float* d_image, uint8_t* d_image_u8, void* stream);
+                   float* d_image, uint8_t* d_image_u8, void* d_tickets, void* stream);
 
 /* R5/R6 (01_Clinical_Engine/surgical_sim.py:25-47, 180-204, 262-329): half-space masks and the
  * rigid move of the two mobile segments, on an arbitrary point set, in float64.

@@ -64,11 +64,10 @@ __device__ __forceinline__ void unpack_extents(float w, float& bx, float& by) {
 #ifndef OMFS_COMP_WARPS
 #define OMFS_COMP_WARPS 1
 #endif
-#ifdef OMFS_COMP_MINCTAS
-#define OMFS_COMP_BOUNDS __launch_bounds__(32 * OMFS_COMP_WARPS, OMFS_COMP_MINCTAS)
-#else
-#define OMFS_COMP_BOUNDS __launch_bounds__(32 * OMFS_COMP_WARPS)
+#ifndef OMFS_COMP_RESIDENT_WARPS
+#define OMFS_COMP_RESIDENT_WARPS 32  // per SM: the 32-CTA cap with one-warp CTAs; needs <= 64 registers
 #endif
+#define OMFS_COMP_BOUNDS __launch_bounds__(32 * OMFS_COMP_WARPS, OMFS_COMP_RESIDENT_WARPS / OMFS_COMP_WARPS)
 #ifndef OMFS_COMP_UNROLL
 #define OMFS_COMP_UNROLL 2
 #endif
@@ -154,26 +153,49 @@ __device__ __forceinline__ void blend_pair(const float2 a0, const float2 a1, con
 // version saturated first (ncu l1tex__data_pipe_lsu_wavefronts 90 %) — and let the blend run packed.
 constexpr int kBlocksPerTile = 4;  // 8x8 pixel blocks (warps) per 16x16 tile
 
-__global__ void OMFS_COMP_BOUNDS composite_kernel(int N, int width, int height, const float4* __restrict__ P0,
+__global__ void OMFS_COMP_BOUNDS composite_kernel(int n_seg, int N, int width, int height, const float4* __restrict__ P0,
                                                        const float4* __restrict__ P1,
                                                        const float4* __restrict__ P2,
                                                        const uint32_t* __restrict__ vals,
                                                        const uint2* __restrict__ ranges, float bg0, float bg1,
                                                        float bg2, float* __restrict__ image,
-                                                       uint8_t* __restrict__ image_u8) {
+                                                       uint8_t* __restrict__ image_u8,
+                                                       unsigned long long* __restrict__ tickets) {
     // survivors of the current round, COMPACTED in depth order and stored as pairs (see kPairFloats)
     __shared__ float4 s_rec_all[kCompWarps][kPairSlots * 5];
     float4* s_rec = s_rec_all[threadIdx.x >> 5];
     float* s_f = reinterpret_cast<float*>(s_rec);
 
     const int gxt = (width + kTile - 1) / kTile, gyt = (height + kTile - 1) / kTile;
-    const int unit = blockIdx.x * kCompWarps + (threadIdx.x >> 5);  // (tile, pixel block) work unit of this warp
-    const int tile = unit / kBlocksPerTile, sub = unit % kBlocksPerTile, seg = blockIdx.y;
     const int lane = threadIdx.x & 31;
     const uint32_t lanemask_lt = (1u << lane) - 1u;
+    // the odd slot of a round with an odd survivor count is evaluated with whatever it holds, made
+    // harmless by lo = -inf: everything else in it must be finite, so start from zeros
+    for (int i = lane; i < kPairSlots * 5; i += 32) s_rec[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncwarp();
+
+    // Work units = (segment, tile, pixel block).  With a ticket counter the grid is ONE resident wave of
+    // persistent warps that draw units from it (the next ticket is requested while the current unit is
+    // processed, so the atomic's latency is hidden); without one the grid has a CTA per unit and the
+    // loop below runs once.  One CTA per unit leaves the SMs at ~72 % of their resident-warp limit (CTA
+    // launch latency against ~20 us of work per unit) and pays the prologue once per unit.
+    const int units_per_seg = gxt * gyt * kBlocksPerTile;
+    const long long units_total = (long long)n_seg * units_per_seg;
+    const long long unit_stride = (long long)gridDim.x * kCompWarps;
+    auto draw = [&]() -> long long {
+        unsigned long long t = 0;
+        if (lane == 0) t = atomicAdd(tickets, 1ull);
+        return (long long)__shfl_sync(0xffffffffu, t, 0);
+    };
+    long long unit = (long long)blockIdx.x * kCompWarps + (threadIdx.x >> 5), unit_next = 0;
+    if (tickets) unit = draw();
+    for (; unit < units_total; unit = unit_next) {
+    unit_next = tickets ? draw() : unit + unit_stride;
+    const int seg = (int)(unit / units_per_seg), rem = (int)(unit % units_per_seg);
+    const int tile = rem / kBlocksPerTile, sub = rem % kBlocksPerTile;
     const int bx0 = (tile % gxt) * kTile + (sub & 1) * 8;
     const int by0 = (tile / gxt) * kTile + (sub >> 1) * 8;
-    if (bx0 >= width || by0 >= height) return;  // pixel block entirely outside the image
+    if (bx0 >= width || by0 >= height) continue;  // pixel block entirely outside the image (cannot happen: tiles start inside)
     const int pxi = bx0 + (lane & 7);
     const int pyi = by0 + (lane >> 3);
     const float2 npx = make_float2(-(float)pxi, -(float)pxi);
@@ -187,11 +209,6 @@ __global__ void OMFS_COMP_BOUNDS composite_kernel(int N, int width, int height, 
     const float4* p0 = P0 + (size_t)seg * N;
     const float4* p1 = P1 + (size_t)seg * N;
     const float4* p2 = P2 + (size_t)seg * N;
-
-    // the odd slot of a round with an odd survivor count is evaluated with whatever it holds, made
-    // harmless by lo = -inf: everything else in it must be finite, so start from zeros
-    for (int i = lane; i < kPairSlots * 5; i += 32) s_rec[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    __syncwarp();
 
     // Software pipeline, three rounds deep, so that no load is consumed in the iteration that issued it
     // (index -> record -> conic are DEPENDENT gathers, each an L2 round trip):
@@ -313,6 +330,15 @@ __global__ void OMFS_COMP_BOUNDS composite_kernel(int N, int width, int height, 
             }
         }
     }
+    }  // work units
+    // the last warp to run out of tickets leaves the counter pair zeroed for the next launch
+    if (tickets && lane == 0) {
+        __threadfence();
+        if (atomicAdd(tickets + 1, 1ull) == (unsigned long long)unit_stride - 1ull) {
+            tickets[0] = 0ull;
+            tickets[1] = 0ull;
+        }
+    }
 }
 
 // float [S,3,H,W] -> uint8 [S,H,W,3] as a separate pass (used when only the float image exists)
@@ -336,19 +362,20 @@ using namespace omfs;
 
 extern "C" int omfs_composite(int S, int N, int width, int height, const float* d_P0, const float* d_P1,
                               const float* d_P2, const uint32_t* d_sorted_vals, const uint32_t* d_ranges,
-                              const float* bg3, float* d_image, uint8_t* d_image_u8, void* stream) {
+                              const float* bg3, float* d_image, uint8_t* d_image_u8, void* d_tickets, void* stream) {
     OMFS_REQUIRE(S >= 0 && N > 0 && width > 0 && height > 0, "bad sizes");
-    OMFS_REQUIRE(S <= 65535, "at most 65535 segments per call");
     OMFS_REQUIRE(d_P0 && d_P1 && d_P2 && d_sorted_vals && d_ranges && bg3, "null input");
     OMFS_REQUIRE(d_image || d_image_u8, "no output requested");
     if (S == 0) return OMFS_OK;
     const int tiles = ((width + kTile - 1) / kTile) * ((height + kTile - 1) / kTile);
-    OMFS_REQUIRE((long long)tiles * 8 < (1ll << 31), "too many tiles");
-    dim3 grid(tiles * kBlocksPerTile / kCompWarps, S);
-    composite_kernel<<<grid, 32 * kCompWarps, 0, (cudaStream_t)stream>>>(N, width, height, (const float4*)d_P0,
-                                                             (const float4*)d_P1, (const float4*)d_P2,
-                                                             d_sorted_vals, (const uint2*)d_ranges, bg3[0], bg3[1],
-                                                             bg3[2], d_image, d_image_u8);
+    const long long units = (long long)S * tiles * kBlocksPerTile;
+    const long long ctas_all = (units + kCompWarps - 1) / kCompWarps;
+    const long long wave = (long long)kNumSMs * (OMFS_COMP_RESIDENT_WARPS / kCompWarps);  // one resident wave of CTAs
+    OMFS_REQUIRE(d_tickets || ctas_all < (1ll << 31), "too many work units for one launch without a ticket counter");
+    const int grid = (int)((d_tickets && ctas_all > wave) ? wave : ctas_all);
+    composite_kernel<<<grid, 32 * kCompWarps, 0, (cudaStream_t)stream>>>(
+        S, N, width, height, (const float4*)d_P0, (const float4*)d_P1, (const float4*)d_P2, d_sorted_vals,
+        (const uint2*)d_ranges, bg3[0], bg3[1], bg3[2], d_image, d_image_u8, (unsigned long long*)d_tickets);
     count_launch();
     OMFS_LAUNCH_CHECK();
     return OMFS_OK;

@@ -145,10 +145,19 @@ def test_level1_stages_and_unsorted_keys(rt, small_scene):
     d_u8 = DA((S, H, W, 3), np.uint8)
     bg = (ctypes.c_float * 3)(1.0, 1.0, 1.0)
     rt.check(L.omfs_composite(S, N, W, H, d_P[0].ptr, d_P[1].ptr, d_P[2].ptr, d_vals.ptr, d_ranges.ptr, bg,
-                              d_img.ptr, d_u8.ptr, None))
+                              d_img.ptr, d_u8.ptr, None, None))
     img = d_img.numpy()
     assert np.abs(img - ref.image).max() <= 2e-4
     assert (oracle.to_uint8(ref.image) != d_u8.numpy()).mean() < 1e-4
+    # the persistent form (ticket counter) gives the same bits, and leaves its counter zeroed
+    d_tk = DA((2,), np.uint64)
+    d_tk.zero()
+    d_img2 = DA((S, 3, H, W), np.float32)
+    for _ in range(2):
+        rt.check(L.omfs_composite(S, N, W, H, d_P[0].ptr, d_P[1].ptr, d_P[2].ptr, d_vals.ptr, d_ranges.ptr, bg,
+                                  d_img2.ptr, None, d_tk.ptr, None))
+        assert np.array_equal(d_img2.numpy(), img)
+        assert not d_tk.numpy().any()
     d_u8b = DA((S, H, W, 3), np.uint8)
     rt.check(L.omfs_to_uint8(S, W, H, d_img.ptr, d_u8b.ptr, None))
     assert np.array_equal(d_u8b.numpy(), d_u8.numpy())
