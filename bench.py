@@ -62,6 +62,26 @@ def peaks():
     return 6650.0, 1590.0, "fallback"
 
 
+def bind_to_gpu_numa_node(gpu_index):
+    """Pin this rank's threads to the CPUs NVML reports as local to its GPU, BEFORE any pinned host buffer
+    is allocated (first touch then places the buffers on that NUMA node): with one process per GPU the
+    device->host frame traffic of 8 ranks otherwise crosses the socket interconnect."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = {w * 64 + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return f"{len(cpus)} cpus ({min(cpus)}-{max(cpus)})"
+    except Exception as e:  # affinity is an optimisation, never a failure
+        return f"unbound ({type(e).__name__})"
+    return "unbound"
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons while the timed region runs."""
 
@@ -188,6 +208,7 @@ def main():
         raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
@@ -421,7 +442,8 @@ def main():
                                   ("copy-engine peer-to-peer pushes (CUDA IPC, NVLink)" if args.gather == "p2p" else "NCCL gather") +
                                   " of every step's uint8 frames into rank 0 inside the timed region, on a second stream: step i's "
                                   "exchange overlaps step i+1's rendering; every rank waits for its last push before its end event "
-                                  "and the time is the max over ranks")},
+                                  "and the time is the max over ranks"),
+                       **({"host_numa": numa} if numa else {})},
             **({"diagnosis": "--no-gather: NOT a valid multi-GPU number"} if args.no_gather and world > 1 else {}),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "steps": e2e_steps, "note": "omfs_session_render_host: pinned host params in, uint8 frames out"},
