@@ -256,10 +256,21 @@ __global__ void __launch_bounds__(kEsThreads) emit_scatter_kernel(
         const int n_g = min(kEsChunk, N - g0);
         const size_t seg_off = (size_t)seg * N;
 
-        // ---- my 4 consecutive depth-ordered Gaussians: tile rectangles and pair counts
+        // ---- my 4 consecutive depth-ordered Gaussians: tile rectangles and pair counts.  The index loads,
+        // then the record gathers, are issued as independent batches (two dependent round trips per chunk
+        // instead of one chain per Gaussian); the pair count is the area of the rectangle, which is what
+        // the preprocess stored in tiles_touched (a culled Gaussian has radius 0 at (0,0): area 0).
         int rminx[kEsGpt], rminy[kEsGpt], rw[kEsGpt];
-        uint32_t cnt[kEsGpt];
+        uint32_t cnt[kEsGpt], gq[kEsGpt];
+        float4 pq[kEsGpt];
         uint32_t acc = 0;
+#pragma unroll
+        for (int q = 0; q < kEsGpt; q++) {
+            const int li = threadIdx.x * kEsGpt + q;
+            gq[q] = (li < n_g) ? __ldg(perm + seg_off + g0 + li) : 0u;
+        }
+#pragma unroll
+        for (int q = 0; q < kEsGpt; q++) pq[q] = ldg4(P0 + seg_off + gq[q]);
 #pragma unroll
         for (int q = 0; q < kEsGpt; q++) {
             const int li = threadIdx.x * kEsGpt + q;
@@ -267,13 +278,11 @@ __global__ void __launch_bounds__(kEsThreads) emit_scatter_kernel(
             rminx[q] = rminy[q] = 0;
             rw[q] = 1;
             if (li < n_g) {
-                const uint32_t g = __ldg(perm + seg_off + g0 + li);
-                s_gidx[li] = g;
-                const uint32_t t = __ldg(tt + seg_off + g);
+                s_gidx[li] = gq[q];
+                int minx, miny, maxx, maxy;
+                ex_tile_rect(pq[q].x, pq[q].y, __float_as_int(pq[q].w), gx, gy, minx, miny, maxx, maxy);
+                const uint32_t t = (uint32_t)((maxx - minx) * (maxy - miny));
                 if (t) {
-                    const float4 p = ldg4(P0 + seg_off + g);
-                    int minx, miny, maxx, maxy;
-                    ex_tile_rect(p.x, p.y, __float_as_int(p.w), gx, gy, minx, miny, maxx, maxy);
                     rminx[q] = minx;
                     rminy[q] = miny;
                     rw[q] = maxx - minx;
