@@ -156,6 +156,8 @@ struct DevBuf {
     }
 };
 
+constexpr int kCompPipelinedWarps = 20;
+
 struct omfs_session {
     omfs_session_config cfg{};
     int V = 0, F = 0, n_expr = 0, N = 0, kpad = 0, npad = 0, tiles = 0;
@@ -567,7 +569,11 @@ static int render_core(omfs_session* s, int T, int n_views, const float* p_expr,
             uint8_t* dst_8 = direct ? (out_u8 ? out_u8 + seg0 * 3 * hw : nullptr) : (out_u8 ? img8 : nullptr);
             if (!dst_f && !dst_8) dst_f = img;  // nothing requested: still render (debug taps)
             if ((rc = mark(kStComposite))) return rc;
-            if ((rc = omfs_composite(S, N, W, H, P0, P1, P2, vals, ranges, s->cfg.bg, dst_f, dst_8, s->tickets.p, cst))) return rc;
+            // Pipelined: the persistent compositing warps leave 12 of the 32 warp slots per SM to the front end of
+            // the next batch (measured on the 512^2 / 100k clip: 20 -> 32.0k frames/s, 32 -> 31.4k, 16 -> 30.5k).
+            if ((rc = composite_launch(S, N, W, H, P0, P1, P2, vals, ranges, s->cfg.bg, dst_f, dst_8, s->tickets.p,
+                                       pipelined ? kCompPipelinedWarps : 0, cst)))
+                return rc;
             if ((rc = mark(-1))) return rc;
             if (pipelined) {
                 OMFS_CUDA(cudaEventRecord(s->ev_comp[ib], cst));

@@ -56,6 +56,12 @@ int binning_rebuild_keys(int S, int N, int width, int height, size_t capacity, c
                          const uint32_t* d_vals, const float* d_P0, uint64_t* d_keys64, void* d_workspace,
                          cudaStream_t stream);
 
+// compositing (composite.cu) with an explicit number of persistent warps per SM (0 = fill the SM).  The
+// session launches fewer than fit (kCompPipelinedWarps) when the next batch's front end runs beside it.
+int composite_launch(int S, int N, int width, int height, const float* d_P0, const float* d_P1, const float* d_P2,
+                     const uint32_t* d_sorted_vals, const uint32_t* d_ranges, const float* bg3, float* d_image,
+                     uint8_t* d_image_u8, void* d_tickets, int warps_per_sm, cudaStream_t stream);
+
 // 128-bit streaming loads / stores.  The frame-invariant avatar streams and per-frame records are
 // read through the read-only path; outputs that the next kernel re-reads stay default-cached so
 // they can live in the 126 MB L2 between the kernels of one batch.

@@ -17,6 +17,8 @@
 // instructions each: the FP32/SFU issue rate binds, not HBM; bench.py reports both.
 #include <cuda_fp16.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 #include "exact_math.cuh"
 
@@ -360,9 +362,10 @@ __global__ void __launch_bounds__(256) to_uint8_kernel(long long n_pix_total, lo
 
 using namespace omfs;
 
-extern "C" int omfs_composite(int S, int N, int width, int height, const float* d_P0, const float* d_P1,
-                              const float* d_P2, const uint32_t* d_sorted_vals, const uint32_t* d_ranges,
-                              const float* bg3, float* d_image, uint8_t* d_image_u8, void* d_tickets, void* stream) {
+namespace omfs {
+int composite_launch(int S, int N, int width, int height, const float* d_P0, const float* d_P1, const float* d_P2,
+                     const uint32_t* d_sorted_vals, const uint32_t* d_ranges, const float* bg3, float* d_image,
+                     uint8_t* d_image_u8, void* d_tickets, int warps_per_sm, cudaStream_t stream) {
     OMFS_REQUIRE(S >= 0 && N > 0 && width > 0 && height > 0, "bad sizes");
     OMFS_REQUIRE(d_P0 && d_P1 && d_P2 && d_sorted_vals && d_ranges && bg3, "null input");
     OMFS_REQUIRE(d_image || d_image_u8, "no output requested");
@@ -370,15 +373,24 @@ extern "C" int omfs_composite(int S, int N, int width, int height, const float* 
     const int tiles = ((width + kTile - 1) / kTile) * ((height + kTile - 1) / kTile);
     const long long units = (long long)S * tiles * kBlocksPerTile;
     const long long ctas_all = (units + kCompWarps - 1) / kCompWarps;
-    const long long wave = (long long)kNumSMs * (OMFS_COMP_RESIDENT_WARPS / kCompWarps);  // one resident wave of CTAs
+    if (warps_per_sm <= 0 || warps_per_sm > OMFS_COMP_RESIDENT_WARPS) warps_per_sm = OMFS_COMP_RESIDENT_WARPS;
+    const long long wave = (long long)kNumSMs * std::max(1, warps_per_sm / kCompWarps);  // persistent CTAs
     OMFS_REQUIRE(d_tickets || ctas_all < (1ll << 31), "too many work units for one launch without a ticket counter");
     const int grid = (int)((d_tickets && ctas_all > wave) ? wave : ctas_all);
-    composite_kernel<<<grid, 32 * kCompWarps, 0, (cudaStream_t)stream>>>(
+    composite_kernel<<<grid, 32 * kCompWarps, 0, stream>>>(
         S, N, width, height, (const float4*)d_P0, (const float4*)d_P1, (const float4*)d_P2, d_sorted_vals,
         (const uint2*)d_ranges, bg3[0], bg3[1], bg3[2], d_image, d_image_u8, (unsigned long long*)d_tickets);
     count_launch();
     OMFS_LAUNCH_CHECK();
     return OMFS_OK;
+}
+}  // namespace omfs
+
+extern "C" int omfs_composite(int S, int N, int width, int height, const float* d_P0, const float* d_P1,
+                              const float* d_P2, const uint32_t* d_sorted_vals, const uint32_t* d_ranges,
+                              const float* bg3, float* d_image, uint8_t* d_image_u8, void* d_tickets, void* stream) {
+    return composite_launch(S, N, width, height, d_P0, d_P1, d_P2, d_sorted_vals, d_ranges, bg3, d_image, d_image_u8,
+                            d_tickets, 0, (cudaStream_t)stream);
 }
 
 extern "C" int omfs_to_uint8(int S, int width, int height, const float* d_image, uint8_t* d_out, void* stream) {
