@@ -127,6 +127,15 @@ int omfs_composite(int S, int N, int width, int height,
                    const uint32_t* d_sorted_vals, const uint32_t* d_ranges, const float* bg3,
                    float* d_image, uint8_t* d_image_u8, void* d_tickets, void* stream);
 
+/* R9 on device (02_Visual_Engine/validation_reporting.py:16-37): the moments behind PSNR and the global SSIM
+ * of T pairs of uint8 frames [T,H,W,3] resident in HBM, one pass over both sets.
+ *   d_moments[T][6] (float64) = sum (a-b)^2 over all channel values (exact), then with x, y the float32
+ *   BT.601 luma of a, b: sum x, sum y, sum x^2, sum y^2, sum xy.
+ * The host finishes MSE -> PSNR (99.0 when identical) and moments -> SSIM.  Frame sets must be 4-byte
+ * aligned; H*W*3 must be a multiple of 4 when T > 1. */
+int omfs_frame_metrics(int T, int height, int width, const uint8_t* d_a_u8, const uint8_t* d_b_u8,
+                       double* d_moments, void* stream);
+
 /* R5/R6 (01_Clinical_Engine/surgical_sim.py:25-47, 180-204, 262-329): half-space masks and the
  * rigid move of the two mobile segments, on an arbitrary point set, in float64.
  *   planes[3][8]  = {nx,ny,nz, ox,oy,oz, 0,0} for Le Fort, BSSO-L, BSSO-R (normals from

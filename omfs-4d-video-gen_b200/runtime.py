@@ -100,6 +100,7 @@ def load_library():
     L.omfs_binning_sort_bits.argtypes = [c_int, c_int, c_int]
     L.omfs_composite.argtypes = [c_int, c_int, c_int, c_int, vp, vp, vp, vp, vp, POINTER(c_float), vp, vp, vp, vp]
     L.omfs_to_uint8.argtypes = [c_int, c_int, c_int, vp, vp, vp]
+    L.omfs_frame_metrics.argtypes = [c_int, c_int, c_int, vp, vp, vp, vp]
     L.omfs_displace_points.argtypes = [c_int, vp, POINTER(c_double), POINTER(c_double), vp, c_int, vp, vp, vp, vp]
     L.omfs_device_check.argtypes = [c_int]
     L.omfs_ipc_export.argtypes = [c_void_p, c_void_p]

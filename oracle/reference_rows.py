@@ -218,6 +218,69 @@ def psnr(a: np.ndarray, b: np.ndarray) -> float:
     return 20.0 * math.log10(255.0 / math.sqrt(mse))
 
 
+def ssim_global(a: np.ndarray, b: np.ndarray) -> float:
+    """02_Visual_Engine/validation_reporting.py:23-37: one global SSIM over the whole image, on the
+    BT.601 luma of RGB inputs (computed in the input dtype, float32 in the report), moments in float64."""
+    if a.ndim == 3:
+        a = (0.299 * a[:, :, 0] + 0.587 * a[:, :, 1] + 0.114 * a[:, :, 2])
+    if b.ndim == 3:
+        b = (0.299 * b[:, :, 0] + 0.587 * b[:, :, 1] + 0.114 * b[:, :, 2])
+    a = a.astype(np.float64)
+    b = b.astype(np.float64)
+    mu_x, mu_y = a.mean(), b.mean()
+    sig_x = ((a - mu_x) ** 2).mean()
+    sig_y = ((b - mu_y) ** 2).mean()
+    sig_xy = ((a - mu_x) * (b - mu_y)).mean()
+    c1, c2 = (0.01 * 255) ** 2, (0.03 * 255) ** 2
+    return float(((2 * mu_x * mu_y + c1) * (2 * sig_xy + c2)) / ((mu_x * mu_x + mu_y * mu_y + c1) * (sig_x + sig_y + c2)))
+
+
+def bucket(progress: float) -> str:
+    """validation_reporting.py:40-45."""
+    if progress < 0.20 or progress > 0.80:
+        return "front"
+    if 0.35 <= progress <= 0.65:
+        return "profile"
+    return "rear"
+
+
+def report_rows(exports: list, renders: dict, gts: dict) -> dict:
+    """validation_reporting.py:58-105 without the file system: `exports` are the manifest rows, `renders` /
+    `gts` map a source file name to a float32 [H,W,3] array.  Returns {"summary", "rows"}."""
+    metrics = []
+    max_index = max((int(r.get("index", 0)) for r in exports), default=1)
+    for row in exports:
+        idx, name = int(row["index"]), row["source"]
+        if name not in renders or name not in gts:
+            continue
+        progress = idx / max(1, max_index)
+        metrics.append({"index": idx, "frame": name, "progress": progress, "bucket": bucket(progress),
+                        "psnr": psnr(renders[name], gts[name]), "ssim": ssim_global(renders[name], gts[name])})
+    summary = {"count": len(metrics), "by_bucket": {}}
+    for bk in ("front", "profile", "rear"):
+        vals = [m for m in metrics if m["bucket"] == bk]
+        if not vals:
+            summary["by_bucket"][bk] = {"count": 0, "psnr": None, "ssim": None}
+            continue
+        summary["by_bucket"][bk] = {"count": len(vals), "psnr": float(np.mean([v["psnr"] for v in vals])),
+                                    "ssim": float(np.mean([v["ssim"] for v in vals]))}
+    return {"summary": summary, "rows": metrics}
+
+
+def frame_moments(a_u8: np.ndarray, b_u8: np.ndarray) -> np.ndarray:
+    """What omfs_frame_metrics accumulates per frame pair, in float64: [sum (a-b)^2 over all channel values,
+    sum x, sum y, sum x^2, sum y^2, sum xy] with x, y the float32 BT.601 luma (validation_reporting.py:24-27
+    order of operations).  a_u8, b_u8: [T,H,W,3] uint8."""
+    out = np.empty((a_u8.shape[0], 6), dtype=np.float64)
+    for t in range(a_u8.shape[0]):
+        a, b = a_u8[t].astype(np.float32), b_u8[t].astype(np.float32)
+        d = a_u8[t].astype(np.int64) - b_u8[t].astype(np.int64)
+        x = (np.float32(0.299) * a[:, :, 0] + np.float32(0.587) * a[:, :, 1] + np.float32(0.114) * a[:, :, 2]).astype(np.float64)
+        y = (np.float32(0.299) * b[:, :, 0] + np.float32(0.587) * b[:, :, 1] + np.float32(0.114) * b[:, :, 2]).astype(np.float64)
+        out[t] = [float((d * d).sum()), x.sum(), y.sum(), (x * x).sum(), (y * y).sum(), (x * y).sum()]
+    return out
+
+
 # ---------------------------------------------------------------------------- fixture of test_surgical_sim
 def uv_sphere(radius=30.0, center=(0.0, 0.0, 0.0), theta_resolution=20, phi_resolution=20) -> np.ndarray:
     """Point set with the layout of pv.Sphere / vtkSphereSource (test/test_surgical_sim.py:18-25):

@@ -232,10 +232,57 @@ def golden_psnr():
     print("psnr golden:", vr.psnr(a, b), vr.psnr(a, a))
 
 
+def golden_report():
+    """R9 + the strict report (validation_reporting.py:16-123) and the deterministic export
+    (render_surgery.py:365-409), run as shipped on a small synthetic model directory: 12 frames of 24x20
+    renders / gt, exported with max_frames=12, then generate_report.  The frames, the manifest rows and the
+    report JSON are stored; ssim_global / psnr of two float images as well."""
+    sys.path.insert(0, os.path.join(REF, "02_Visual_Engine"))
+    import render_surgery as rs
+    import validation_reporting as vr
+    from pathlib import Path
+    from PIL import Image
+
+    rng = np.random.default_rng(21)
+    T, H, W = 12, 20, 24
+    yy, xx = np.mgrid[0:H, 0:W]
+    gt = np.stack([np.stack([(xx * 9 + t * 7) % 256, (yy * 11 + t * 3) % 256, ((xx + yy) * 5 + t * 13) % 256], -1)
+                   for t in range(T)]).astype(np.uint8)
+    noise = rng.normal(0, 6.0, gt.shape)
+    noise[4] = 0.0  # one identical pair (index 4 is exported): psnr 99.0
+    renders = np.clip(gt.astype(np.float64) + noise, 0, 255).astype(np.uint8)
+    with tempfile.TemporaryDirectory() as d:
+        model = Path(d) / "model"
+        for it in (500, 3000):
+            (model / "train" / f"ours_{it}" / "renders").mkdir(parents=True)
+            (model / "train" / f"ours_{it}" / "gt").mkdir(parents=True)
+        for t in range(T):
+            Image.fromarray(renders[t]).save(model / "train" / "ours_3000" / "renders" / f"{t:05d}.png")
+            Image.fromarray(gt[t]).save(model / "train" / "ours_3000" / "gt" / f"{t:05d}.png")
+        det = Path(d) / "det"
+        rs.export_deterministic_frames(str(model / "train" / "ours_3000" / "renders"), str(det), None, 12)
+        manifest = json.load(open(det / "deterministic_indices_manifest.json"))
+        out = Path(d) / "report"
+        vr.generate_report(model, det, out)
+        report = json.load(open(out / "strict_scores.json"))
+        checklist = (out / "human_review_checklist.md").read_text()
+    a = renders[5].astype(np.float32)
+    b = gt[5].astype(np.float32)
+    np.savez_compressed(os.path.join(HERE, "report_golden.npz"), renders=renders, gt=gt,
+                        manifest_exports=json.dumps(manifest["exports"]),
+                        selected=np.array(manifest["selected_indices"], dtype=np.int64),
+                        report=json.dumps(report), checklist=checklist,
+                        ssim_ab=np.float64(vr.ssim_global(a, b)), ssim_aa=np.float64(vr.ssim_global(a, a)),
+                        ssim_gray=np.float64(vr.ssim_global(a[:, :, 0], b[:, :, 1])),
+                        buckets=json.dumps({str(p): vr._bucket(p) for p in (0.0, 0.19, 0.2, 0.3, 0.35, 0.5, 0.65, 0.7, 0.8, 0.81, 1.0)}))
+    print("report golden:", report["summary"])
+
+
 if __name__ == "__main__":
     if not os.path.isdir(REF):
         raise SystemExit("the reference tree is not available here; the committed goldens are authoritative")
     golden_render_surgery()
     golden_psnr()
+    golden_report()
     golden_surgical_sim()
     golden_simple_flame()

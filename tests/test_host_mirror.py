@@ -163,6 +163,38 @@ def test_psnr_mirror(golden_dir):
     assert validation_reporting.psnr(g["a"], g["a"]) == 99.0
 
 
+def test_validation_report_mirror(golden_dir, tmp_path):
+    """generate_report on PNG files rebuilt from the golden frames writes the reference's JSON and checklist;
+    error behaviour follows validation_reporting.py:48-70."""
+    import json
+    from PIL import Image
+    g = np.load(os.path.join(golden_dir, "report_golden.npz"))
+    model = tmp_path / "model"
+    for it in (500, 3000):
+        (model / "train" / f"ours_{it}" / "renders").mkdir(parents=True)
+        (model / "train" / f"ours_{it}" / "gt").mkdir(parents=True)
+    for t in range(len(g["renders"])):
+        Image.fromarray(g["renders"][t]).save(model / "train" / "ours_3000" / "renders" / f"{t:05d}.png")
+        Image.fromarray(g["gt"][t]).save(model / "train" / "ours_3000" / "gt" / f"{t:05d}.png")
+    det = tmp_path / "det"
+    rs.export_deterministic_frames(str(model / "train" / "ours_3000" / "renders"), str(det), None, 12)
+    out = tmp_path / "report"
+    validation_reporting.generate_report(model, det, out)
+    assert json.load(open(out / "strict_scores.json")) == json.loads(str(g["report"]))
+    assert (out / "human_review_checklist.md").read_text() == str(g["checklist"])
+    a, b = g["renders"][5].astype(np.float32), g["gt"][5].astype(np.float32)
+    assert validation_reporting.ssim_global(a, b) == float(g["ssim_ab"])
+    for p, name in json.loads(str(g["buckets"])).items():
+        assert validation_reporting._bucket(float(p)) == name
+    with pytest.raises(FileNotFoundError):
+        validation_reporting.generate_report(tmp_path / "nope", det, out)
+    with pytest.raises(FileNotFoundError):
+        validation_reporting.generate_report(model, tmp_path / "no_manifest", out)
+    os.makedirs(tmp_path / "m2" / "train")
+    with pytest.raises(FileNotFoundError):
+        validation_reporting._find_latest_train_dir(tmp_path / "m2")
+
+
 def test_avatar_bake_is_the_upstream_activation():
     from omfs_b200 import avatar
     av = synthetic.make_avatar(500, 100, seed=3)

@@ -176,3 +176,37 @@ def test_blendshape_gemm_formulation_matches_einsum(golden_dir):
     v_ein = g["v_template"][None] + np.einsum("ijk,bk->bij", sd[:, :, :100], g["shape"]) + \
         np.einsum("ijk,bk->bij", sd[:, :, 300:350], g["expr"])
     np.testing.assert_allclose(v_gemm.reshape(v_ein.shape), v_ein, rtol=0, atol=1e-6)
+
+
+def test_ssim_bucket_and_report_match_reference(golden_dir):
+    """validation_reporting.py run as shipped (tests/golden/make_golden.py: golden_report) against the
+    restatement: ssim_global, _bucket, and the whole report (rows and per-bucket summary)."""
+    import json
+    g = _load(golden_dir, "report_golden.npz")
+    a, b = g["renders"][5].astype(np.float32), g["gt"][5].astype(np.float32)
+    assert rr.ssim_global(a, b) == float(g["ssim_ab"])
+    assert rr.ssim_global(a, a) == float(g["ssim_aa"]) == 1.0
+    assert rr.ssim_global(a[:, :, 0], b[:, :, 1]) == float(g["ssim_gray"])
+    for p, name in json.loads(str(g["buckets"])).items():
+        assert rr.bucket(float(p)) == name
+    exports = json.loads(str(g["manifest_exports"]))
+    assert [e["index"] for e in exports] == list(g["selected"])
+    renders = {f"{t:05d}.png": g["renders"][t].astype(np.float32) for t in range(len(g["renders"]))}
+    gts = {f"{t:05d}.png": g["gt"][t].astype(np.float32) for t in range(len(g["gt"]))}
+    assert rr.report_rows(exports, renders, gts) == json.loads(str(g["report"]))
+
+
+def test_frame_moments_reproduce_report_metrics(golden_dir):
+    """The six moments omfs_frame_metrics accumulates give the reference's PSNR / SSIM back (PSNR to 1e-5 dB:
+    the reference averages squared errors in float32; SSIM to 1e-12)."""
+    import json
+    import omfs_b200  # noqa: F401
+    from omfs_b200 import validation_reporting as vrep
+    g = _load(golden_dir, "report_golden.npz")
+    m = rr.frame_moments(g["renders"], g["gt"])
+    p, s = vrep.metrics_from_moments(m, g["renders"].shape[1] * g["renders"].shape[2])
+    rows = {r["index"]: r for r in json.loads(str(g["report"]))["rows"]}
+    for i, r in rows.items():
+        assert abs(p[i] - r["psnr"]) <= 1e-5
+        assert abs(s[i] - r["ssim"]) <= 1e-12
+    assert p[4] == 99.0
