@@ -172,6 +172,24 @@ def _write_png(path: str, rgb_u8: np.ndarray) -> None:
     Image.fromarray(rgb_u8, mode="RGB").save(path, compress_level=1)
 
 
+def write_frames_png(renders_dir: str, frames_u8: np.ndarray, workers: int | None = None) -> list[str]:
+    """The frame sink: uint8 [T,H,W,3] -> renders_dir/%05d.png (the names the reference's upstream renderer
+    writes, render_surgery.py:324-362).  After the GPU path the PNG encode is the wall-clock bottleneck of
+    render_with_gaussians, so the files are written by a thread pool (zlib releases the GIL)."""
+    from concurrent.futures import ThreadPoolExecutor
+    os.makedirs(renders_dir, exist_ok=True)
+    paths = [os.path.join(renders_dir, f"{i:05d}.png") for i in range(len(frames_u8))]
+    if workers is None:
+        workers = min(16, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
+    if workers <= 1 or len(paths) <= 1:
+        for q, img in zip(paths, frames_u8):
+            _write_png(q, img)
+    else:
+        with ThreadPoolExecutor(max_workers=workers) as pool:
+            list(pool.map(_write_png, paths, frames_u8))
+    return paths
+
+
 def render_with_gaussians(model_path: str, data_dir: str, iteration: int = -1,
                           clear_old_renders: bool = True) -> str:
     """Render every train-split frame of `data_dir` with the avatar in `model_path`.
@@ -203,9 +221,7 @@ def render_with_gaussians(model_path: str, data_dir: str, iteration: int = -1,
     except Exception as e:  # the reference surfaces renderer failures as RuntimeError (:317-322)
         raise RuntimeError(f"Rendering failed:\n{str(e)[-2000:]}") from e
     renders_dir = os.path.join(train_dir, f"ours_{it}", "renders")
-    os.makedirs(renders_dir, exist_ok=True)
-    for i, img in enumerate(images):
-        _write_png(os.path.join(renders_dir, f"{i:05d}.png"), img)
+    write_frames_png(renders_dir, images)
     print(f"[render_surgery] Frames rendered to: {renders_dir}")
     return renders_dir
 
@@ -301,6 +317,27 @@ def stitch_video(frames_dir: str, output_path: str, fps: int = 30):
         shutil.rmtree(seq, ignore_errors=True)
     if result.returncode != 0:
         raise RuntimeError(f"ffmpeg failed:\n{result.stderr}")
+    print(f"[render_surgery] Video saved to {output_path}")
+
+
+def stitch_video_frames(frames_u8: np.ndarray, output_path: str, fps: int = 30):
+    """stitch_video for frames that are already in memory: the uint8 frames go to ffmpeg's stdin as raw RGB24,
+    with the reference's codec settings (libx264, yuv420p, preset medium, crf 18; render_surgery.py:432-443).
+    This replaces the reference's copy of every PNG into a temporary frame_%05d.png sequence (:425-429) and the
+    PNG decode inside ffmpeg."""
+    frames_u8 = np.ascontiguousarray(frames_u8, dtype=np.uint8)
+    if frames_u8.ndim != 4 or frames_u8.shape[3] != 3 or len(frames_u8) == 0:
+        raise FileNotFoundError("No frames to stitch")
+    ffmpeg_bin = _get_ffmpeg_path()
+    out_dir = os.path.dirname(output_path)
+    if out_dir:
+        os.makedirs(out_dir, exist_ok=True)
+    _, h, w, _ = frames_u8.shape
+    cmd = [ffmpeg_bin, "-y", "-f", "rawvideo", "-pix_fmt", "rgb24", "-s", f"{w}x{h}", "-framerate", str(fps),
+           "-i", "-", "-c:v", "libx264", "-pix_fmt", "yuv420p", "-preset", "medium", "-crf", "18", output_path]
+    result = subprocess.run(cmd, input=frames_u8.tobytes(), capture_output=True)
+    if result.returncode != 0:
+        raise RuntimeError(f"ffmpeg failed:\n{result.stderr.decode(errors='replace')}")
     print(f"[render_surgery] Video saved to {output_path}")
 
 

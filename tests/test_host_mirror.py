@@ -163,6 +163,37 @@ def test_psnr_mirror(golden_dir):
     assert validation_reporting.psnr(g["a"], g["a"]) == 99.0
 
 
+def test_frame_sink(tmp_path, monkeypatch):
+    """write_frames_png writes the upstream names and round-trips the pixels; stitch_video_frames hands the raw
+    frames to ffmpeg with the reference's codec flags (a stand-in ffmpeg records what it was given)."""
+    from PIL import Image
+    rng = np.random.default_rng(5)
+    frames = rng.integers(0, 256, (7, 12, 16, 3), dtype=np.uint8)
+    paths = rs.write_frames_png(str(tmp_path / "renders"), frames, workers=3)
+    assert [os.path.basename(q) for q in paths] == [f"{i:05d}.png" for i in range(7)]
+    for q, f in zip(paths, frames):
+        assert np.array_equal(np.asarray(Image.open(q)), f)
+    fake = tmp_path / "ffmpeg"
+    fake.write_text("#!/bin/sh\nfor a in \"$@\"; do echo \"$a\" >> %s; done\ncat > %s\n" %
+                    (tmp_path / "args.txt", tmp_path / "stdin.bin"))
+    fake.chmod(0o755)
+    monkeypatch.setattr(rs, "_get_ffmpeg_path", lambda: str(fake))
+    rs.stitch_video_frames(frames, str(tmp_path / "out" / "v.mp4"), fps=25)
+    args = (tmp_path / "args.txt").read_text().split("\n")
+    for flag, val in (("-s", "16x12"), ("-framerate", "25"), ("-c:v", "libx264"), ("-crf", "18"), ("-preset", "medium")):
+        assert args[args.index(flag) + 1] == val
+    assert args[args.index("-i") + 1] == "-" and args[-2] == str(tmp_path / "out" / "v.mp4")
+    assert (tmp_path / "stdin.bin").read_bytes() == frames.tobytes()
+    bad = tmp_path / "ffmpeg_bad"
+    bad.write_text("#!/bin/sh\ncat > /dev/null\necho boom >&2\nexit 3\n")
+    bad.chmod(0o755)
+    monkeypatch.setattr(rs, "_get_ffmpeg_path", lambda: str(bad))
+    with pytest.raises(RuntimeError, match="ffmpeg failed"):
+        rs.stitch_video_frames(frames, str(tmp_path / "v2.mp4"))
+    with pytest.raises(FileNotFoundError):
+        rs.stitch_video_frames(frames[:0], str(tmp_path / "v3.mp4"))
+
+
 def test_validation_report_mirror(golden_dir, tmp_path):
     """generate_report on PNG files rebuilt from the golden frames writes the reference's JSON and checklist;
     error behaviour follows validation_reporting.py:48-70."""
