@@ -10,7 +10,7 @@ $CMD > gpurun_out/${tag}_plain.log 2>&1 || { echo "plain run failed"; exit 1; }
 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,smsp__inst_executed.sum --clock-control none -c 400 --csv \
     --log-file gpurun_out/${tag}_launches.csv $CMD > gpurun_out/${tag}_ncu1.log 2>&1
 ncu --set full --clock-control none --import-source on \
-    -k regex:'composite_kernel|emit_scatter|bind_preprocess|flame_blend_tc|rs_onesweep|tile_count' -s 6 -c 9 \
+    -k regex:'composite_kernel|emit_scatter|bind_preprocess|flame_blend_tc|rs_onesweep|tile_count|face_frames|flame_lbs' -s 6 -c 12 \
     -o gpurun_out/${tag}_full -f $CMD > gpurun_out/${tag}_ncu2.log 2>&1
 ls -la gpurun_out/${tag}_*
 python -c "
