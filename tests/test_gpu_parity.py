@@ -202,6 +202,43 @@ def test_ragged_batches_views_and_odd_image_size(rt):
     sess.close()
 
 
+def test_tapered_multi_batch_call_and_dense_opaque_splats(rt):
+    """A host-output call of many batches (the session tapers its last batch: 24 frames in batches of 8 become
+    8,8,4,4) over an avatar of LARGE, nearly opaque Gaussians: long tile lists, every pixel saturates, so
+    the early-termination rule (T < 1e-4 stops BEFORE the Gaussian is blended), the parked-pixel path and the
+    per-warp early exit all decide the image.  Against the oracle on the same vertices, every frame."""
+    import omfs_b200  # noqa: F401
+    import oracle
+    from omfs_b200 import avatar, synthetic
+    W, H, T = 96, 64, 24
+    model = synthetic.make_flame_model(seed=21, n_verts=642)
+    params = synthetic.make_frame_params(T, seed=22, n_verts=642)
+    av = synthetic.make_avatar(5000, model.n_faces, seed=23)
+    av.scaling[:] = av.scaling + np.float32(1.2)      # log-scales: 3.3x larger splats
+    av.opacity[:] = np.abs(av.opacity) + np.float32(3.0)   # logits >= 3: alpha saturates at 0.99 near the centre
+    baked = avatar.bake(av)
+    cam = synthetic.make_camera(W, H)
+    sess = rt.Session(model, baked, W, H, max_batch=8)
+    sess.set_subject(params.shape, params.static_offset)
+    u8, img = sess.render_host(params, [cam], want_f32=True)
+    assert sess.stats()["batches"] == 4
+    # vertices of the whole call are not kept (FLAME runs per chunk, taps hold the last one): compare against the
+    # independent oracle chain with the knife-edge allowance, and pin the decisions on a single-batch call below
+    full = oracle.render(model, params, baked, [cam.pack()] * T, W, H)
+    assert full.binned.n_pairs / (T * 24) > 400            # long lists: > 400 pairs per tile on average
+    assert_independent_image_parity(img, full.image)
+    assert (oracle.to_uint8(full.image) != u8).mean() < 2e-3
+    sess.close()
+    sess, u8b, imgb = run_session(rt, model, params, baked, [cam], W, H, max_batch=T)
+    verts = sess.tap_array("verts", (T, 642, 3), np.float32)
+    ref = oracle.render(model, params, baked, [cam.pack()] * T, W, H, verts=verts)
+    assert np.abs(imgb - ref.image).max() <= 2e-4
+    assert np.array_equal(imgb, img) and np.array_equal(u8b, u8)   # batching does not change a bit
+    # most pixels of the head saturated: transmittance left is below the stop threshold
+    assert (ref.image[:, :, H // 2, W // 2] < 1.0).all()
+    sess.close()
+
+
 def test_empty_and_fully_culled(rt, small_scene):
     """No frames -> no work; a camera looking away culls everything -> background only, zero pairs."""
     import oracle
