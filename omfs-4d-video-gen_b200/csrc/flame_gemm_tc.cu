@@ -4,26 +4,39 @@
 //
 // sm_100a design:
 //   * operands are K-major fp32 rows; TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B) stages
-//     128 x 32 (A) and 128 x 32 (B) tiles into a 4-deep shared-memory ring — 128 bytes per row is
+//     128 x 32 (A) and 256 x 32 (B) tiles into a 2-deep shared-memory ring — 128 bytes per row is
 //     exactly one swizzle atom, which is what the UMMA shared-memory descriptor expects;
-//   * one elected thread issues tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=128, K=8 per
-//     instruction, four per stage); the fp32 accumulator lives in 128 TMEM columns;
+//   * one elected thread issues tcgen05.mma.cta_group::1.kind::tf32 (M=128, N=256, K=8 per
+//     instruction, four per stage); the fp32 accumulator lives in 256 TMEM columns;
 //   * tcgen05.commit releases smem stages back to the TMA warp and finally signals the epilogue,
-//     which reads TMEM with tcgen05.ld (32 lanes x 32 columns per instruction), adds the per-subject
-//     base row and writes VP with 16-byte stores;
-//   * rows of A beyond T and the K tail beyond K3 come back as zeros from TMA's out-of-bounds
-//     fill, so no operand padding is needed in HBM.
+//     which reads TMEM with tcgen05.ld (32 lanes x 32 columns per instruction), transposes each 32x32
+//     chunk through shared memory, adds the per-subject base row and writes VP as full 128-byte rows;
+//   * rows of A beyond T, rows of B beyond npad and the K tail beyond K3 come back as zeros from TMA's
+//     out-of-bounds fill, so no operand padding is needed in HBM.
 // Warp roles (192 threads): warps 0-3 epilogue (warp id % 4 selects the TMEM lane quarter),
-// warp 4 TMA producer, warp 5 TMEM allocation + MMA issue.  One output tile per CTA: at the
-// largest configuration (T = 7 680 plan-frames) that is 60 x 121 = 7 260 CTAs, ~49 per SM.
+// warp 4 TMA producer, warp 5 TMEM allocation + MMA issue.  One output tile per CTA, TWO CTAs per SM
+// (97 KB of shared memory and 256 TMEM columns each): one CTA's epilogue overlaps the other's main loop.
+// Measured at the largest configuration (T = 7 680 plan-frames, 60 x 61 CTAs): the kernel is bound by the
+// L2 -> shared-memory operand traffic (K is only 408, every tile re-reads its A and B panels: 9.4 TB/s),
+// which is why the wide N tile and the co-resident CTAs pay: 0.44 ms (M128 x N128, 4 stages, 1 CTA/SM,
+// row-per-lane stores) -> 0.24 ms, 400 TFLOP/s executed tf32, 1.96 TB/s of output (tools/bench_gemm.py).
 #include <cuda.h>
 
 #include "common.cuh"
 
 namespace omfs {
 
-constexpr int BM = 128, BN = 128, BK = 32;  // BK fp32 = 128 bytes = one SWIZZLE_128B atom
-constexpr int kStages = 4;
+#ifndef OMFS_GEMM_BN
+#define OMFS_GEMM_BN 256
+#endif
+constexpr int BM = 128, BN = OMFS_GEMM_BN, BK = 32;  // BK fp32 = 128 bytes = one SWIZZLE_128B atom
+#ifndef OMFS_GEMM_STAGES
+#define OMFS_GEMM_STAGES 2
+#endif
+#ifndef OMFS_GEMM_CTAS
+#define OMFS_GEMM_CTAS 2
+#endif
+constexpr int kStages = OMFS_GEMM_STAGES;
 constexpr int kUmmaK = 8;                   // tf32: 32 bytes per MMA along K
 constexpr uint32_t kStageBytesA = BM * BK * 4, kStageBytesB = BN * BK * 4;
 constexpr uint32_t kTmemCols = BN;
@@ -84,7 +97,7 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 // kind::tf32, fp32 accumulate, A and B K-major, M=128, N=BN
 constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
-__global__ void __launch_bounds__(kGemmThreads, 1)
+__global__ void __launch_bounds__(kGemmThreads, OMFS_GEMM_CTAS)
 flame_blend_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, int T,
                       int K3, int npad, const float* __restrict__ base, float* __restrict__ C) {
     extern __shared__ unsigned char gemm_smem_raw[];
@@ -93,7 +106,7 @@ flame_blend_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
     const uint32_t tiles = (raw + 1023u) & ~1023u;
     const uint32_t smem_a = tiles;
     const uint32_t smem_b = tiles + kStages * kStageBytesA;
-    const uint32_t bars = smem_b + kStages * kStageBytesB;  // full[4], empty[4], tmem_full, tmem_ptr
+    const uint32_t bars = smem_b + kStages * kStageBytesB;  // full[kStages], empty[kStages], tmem_full, tmem_ptr
     const uint32_t bar_full = bars, bar_empty = bars + 8 * kStages, bar_tmem_full = bars + 16 * kStages;
     const uint32_t tmem_ptr_addr = bar_tmem_full + 8;
     volatile uint32_t* tmem_ptr_generic =
@@ -158,9 +171,16 @@ flame_blend_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
         }
     } else {
         // ===== epilogue: warps 0-3, TMEM lanes [32*warp, 32*warp+32) =====
+        // tcgen05.ld hands lane l the 32 columns of accumulator ROW l; stored as they come, one STG.128
+        // would touch 32 different rows (16 of every 32-byte sector).  Each 32x32 chunk is therefore
+        // transposed through shared memory (the operand ring is idle once the accumulator is complete):
+        // rows padded to 144 bytes keep both the row-wise STS.128 and the read-back conflict-free, and the
+        // global stores become 4 full 128-byte rows per instruction.
         mbar_wait(bar_tmem_full, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const int row = m0 + warp * 32 + lane;
+        constexpr int kRowPad = 36;  // floats per staged row (32 + 4)
+        float* stage = reinterpret_cast<float*>(gemm_smem_raw + (tiles - raw)) + warp * 32 * kRowPad;
+        const int cq = (lane & 7) * 4, rq = lane >> 3;  // read-back: 8 lanes per row, 4 rows per instruction
 #pragma unroll 1
         for (int c = 0; c < BN / 32; c++) {
             uint32_t v[32];
@@ -177,17 +197,25 @@ flame_blend_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_co
                 : "r"(taddr)
                 : "memory");
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (row < T) {
-                const int nb = n0 + c * 32;
-                float4* dst = reinterpret_cast<float4*>(C + (size_t)row * npad + nb);
-                const float4* bsrc = reinterpret_cast<const float4*>(base + nb);
+            const int nb = n0 + c * 32;
+            if (nb >= npad) break;  // ragged last N tile (warp-uniform)
+            float4* srow = reinterpret_cast<float4*>(stage + lane * kRowPad);
 #pragma unroll
-                for (int j = 0; j < 8; j++) {
-                    const float4 b = __ldg(bsrc + j);
-                    dst[j] = make_float4(__uint_as_float(v[4 * j]) + b.x, __uint_as_float(v[4 * j + 1]) + b.y,
-                                         __uint_as_float(v[4 * j + 2]) + b.z, __uint_as_float(v[4 * j + 3]) + b.w);
-                }
+            for (int j = 0; j < 8; j++)
+                srow[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                      __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+            __syncwarp();
+            const float4 b = __ldg(reinterpret_cast<const float4*>(base + nb + cq));
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int r = rq + 4 * i;
+                const float4 a = *reinterpret_cast<const float4*>(stage + r * kRowPad + cq);
+                const int row = m0 + warp * 32 + r;
+                if (row < T)
+                    *reinterpret_cast<float4*>(C + (size_t)row * npad + nb + cq) =
+                        make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
             }
+            __syncwarp();
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -240,8 +268,8 @@ static int make_map(CUtensorMap* map, const float* ptr, uint64_t rows, uint64_t 
 int launch_blend_gemm_tc(int T, int kpad, int npad, const float* d_acoef, const float* d_bt, const float* d_base,
                          float* d_vp, cudaStream_t stream) {
     const int K3 = 3 * kpad;
-    if (npad % BN != 0) {
-        set_error("blend gemm: npad (%d) must be a multiple of %d", npad, BN);
+    if (npad % 32 != 0) {  // the epilogue writes whole 32-column chunks; a ragged last N tile is zero-filled by TMA
+        set_error("blend gemm: npad (%d) must be a multiple of 32", npad);
         return OMFS_ERR_INVALID;
     }
     if (((uintptr_t)d_acoef | (uintptr_t)d_bt | (uintptr_t)d_vp | (uintptr_t)d_base) & 15) {
@@ -259,7 +287,7 @@ int launch_blend_gemm_tc(int T, int kpad, int npad, const float* d_acoef, const 
                                        (int)kGemmSmem));
         attr_set = true;
     }
-    dim3 grid(npad / BN, ceil_div(T, BM));
+    dim3 grid(ceil_div(npad, BN), ceil_div(T, BM));
     flame_blend_tc_kernel<<<grid, kGemmThreads, kGemmSmem, stream>>>(map_a, map_b, T, K3, npad, d_base, d_vp);
     count_launch();
     OMFS_LAUNCH_CHECK();
