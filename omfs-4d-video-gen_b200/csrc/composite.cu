@@ -9,12 +9,14 @@
 //     at a time with a lane-parallel footprint cull (extents precomputed by the preprocess kernel and
 //     carried in P2.w) and a ballot, so only the ~1/3 of the tile's Gaussians that can touch the
 //     block are evaluated — the kernel is FP32-issue bound, skipped (Gaussian, warp) pairs are the win;
-//   * no block barriers: a finished pixel block frees its slot at once (see the kernel comment);
+//   * persistent one-warp CTAs that draw (segment, tile, block) work units from a ticket counter; no block
+//     barriers anywhere: a finished pixel block goes straight on to the next unit;
 //   * early termination per pixel (T < 1e-4) and per warp (all 64 pixels saturated);
 //   * the optional uint8 HWC image (the save_image quantisation) is produced by the same kernel,
 //     so the frame sink costs no extra pass over HBM.
-// Roofline: 40 B per tile pair against ~256 pixel evaluations of ~10-20
-// instructions each: the FP32/SFU issue rate binds, not HBM; bench.py reports both.
+// Roofline: 40 B per tile pair against ~256 pixel evaluations of ~7 issue slots each: the
+// issue rate and the L1/shared data pipe bind (both ~71 % busy, profiles/r1_ncu_summary.md), not HBM (4 %);
+// bench.py reports the HBM fraction BASELINE.json asks for and says so.
 #include <cuda_fp16.h>
 
 #include <algorithm>
@@ -34,9 +36,9 @@ struct Ex2Dev {
     __device__ __forceinline__ float operator()(float x) const { return ex2_approx(x); }
 };
 
-// One warp = one 8x8 pixel block of a 16x16 tile; a CTA is kCompWarps such warps (default 1: at 62
+// One warp = one 8x8 pixel block of a 16x16 tile; a CTA is kCompWarps such warps (default 1: at 64
 // registers the 32-CTA-per-SM cap and the register file both allow 32 resident warps, and a one-warp CTA
-// frees its slot the moment its block is finished — measured 6.5 % faster than 4 warps per CTA).  The warps
+// never waits for a slower sibling — measured 6.5 % faster than 4 warps per CTA).  The warps
 // never synchronise with each other: there is no block barrier anywhere, a warp that saturates or runs out
 // of Gaussians stops at once, which removes the barrier stalls (the top stall reason of the 256-thread
 // tile-per-CTA version: ncu ..._issue_stalled_barrier 7.1 per issue).
