@@ -106,49 +106,46 @@ constexpr uint32_t kStopBits = 0x38d1b717u;  // 0.0001f; T < 0.0001f  <=>  bits(
 
 __device__ __forceinline__ bool stops(float testT) { return __float_as_uint(testT) < kStopBits; }
 
-// The exact per-Gaussian step with the saturation rule (same arithmetic as ex_blend).  Only reached for
-// the few pairs in which some pixel of the warp saturates.
-__device__ __forceinline__ void blend_step_stop(float alpha, const float4& c, float& T, float& Tbg, float& C0,
-                                                float& C1, float& C2) {
-    const float testT = T * (1.0f - alpha);
-    const bool stop = stops(testT);  // never true for a parked pixel (testT == -0)
-    float w = alpha * T;
-    w = stop ? 0.0f : w;     // the saturating Gaussian is NOT blended
-    Tbg = stop ? T : Tbg;    // ... and the pixel keeps the transmittance it had before it
-    T = stop ? -0.0f : testT;
-    C0 = fmaf(c.x, w, C0);
-    C1 = fmaf(c.y, w, C1);
-    C2 = fmaf(c.z, w, C2);
+// The saturation rule for one pixel across a PAIR of Gaussians, applied to the weights of the no-saturation
+// evaluation (T1 = T(1-a0), T2 = T1(1-a1), w0 = a0 T, w1 = a1 T1 already computed).  ex_blend, twice:
+//   Gaussian 0 stops the pixel (T1 < 1e-4): neither Gaussian is blended, the pixel keeps T;
+//   else Gaussian 1 stops it (T2 < 1e-4): only Gaussian 0 is blended, the pixel keeps T1.
+// A weight of +0 leaves the colour bit-identical (fma(c, 0, C) == C for C >= +0); a parked pixel (-0) never stops.
+__device__ __forceinline__ void saturate_pixel(float T, float T1, float T2, float& w0, float& w1, float& Tnew,
+                                               float& Tbg) {
+    const bool s0 = stops(T1);
+    const bool s1 = !s0 && stops(T2);
+    w0 = s0 ? 0.0f : w0;
+    w1 = (s0 || s1) ? 0.0f : w1;
+    Tbg = s0 ? T : (s1 ? T1 : Tbg);
+    Tnew = (s0 || s1) ? -0.0f : T2;
 }
 
 // Two consecutive Gaussians (alphas a0, a1 at the lane's two pixels) onto the two pixels.  Saturation
-// happens ONCE per pixel, so the pair is first evaluated as if nobody saturates (no selects: the kernel is
-// bound by issue slots); one integer compare per pixel + one vote per PAIR detects the rare case, which is
-// then redone with the exact rule.  T2 = T*(1-a0)*(1-a1) <= T*(1-a0), so testing T2 covers both steps.
-// Every packed instruction is two individually rounded binary32 operations: the per-pixel sequence is
-// exactly ex_blend's.
+// happens ONCE per pixel, so the pair is evaluated as if nobody saturates (no selects: the kernel is bound by
+// issue slots); one integer compare per pixel + one vote per PAIR detects the other case (19 % of the pairs:
+// some pixel of the 64 saturates), and only then the weights are corrected by selects.
+// T2 = T*(1-a0)*(1-a1) <= T*(1-a0), so testing T2 covers both steps.  Every packed instruction is two
+// individually rounded binary32 operations: the per-pixel sequence is exactly ex_blend's.
 __device__ __forceinline__ void blend_pair(const float2 a0, const float2 a1, const float4& c0, const float4& c1,
                                            Pixels& p) {
     const float2 one = make_float2(1.0f, 1.0f);
     const float2 T1 = __fmul2_rn(p.T, __fadd2_rn(one, make_float2(-a0.x, -a0.y)));
     const float2 T2 = __fmul2_rn(T1, __fadd2_rn(one, make_float2(-a1.x, -a1.y)));
+    float2 w0 = __fmul2_rn(a0, p.T), w1 = __fmul2_rn(a1, T1), Tn = T2;
     const bool sat = stops(T2.x) || stops(T2.y);
     if (__builtin_expect(__any_sync(0xffffffffu, sat), 0)) {
-        blend_step_stop(a0.x, c0, p.T.x, p.Tbg.x, p.C0.x, p.C1.x, p.C2.x);
-        blend_step_stop(a1.x, c1, p.T.x, p.Tbg.x, p.C0.x, p.C1.x, p.C2.x);
-        blend_step_stop(a0.y, c0, p.T.y, p.Tbg.y, p.C0.y, p.C1.y, p.C2.y);
-        blend_step_stop(a1.y, c1, p.T.y, p.Tbg.y, p.C0.y, p.C1.y, p.C2.y);
+        saturate_pixel(p.T.x, T1.x, T2.x, w0.x, w1.x, Tn.x, p.Tbg.x);
+        saturate_pixel(p.T.y, T1.y, T2.y, w0.y, w1.y, Tn.y, p.Tbg.y);
         asm volatile("" ::: "memory");  // keep this a real (warp-uniform) branch, not a chain of selects
-    } else {
-        const float2 w0 = __fmul2_rn(a0, p.T), w1 = __fmul2_rn(a1, T1);
-        p.C0 = __ffma2_rn(make_float2(c0.x, c0.x), w0, p.C0);
-        p.C1 = __ffma2_rn(make_float2(c0.y, c0.y), w0, p.C1);
-        p.C2 = __ffma2_rn(make_float2(c0.z, c0.z), w0, p.C2);
-        p.C0 = __ffma2_rn(make_float2(c1.x, c1.x), w1, p.C0);
-        p.C1 = __ffma2_rn(make_float2(c1.y, c1.y), w1, p.C1);
-        p.C2 = __ffma2_rn(make_float2(c1.z, c1.z), w1, p.C2);
-        p.T = T2;
     }
+    p.C0 = __ffma2_rn(make_float2(c0.x, c0.x), w0, p.C0);
+    p.C1 = __ffma2_rn(make_float2(c0.y, c0.y), w0, p.C1);
+    p.C2 = __ffma2_rn(make_float2(c0.z, c0.z), w0, p.C2);
+    p.C0 = __ffma2_rn(make_float2(c1.x, c1.x), w1, p.C0);
+    p.C1 = __ffma2_rn(make_float2(c1.y, c1.y), w1, p.C1);
+    p.C2 = __ffma2_rn(make_float2(c1.z, c1.z), w1, p.C2);
+    p.T = Tn;
 }
 
 // A warp owns an 8x8 pixel block of its tile: lane l holds the two pixels (x, y) and (x, y + 4).  Two pixels
