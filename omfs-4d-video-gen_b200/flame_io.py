@@ -239,7 +239,7 @@ def load_dataset_params(data_dir: str, frames: list[DatasetFrame], n_verts: int)
 # --------------------------------------------------------------------------------------- synthetic dataset on disk
 def write_synthetic_dataset(data_dir: str, model_dir: str, model: FlameModel, params: FrameParams, avatar: Avatar,
                             cam_c2w: np.ndarray, camera_angle_x: float, width: int, height: int,
-                            iteration: int = 30000) -> None:
+                            iteration: int = 30000, write_images: bool = False) -> None:
     """Lay a synthetic subject out exactly as the reference's pipeline leaves a real one on disk:
     dataset dir (preprocess_video.py:246-416) + trained-model dir (render_surgery.py:271-287)."""
     os.makedirs(os.path.join(data_dir, "images"), exist_ok=True)
@@ -254,9 +254,24 @@ def write_synthetic_dataset(data_dir: str, model_dir: str, model: FlameModel, pa
     save_flame_params(os.path.join(data_dir, "canonical_flame_param.npz"), canon)
     frames = [{"file_path": f"images/{t:05d}_00.png", "flame_param_path": f"flame_param/{t:05d}.npz",
                "transform_matrix": np.asarray(cam_c2w).tolist(), "timestep_index": t, "camera_index": 0,
-               "camera_angle_x": camera_angle_x, "w": width, "h": height} for t in range(T)]
-    top = {"camera_angle_x": camera_angle_x, "w": width, "h": height, "frames": frames,
+               "camera_angle_x": camera_angle_x, "w": width, "h": height,
+               "fg_mask_path": f"fg_masks/{t:05d}_00.png"} for t in range(T)]
+    # top-level intrinsics as preprocess_video.py:389-401 writes them
+    fl_x = cam_mod.fov2focal(camera_angle_x, width)
+    top = {"camera_angle_x": camera_angle_x, "camera_angle_y": cam_mod.focal2fov(fl_x, height), "fl_x": fl_x,
+           "fl_y": fl_x, "cx": width / 2.0, "cy": height / 2.0, "w": width, "h": height, "frames": frames,
            "timestep_indices": list(range(T)), "camera_indices": [0]}
+    if write_images:
+        # placeholder ground-truth frames and foreground masks (the renderer never reads them; the single-frame
+        # experiment and the validation report copy / compare them)
+        from PIL import Image
+        os.makedirs(os.path.join(data_dir, "fg_masks"), exist_ok=True)
+        yy, xx = np.mgrid[0:height, 0:width]
+        for t in range(T):
+            img = np.stack([(xx + 3 * t) % 256, (yy + 5 * t) % 256, (xx + yy) % 256], -1).astype(np.uint8)
+            Image.fromarray(img).save(os.path.join(data_dir, "images", f"{t:05d}_00.png"))
+            Image.fromarray(np.full((height, width), 255, np.uint8)).save(
+                os.path.join(data_dir, "fg_masks", f"{t:05d}_00.png"))
     split = max(1, T - T // 10)
     for name, fr in (("train", frames[:split]), ("test", frames[split:]), ("val", frames[split:])):
         with open(os.path.join(data_dir, f"transforms_{name}.json"), "w") as f:

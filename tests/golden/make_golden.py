@@ -278,11 +278,45 @@ def golden_report():
     print("report golden:", report["summary"])
 
 
+def _tiny_dataset(root):
+    """The seeded on-disk subject shared by golden_single_frame and tests/test_host_mirror.py."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    import omfs_b200  # noqa: F401
+    from omfs_b200 import cameras, flame_io, synthetic
+    model = synthetic.make_flame_model(seed=31, n_verts=162)
+    params = synthetic.make_frame_params(3, seed=32, n_verts=162)
+    av = synthetic.make_avatar(200, model.n_faces, seed=33)
+    c2w = cameras.look_at_c2w((0.0, 0.0, synthetic.camera_distance(32, 24)), (0.0, 0.0, 0.0))
+    flame_io.write_synthetic_dataset(os.path.join(root, "data_conda"), os.path.join(root, "model"), model, params, av,
+                                     c2w, 0.3, 32, 24, iteration=3000, write_images=True)
+    return os.path.join(root, "data_conda")
+
+
+def golden_single_frame():
+    """single_frame_experiment.build_single_frame_dataset (:32-81) run as shipped (its module-level directory
+    constants pointed at a temporary tree) on the tiny synthetic dataset: the file listing, the one-frame
+    transforms and the batched flame_param.npz it writes."""
+    sys.path.insert(0, os.path.join(REF, "02_Visual_Engine"))
+    from pathlib import Path
+    import single_frame_experiment as sfe
+    with tempfile.TemporaryDirectory() as d:
+        sfe.DATA_CONDA = Path(_tiny_dataset(d))
+        sfe.DATA_SINGLE = Path(d) / "data_single_frame"
+        sfe.build_single_frame_dataset()
+        listing = sorted(str(p.relative_to(sfe.DATA_SINGLE)) for p in sfe.DATA_SINGLE.rglob("*") if p.is_file())
+        transforms = {n: json.load(open(sfe.DATA_SINGLE / f"transforms_{n}.json")) for n in ("train", "test", "val")}
+        batched = dict(np.load(sfe.DATA_SINGLE / "flame_param.npz", allow_pickle=True))
+    np.savez_compressed(os.path.join(HERE, "single_frame_golden.npz"), listing=json.dumps(listing),
+                        transforms=json.dumps(transforms), **{f"batched_{k}": v for k, v in batched.items()})
+    print("single-frame golden:", listing)
+
+
 if __name__ == "__main__":
     if not os.path.isdir(REF):
         raise SystemExit("the reference tree is not available here; the committed goldens are authoritative")
     golden_render_surgery()
     golden_psnr()
     golden_report()
+    golden_single_frame()
     golden_surgical_sim()
     golden_simple_flame()

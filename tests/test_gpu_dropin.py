@@ -159,3 +159,32 @@ def test_config1_lefort_advance_on_flame_mesh():
     assert np.abs(verts - ref.verts).max() <= 1e-5
     ref2 = oracle.render(model, params, baked, [cam.pack()] * 2, 96, 96, verts=verts)
     assert np.abs(img - ref2.image).max() <= 2e-4
+
+
+def test_config2_single_frame_experiment_driver(tmp_path):
+    """BASELINE.json configs[1] through the reference's driver shape (single_frame_experiment.py): frame 0 of a
+    512x512, 100k-Gaussian dataset on disk -> one-frame dataset -> render with zero offsets -> render + GT PNGs;
+    the rendered PNG against the oracle."""
+    import oracle
+    from oracle import reference_rows as rr
+    from PIL import Image
+    from omfs_b200 import avatar, cameras, flame_io, single_frame_experiment as sfe, synthetic
+    W = H = 512
+    model, params, av, cam = synthetic.make_scene(n_gauss=100_000, n_frames=2, width=W, height=H)
+    c2w = cameras.look_at_c2w((0.0, 0.0, synthetic.camera_distance(W, H)), (0.0, 0.0, 0.0))
+    data_conda, mdl = tmp_path / "data_conda", tmp_path / "model_single_frame"
+    flame_io.write_synthetic_dataset(str(data_conda), str(mdl), model, params, av, c2w, 0.3, W, H, iteration=3000,
+                                     write_images=True)
+    single = sfe.build_single_frame_dataset(data_conda, tmp_path / "data_single_frame")
+    sfe.train_single_frame(mdl)
+    render_png, gt_png = sfe.render_single_frame_and_save(mdl, single, tmp_path / "out")
+    assert render_png.name == "single_frame_render.png" and gt_png.name == "single_frame_gt.png"
+    assert open(gt_png, "rb").read() == open(data_conda / "images" / "00000_00.png", "rb").read()
+    got = np.asarray(Image.open(render_png))
+    cam0 = cameras.camera_from_c2w(c2w, 0.3, W, H)
+    ref = oracle.render(model, params.slice(0, 1), avatar.bake(av), [cam0.pack()], W, H)
+    want = oracle.to_uint8(ref.image)[0]
+    assert got.shape == want.shape == (H, W, 3)
+    assert rr.psnr(got.astype(np.float32), want.astype(np.float32)) > 50.0
+    assert (np.abs(got.astype(int) - want.astype(int)) > 1).mean() < 2e-3
+    assert sorted(os.listdir(mdl / "train" / "ours_3000" / "renders")) == ["00000.png"]

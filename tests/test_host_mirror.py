@@ -163,6 +163,45 @@ def test_psnr_mirror(golden_dir):
     assert validation_reporting.psnr(g["a"], g["a"]) == 99.0
 
 
+def test_single_frame_dataset_matches_reference(golden_dir, tmp_path):
+    """single_frame_experiment.build_single_frame_dataset against what the reference's own builder wrote for the
+    same seeded dataset (tests/golden/make_golden.py: golden_single_frame): file listing, one-frame transforms for
+    the three splits, batched flame_param.npz; then the guards of the other two steps."""
+    import sys
+    sys.path.insert(0, golden_dir)
+    import make_golden
+    from omfs_b200 import single_frame_experiment as sfe
+    g = np.load(os.path.join(golden_dir, "single_frame_golden.npz"))
+    data_conda = make_golden._tiny_dataset(str(tmp_path))
+    single = sfe.build_single_frame_dataset(data_conda, tmp_path / "data_single_frame")
+    listing = sorted(str(p.relative_to(single)) for p in single.rglob("*") if p.is_file())
+    assert listing == json.loads(str(g["listing"]))
+    want = json.loads(str(g["transforms"]))
+    for split in ("train", "test", "val"):
+        assert json.load(open(single / f"transforms_{split}.json")) == want[split]
+    batched = dict(np.load(single / "flame_param.npz", allow_pickle=True))
+    keys = sorted(k[len("batched_"):] for k in g.files if k.startswith("batched_"))
+    assert sorted(batched) == keys
+    for k in keys:
+        assert batched[k].shape == g[f"batched_{k}"].shape and np.array_equal(batched[k], g[f"batched_{k}"])
+    assert open(single / "images" / "00000_00.png", "rb").read() == open(
+        os.path.join(data_conda, "images", "00000_00.png"), "rb").read()
+    # rebuilding replaces the directory; an incomplete transforms file is a KeyError, as upstream
+    (single / "stale.txt").write_text("x")
+    sfe.build_single_frame_dataset(data_conda, single)
+    assert not (single / "stale.txt").exists()
+    t = json.load(open(os.path.join(data_conda, "transforms_train.json")))
+    del t["fl_x"]
+    json.dump(t, open(os.path.join(data_conda, "transforms_train.json"), "w"))
+    with pytest.raises(KeyError):
+        sfe.build_single_frame_dataset(data_conda, single)
+    with pytest.raises(RuntimeError, match="Training failed"):
+        sfe.train_single_frame(tmp_path / "no_model")
+    sfe.train_single_frame(tmp_path / "model")            # the synthetic "trained" avatar is accepted
+    with pytest.raises(SystemExit):
+        sfe.main(tmp_path / "missing_data_conda")
+
+
 def test_frame_sink(tmp_path, monkeypatch):
     """write_frames_png writes the upstream names and round-trips the pixels; stitch_video_frames hands the raw
     frames to ffmpeg with the reference's codec flags (a stand-in ffmpeg records what it was given)."""
