@@ -9,7 +9,7 @@ Liveness (early termination) is applied per block (A, C) or per quad (B, D), ref
 """
 import sys, os
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import omfs_b200  # noqa
 from omfs_b200 import avatar, synthetic

@@ -8,7 +8,7 @@ import sys
 import os
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import omfs_b200  # noqa
 from omfs_b200 import avatar, synthetic

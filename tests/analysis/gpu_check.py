@@ -1,7 +1,7 @@
 """Bring-up / diagnostics script for a GPU box: stage-by-stage parity of the CUDA path against the
 oracle, with verbose mismatch reports.  (The judged parity tests live in tests/; this prints more.)
 
-    python tools/gpu_check.py [--n 20000] [--frames 3] [--size 256] [--gemm 0|1]
+    python tests/analysis/gpu_check.py [--n 20000] [--frames 3] [--size 256] [--gemm 0|1]
 """
 from __future__ import annotations
 
@@ -13,7 +13,7 @@ import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import omfs_b200  # noqa: E402,F401
 from omfs_b200 import avatar, runtime, synthetic  # noqa: E402
