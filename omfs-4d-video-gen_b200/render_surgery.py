@@ -190,12 +190,10 @@ def write_frames_png(renders_dir: str, frames_u8: np.ndarray, workers: int | Non
     return paths
 
 
-def render_with_gaussians(model_path: str, data_dir: str, iteration: int = -1,
-                          clear_old_renders: bool = True) -> str:
-    """Render every train-split frame of `data_dir` with the avatar in `model_path`.
-
-    Writes `model_path/train/ours_<iter>/renders/%05d.png` (the layout the reference's caller and
-    validation report expect, :324-362) and returns that directory."""
+def _render_dataset(model_path: str, data_dir: str, iteration: int = -1,
+                    clear_old_renders: bool = True) -> tuple[str, np.ndarray]:
+    """render_with_gaussians, also returning the frames it wrote (uint8 [T,H,W,3]) so that main() can hand them
+    to the encoder without reading the PNGs back."""
     train_dir = os.path.join(model_path, "train")
     if clear_old_renders and os.path.isdir(train_dir):  # stale frames must never be picked up (:260-267)
         for d in os.listdir(train_dir):
@@ -223,7 +221,16 @@ def render_with_gaussians(model_path: str, data_dir: str, iteration: int = -1,
     renders_dir = os.path.join(train_dir, f"ours_{it}", "renders")
     write_frames_png(renders_dir, images)
     print(f"[render_surgery] Frames rendered to: {renders_dir}")
-    return renders_dir
+    return renders_dir, images
+
+
+def render_with_gaussians(model_path: str, data_dir: str, iteration: int = -1,
+                          clear_old_renders: bool = True) -> str:
+    """Render every train-split frame of `data_dir` with the avatar in `model_path`.
+
+    Writes `model_path/train/ours_<iter>/renders/%05d.png` (the layout the reference's caller and
+    validation report expect, :324-362) and returns that directory."""
+    return _render_dataset(model_path, data_dir, iteration, clear_old_renders)[0]
 
 
 def _render_frames(model, params: FrameParams, av, cams, plan_offset=None, device: int | None = None) -> np.ndarray:
@@ -372,12 +379,14 @@ def main(argv: list[str] | None = None):
     print(f"[render_surgery] Rig mode: {mode} ({reason})")
     modified_dir = create_modified_dataset(args.data_dir, lefort_offset, bsso_offset, deformation_map=deformation_map)
     try:
-        frames_dir = render_with_gaussians(args.model_path, modified_dir, iteration=args.iteration)
+        frames_dir, frames_u8 = _render_dataset(args.model_path, modified_dir, iteration=args.iteration)
         if args.export_frames_dir:
             export_deterministic_frames(frames_dir, args.export_frames_dir,
                                         index_file=args.deterministic_indices or None,
                                         max_frames=args.deterministic_max_frames)
-        stitch_video(frames_dir, args.output, fps=args.fps)
+        # same video as stitch_video(frames_dir, ...): the PNGs above are lossless, so the encoder gets the same
+        # pixels, without the reference's per-frame file copy and the PNG decode
+        stitch_video_frames(frames_u8, args.output, fps=args.fps)
     finally:
         shutil.rmtree(modified_dir, ignore_errors=True)
     print("[render_surgery] Done.")

@@ -59,6 +59,39 @@ def test_render_with_gaussians_from_disk_matches_oracle(tmp_path):
     assert json.load(open(os.path.join(exp, "deterministic_indices_manifest.json")))["selected_indices"] == [0, n_train - 1]
 
 
+def test_main_cli_flow(tmp_path, monkeypatch):
+    """render_surgery.main with the reference's flags: modified dataset -> in-process render -> PNGs in the upstream
+    layout -> deterministic export -> encoder.  A stand-in ffmpeg records the raw frames it is handed: they are the
+    frames of the PNGs, in order; the temporary dataset is removed afterwards."""
+    from PIL import Image
+    from omfs_b200 import render_surgery as rs
+    data, mdl, model, params, av, cam = _dataset(tmp_path, T=4)
+    fake = tmp_path / "ffmpeg"
+    fake.write_text("#!/bin/sh\nfor a in \"$@\"; do echo \"$a\" >> %s; done\ncat > %s\n" %
+                    (tmp_path / "args.txt", tmp_path / "stdin.bin"))
+    fake.chmod(0o755)
+    monkeypatch.setattr(rs, "_get_ffmpeg_path", lambda: str(fake))
+    made = []
+    real_create = rs.create_modified_dataset
+    monkeypatch.setattr(rs, "create_modified_dataset", lambda *a, **k: made.append(real_create(*a, **k)) or made[-1])
+    out = tmp_path / "video" / "final_prediction.mp4"
+    rs.main(["--lefort_mm", "5", "--bsso_mm", "-3", "--sensitivity", "1.5", "--model_path", mdl, "--data_dir", data,
+             "--output", str(out), "--fps", "24", "--export_frames_dir", str(tmp_path / "ab"),
+             "--deterministic_max_frames", "2"])
+    renders = os.path.join(mdl, "train", "ours_3000", "renders")
+    names = sorted(os.listdir(renders))
+    assert names == [f"{i:05d}.png" for i in range(4)]
+    frames = np.stack([np.asarray(Image.open(os.path.join(renders, n))) for n in names])
+    assert (tmp_path / "stdin.bin").read_bytes() == frames.tobytes()
+    args = (tmp_path / "args.txt").read_text().split("\n")
+    assert args[args.index("-framerate") + 1] == "24" and args[args.index("-s") + 1] == f"{cam.width}x{cam.height}"
+    assert json.load(open(tmp_path / "ab" / "deterministic_indices_manifest.json"))["selected_indices"] == [0, 3]
+    assert made and not os.path.exists(made[0])            # the caller's temporary dataset is cleaned up (:537-539)
+    # the plan moved the face: frames differ from a zero-offset render of the same dataset
+    zero = rs.render_surgery_frames(model, params, av, [cam] * 4, 0.0, 0.0)
+    assert not np.array_equal(zero, frames)
+
+
 def test_render_failure_is_a_runtime_error(tmp_path):
     from omfs_b200 import flame_io, render_surgery as rs
     data, mdl, model, params, av, cam = _dataset(tmp_path, T=2)
