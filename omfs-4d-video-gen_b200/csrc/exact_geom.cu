@@ -63,8 +63,12 @@ __global__ void __launch_bounds__(256) face_frames_kernel(int T, int V, int F, c
 }
 
 // ------------------------------------------------------------------------------------- U5+U6
-// grid = (ceil(N/256), S).  One thread per (segment, Gaussian).
-__global__ void __launch_bounds__(256) bind_preprocess_kernel(
+// grid = (ceil(N/kBindThreads), S).  One thread per (segment, Gaussian).
+#ifndef OMFS_BIND_THREADS
+#define OMFS_BIND_THREADS 128  // 56 registers; small CTAs also fit beside the persistent compositing warps of the previous batch
+#endif
+constexpr int kBindThreads = OMFS_BIND_THREADS;
+__global__ void __launch_bounds__(kBindThreads) bind_preprocess_kernel(
     int N, int F, int width, int height, const float4* __restrict__ ff, const int32_t* __restrict__ seg_frame,
     const float* __restrict__ cams, const float4* __restrict__ xyzb, const float4* __restrict__ scale_lo,
     const float4* __restrict__ rot, const float4* __restrict__ sh, float4* __restrict__ P0,
@@ -164,8 +168,8 @@ extern "C" int omfs_bind_preprocess(int S, int N, int F, int width, int height, 
     OMFS_REQUIRE(d_ff && d_seg_frame && d_cams && d_xyzb && d_scale_lo && d_rot && d_sh, "null input");
     OMFS_REQUIRE(d_P0 && d_P1 && d_P2 && d_tiles_touched, "null output");
     if (S == 0) return OMFS_OK;
-    dim3 grid(ceil_div(N, 256), S);
-    bind_preprocess_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+    dim3 grid(ceil_div(N, kBindThreads), S);
+    bind_preprocess_kernel<<<grid, kBindThreads, 0, (cudaStream_t)stream>>>(
         N, F, width, height, (const float4*)d_ff, d_seg_frame, d_cams, (const float4*)d_xyzb,
         (const float4*)d_scale_lo, (const float4*)d_rot, (const float4*)d_sh, (float4*)d_P0, (float4*)d_P1,
         (float4*)d_P2, d_tiles_touched, d_depth_keys);
