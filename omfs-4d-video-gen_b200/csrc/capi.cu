@@ -156,7 +156,10 @@ struct DevBuf {
     }
 };
 
-constexpr int kCompPipelinedWarps = 20;
+#ifndef OMFS_COMP_PIPELINED_WARPS
+#define OMFS_COMP_PIPELINED_WARPS 20
+#endif
+constexpr int kCompPipelinedWarps = OMFS_COMP_PIPELINED_WARPS;
 
 struct omfs_session {
     omfs_session_config cfg{};
