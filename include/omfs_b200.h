@@ -65,8 +65,10 @@ int omfs_flame_pose_prep(int T, int n_expr, int kpad,
 
 /* U1+U2 contraction: d_vp[T,npad] = d_base[npad] + A[T,3*kpad] . Bt[npad,3*kpad]^T.
  * Columns 0..3V-1 are posed-template vertices before skinning, 3V..3V+14 the 5 joints.
- * impl 0 = tcgen05/TMA tensor-core kernel (tf32x3), 1 = fp32 CUDA-core kernel (same operands;
- * kept as the cross-check and for T < 16). */
+ * impl 0 = tcgen05/TMA tensor-core kernels (tf32x3: A = [Ah | Ah | Al], Bt = [Bh | Bl | Bh]; below 1024 rows the
+ * kernel that streams the concatenated operands, from there on the one that stages the four panels once per K
+ * block and issues the three products from the same tiles), 2 / 3 = force the first / the second,
+ * 1 = fp32 CUDA-core kernel (same operands; kept as the cross-check). */
 int omfs_flame_blend_gemm(int T, int kpad, int npad,
                           const float* d_acoef, const float* d_bt, const float* d_base,
                           float* d_vp, int impl, void* stream);

@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(256) flame_lbs_kernel(int V, int npad, const f
 }
 
 int launch_blend_gemm_tc(int T, int kpad, int npad, const float* d_acoef, const float* d_bt, const float* d_base,
-                         float* d_vp, cudaStream_t stream);  // flame_gemm_tc.cu
+                         float* d_vp, int variant, cudaStream_t stream);  // flame_gemm_tc.cu
 
 }  // namespace omfs
 
@@ -298,7 +298,12 @@ extern "C" int omfs_flame_blend_gemm(int T, int kpad, int npad, const float* d_a
     OMFS_REQUIRE(T >= 0 && kpad > 0 && kpad % 8 == 0 && npad > 0, "bad sizes");
     OMFS_REQUIRE(d_acoef && d_bt && d_base && d_vp, "null pointer");
     if (T == 0) return OMFS_OK;
-    if (impl == 0) return launch_blend_gemm_tc(T, kpad, npad, d_acoef, d_bt, d_base, d_vp, (cudaStream_t)stream);
+    // impl 0: tensor cores (the panel re-use kernel from 1024 rows up, where it is the faster one; the
+    // concatenated-K kernel below), 2 / 3: force the concatenated-K / panel re-use kernel, 1: CUDA cores
+    if (impl == 0 || impl == 2 || impl == 3) {
+        const int variant = impl == 0 ? (T >= 1024 ? 0 : 2) : (impl == 3 ? 0 : 2);
+        return launch_blend_gemm_tc(T, kpad, npad, d_acoef, d_bt, d_base, d_vp, variant, (cudaStream_t)stream);
+    }
     dim3 grid(ceil_div(npad, 64), ceil_div(T, 32));
     flame_blend_simt_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(T, 3 * kpad, npad, d_acoef, d_bt, d_base, d_vp);
     count_launch();

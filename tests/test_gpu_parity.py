@@ -259,18 +259,19 @@ def test_empty_and_fully_culled(rt, small_scene):
 
 
 def test_blend_gemm_tensor_core_vs_cuda_core(rt):
-    """U1+U2: the tcgen05 kernel against the fp32 CUDA-core kernel on the same operands, ragged M
-    (T = 1, 130, 257) so that TMA's out-of-bounds fill is exercised."""
+    """U1+U2: both tcgen05 kernels (concatenated-K operands, impl 2; panel re-use, impl 3; impl 0 picks by size)
+    against the fp32 CUDA-core kernel on the same operands, ragged M (T = 1, 130, 257, 1100) and a ragged last N
+    tile (npad = 1024 + 128) so that TMA's out-of-bounds fill is exercised on every side."""
     from omfs_b200.runtime import DeviceArray as DA
     L = rt.load_library()
     rng = np.random.default_rng(0)
-    kpad, npad = 136, 1024
+    kpad, npad = 136, 1024 + 128
     K3 = 3 * kpad
 
     def hi(x):
         return (x.view(np.uint32) & np.uint32(0xFFFFE000)).view(np.float32)
 
-    for T in (1, 130, 257):
+    for T in (1, 130, 257, 1100):
         a = rng.normal(0, 0.5, (T, kpad)).astype(np.float32)
         b = rng.normal(0, 1e-3, (npad, kpad)).astype(np.float32)
         ah, bh = hi(a), hi(b)
@@ -281,12 +282,14 @@ def test_blend_gemm_tensor_core_vs_cuda_core(rt):
         want = base[None].astype(np.float64) + a.astype(np.float64) @ b.astype(np.float64).T
         dA, dB, dbase = DA.from_numpy(A), DA.from_numpy(Bt), DA.from_numpy(base)
         out = {}
-        for impl in (0, 1):
+        for impl in (0, 1, 2, 3):
             dC = DA((T, npad), np.float32)
             rt.check(L.omfs_flame_blend_gemm(T, kpad, npad, dA.ptr, dB.ptr, dbase.ptr, dC.ptr, impl, None))
             out[impl] = dC.numpy()
             assert np.abs(out[impl] - want).max() <= 2e-7, (T, impl)   # fp32-class accuracy from tf32x3
-        assert np.abs(out[0] - out[1]).max() <= 2e-7
+        for impl in (0, 2, 3):
+            assert np.abs(out[impl] - out[1]).max() <= 2e-7
+        assert np.array_equal(out[0], out[3] if T >= 1024 else out[2])
         assert A.shape[1] == K3
 
 

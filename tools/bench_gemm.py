@@ -2,7 +2,7 @@
 
     python tools/bench_gemm.py [--T 7680]
 
-Times omfs_flame_blend_gemm (tcgen05 tf32x3 vs the CUDA-core kernel) with CUDA events and prints
+Times omfs_flame_blend_gemm (both tcgen05 tf32x3 forms and the CUDA-core kernel) with CUDA events and prints
 useful / executed TFLOP/s and the output bandwidth.  `ncu -k regex:flame_blend_tc` on this script
 gives the tensor-pipe utilisation quoted in profiles/.
 """
@@ -49,7 +49,9 @@ def main():
         A = split3(a_full, "A").to(dev)
         C = torch.empty(T, npad, device=dev)
         stream = torch.cuda.current_stream()
-        for impl in (0, 1):
+        ref = (a_full.double().to(dev) @ b_full.double().to(dev).T + base.double()).float()
+        names = {0: "tcgen05 tf32x3 (panel re-use)", 2: "tcgen05 tf32x3 (concatenated K)", 1: "cuda-core fp32"}
+        for impl in (0, 2, 1):
             def run():
                 runtime.check(L.omfs_flame_blend_gemm(T, kpad, npad, A.data_ptr(), Bt.data_ptr(), base.data_ptr(),
                                                       C.data_ptr(), impl, stream.cuda_stream or None))
@@ -65,14 +67,12 @@ def main():
             ms = e0.elapsed_time(e1) / args.reps
             useful = 2.0 * T * (100 + 36) * n_useful
             executed = 2.0 * T * K3 * npad
-            out.append({"T": T, "impl": "tcgen05 tf32x3" if impl == 0 else "cuda-core fp32", "ms": ms,
+            C.zero_()
+            run()
+            torch.cuda.synchronize()
+            out.append({"T": T, "impl": names[impl], "ms": ms, "max_abs_err_vs_fp64": float((C - ref).abs().max()),
                         "useful_TFLOPs": useful / ms / 1e9, "executed_TFLOPs": executed / ms / 1e9,
                         "output_GBs": 4.0 * T * npad / ms / 1e6})
-        ref = (a_full.double().to(dev) @ b_full.double().to(dev).T + base.double()).float()
-        runtime.check(L.omfs_flame_blend_gemm(T, kpad, npad, A.data_ptr(), Bt.data_ptr(), base.data_ptr(),
-                                              C.data_ptr(), 0, None))
-        torch.cuda.synchronize()
-        out[-2]["max_abs_err_vs_fp64"] = float((C - ref).abs().max())
     for o in out:
         print(json.dumps(o))
 
