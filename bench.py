@@ -415,9 +415,10 @@ def main():
                     "unit": "GB/s", "frac": stages[dom]["achieved_GBs"] / hbm, "traffic": traffic,
                     "peak_source": f"{peak_kind} (MEASURED_PEAKS.json hbm_gbs)",
                     "note": "algorithmic bytes per launch (SURVEY 8d: 40 B x tile pairs + 12 B x pixels, x frames per "
-                            "launch) / in-situ CUDA-event time of the stage.  The compositing kernel is FP32-issue "
-                            "bound, not HBM bound (ncu: issue slots 70 % busy, DRAM 3 % of peak, "
-                            "profiles/r1_ncu_summary.md), so its HBM fraction is low by construction"}
+                            "launch) / in-situ CUDA-event time of the stage.  The compositing kernel is bound by the "
+                            "issue rate and the L1/shared data pipe, not by HBM (ncu: issue slots 71 % busy, L1 data "
+                            "pipe 73 %, DRAM 4 % of peak, profiles/r1_ncu_summary.md), so its HBM fraction is low by "
+                            "construction; bind_preprocess, the other kernel BASELINE.json names, is in `stages`"}
         # tensor-pipe figure for the blendshape GEMM: 2*T*K3*npad flops per launch group
         flops_gemm = 2.0 * 3 * d["kpad"] * d["npad"]
         cpu = None
