@@ -71,9 +71,17 @@ def main():
     out = torch.empty((T * n_views, H, W, 3), dtype=torch.uint8, device=dev)
     ms = timed(sess, [(ptrs, T, n_views, out.data_ptr())])
     S = T * n_views
+    pairs = sess.stats()["pairs"] / S
+    # per-stage CUDA-event times of one more pass (stages serialised on one stream: shares, not the pipelined total)
+    sess.set_profiling(True)
+    sess.render_device(ptrs, T, n_views, d_out_u8=out.data_ptr(), stream=torch.cuda.current_stream().cuda_stream)
+    sess.sync()
+    stages = {k: round(v["ms"], 4) for k, v in sess.stage_ms().items()}
+    sess.set_profiling(False)
     print(json.dumps({"config": "configs[3]: 1024x1024 x 16 views, 500k Gaussians", "frames": T, "segments": S,
                       "ms": ms, "segments_per_s": S / ms * 1e3, "frames_per_s_all_views": T / ms * 1e3,
-                      "tile_pairs_per_segment": sess.stats()["pairs"] / S, "batch_segments": 2 * n_views}), flush=True)
+                      "tile_pairs_per_segment": pairs, "batch_segments": 2 * n_views,
+                      "stage_ms_serialised": stages}), flush=True)
     sess.close()
     del out
 
