@@ -326,7 +326,10 @@ __global__ void __launch_bounds__(kEsThreads) emit_scatter_kernel(
             }
         }
         __syncthreads();
-        // ---- per tile: offsets of the warps inside the chunk, chunk aggregate, look-back
+        // ---- per tile: offsets of the warps inside the chunk and the chunk aggregate.  EVERY aggregate of the
+        // chunk is published before any look-back starts, so a successor never waits for a tile whose owner
+        // thread is still busy looking back for an earlier one.
+        volatile uint32_t* my_status = status + (size_t)chunk * tiles;
         for (int t = threadIdx.x; t < tiles; t += kEsThreads) {
             uint32_t off = 0;
 #pragma unroll
@@ -335,28 +338,52 @@ __global__ void __launch_bounds__(kEsThreads) emit_scatter_kernel(
                 s_wcnt[w * tp + t] = (uint16_t)off;
                 off += c;
             }
-            volatile uint32_t* my_status = status + (size_t)chunk * tiles;
             my_status[t] = (lc == 0 ? kFlagPrefix : kFlagAgg) | off;
-            uint32_t excl = 0;
-            if (lc > 0) {
-                uint32_t look = chunk - 1;
-                uint32_t spins = 0;
-                while (true) {
-                    if (++spins > (1u << 28)) __trap();  // a lost predecessor is a bug: fail, do not hang
-                    const uint32_t sv = status[(size_t)look * tiles + t];
-                    const uint32_t flag = sv & kFlagMask;
-                    if (flag == kFlagPrefix) {
-                        excl += sv & kValMask;
-                        break;
-                    }
-                    if (flag == kFlagAgg) {
-                        excl += sv & kValMask;
-                        look--;
-                    }
-                }
-                my_status[t] = kFlagPrefix | ((excl + off) & kValMask);
+            s_base[t] = off;  // parked here until the look-back below turns it into the tile's base
+        }
+        // ---- look-back, kEsLook tiles per thread at a time: the probes of a batch are independent loads, so a
+        // thread pays one round trip per batch and step, not one per tile (at 4096 tiles a thread owns 16)
+        constexpr int kEsLook = 4;
+        for (int t0 = threadIdx.x; t0 < tiles; t0 += kEsThreads * kEsLook) {
+            uint32_t excl[kEsLook], look[kEsLook];
+            bool pend[kEsLook];
+            bool any = false;
+#pragma unroll
+            for (int g = 0; g < kEsLook; g++) {
+                excl[g] = 0;
+                look[g] = chunk - 1;
+                pend[g] = lc > 0 && t0 + g * kEsThreads < tiles;
+                any = any || pend[g];
             }
-            s_base[t] = __ldg(tile_start + (size_t)seg * tiles + t) + excl;
+            uint32_t spins = 0;
+            while (any) {
+                if (++spins > (1u << 28)) __trap();  // a lost predecessor is a bug: fail, do not hang
+                uint32_t sv[kEsLook];
+#pragma unroll
+                for (int g = 0; g < kEsLook; g++)
+                    sv[g] = pend[g] ? status[(size_t)look[g] * tiles + t0 + g * kEsThreads] : 0u;
+                any = false;
+#pragma unroll
+                for (int g = 0; g < kEsLook; g++) {
+                    if (!pend[g]) continue;
+                    const uint32_t flag = sv[g] & kFlagMask;
+                    if (flag == kFlagPrefix) {
+                        excl[g] += sv[g] & kValMask;
+                        pend[g] = false;
+                    } else if (flag == kFlagAgg) {
+                        excl[g] += sv[g] & kValMask;
+                        look[g]--;
+                    }
+                    any = any || pend[g];
+                }
+            }
+#pragma unroll
+            for (int g = 0; g < kEsLook; g++) {
+                const int t = t0 + g * kEsThreads;
+                if (t >= tiles) continue;
+                if (lc > 0) my_status[t] = kFlagPrefix | ((excl[g] + s_base[t]) & kValMask);
+                s_base[t] = __ldg(tile_start + (size_t)seg * tiles + t) + excl[g];
+            }
         }
         // ---- pass B: expand the pairs IN ORDER into the owning warp's window, rank, scatter
         for (uint32_t win = 0; win < n_win; win++) {
