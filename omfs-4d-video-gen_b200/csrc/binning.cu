@@ -202,15 +202,20 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(int n_tiles_total, cons
 constexpr int kEsThreads = 256;
 constexpr int kEsGpt = 4;                            // Gaussians per thread
 constexpr int kEsChunk = kEsThreads * kEsGpt;        // 1024 depth-ordered Gaussians per work item
-constexpr int kEsWin = 1024;                         // pairs per warp per window
+constexpr int kEsWin = 1024;                         // pairs per warp per window (up to 1024 tiles)
 constexpr int kEsWarps = kEsThreads / 32;
 
 // dynamic shared memory: pair[8][kEsWin] u32 | gidx[kEsChunk] u32 | base[tiles] u32 | wcnt[8][tiles] u16
 constexpr int kEsWinShift = 10;
 static_assert((1 << kEsWinShift) == kEsWin, "window size must match its shift");
+// Above 1024 tiles the per-tile arrays dominate the footprint (4096 tiles: 16 KB of bases + 64 KB of counters):
+// with 1024-pair windows a CTA needs 119 KB and only ONE fits an SM (ncu: 12.5 % occupancy, issue slots 36 %
+// busy).  Halving the windows brings it to 103 KB, two CTAs per SM, at the price of a second expansion pass.
+static inline int emit_scatter_win_shift(int tiles) { return tiles > 1024 ? kEsWinShift - 1 : kEsWinShift; }
 static inline size_t emit_scatter_smem(int tiles) {
     const int tp = (tiles + 1) & ~1;  // even row stride: the packed 16-bit counters are updated as 32-bit words
-    return sizeof(uint32_t) * (kEsWarps * kEsWin + kEsChunk + tiles) + sizeof(uint16_t) * kEsWarps * tp + 64;
+    const int win = 1 << emit_scatter_win_shift(tiles);
+    return sizeof(uint32_t) * (kEsWarps * win + kEsChunk + tiles) + sizeof(uint16_t) * kEsWarps * tp + 64;
 }
 
 template <int TILE_BITS>
@@ -221,8 +226,11 @@ __global__ void __launch_bounds__(kEsThreads) emit_scatter_kernel(
     const uint32_t* __restrict__ sort_count, uint32_t* __restrict__ chunk_counter,
     volatile uint32_t* __restrict__ status /*[chunks][tiles]*/, uint32_t* __restrict__ vals_out) {
     extern __shared__ __align__(16) unsigned char es_raw[];
-    uint32_t* s_pair = reinterpret_cast<uint32_t*>(es_raw);            // [8][kEsWin]: tile << 10 | local Gaussian
-    uint32_t* s_gidx = s_pair + kEsWarps * kEsWin;                     // [kEsChunk]
+    // window size of this instantiation (see emit_scatter_win_shift)
+    constexpr int kWinShift = TILE_BITS > 10 ? kEsWinShift - 1 : kEsWinShift;
+    constexpr int kWin = 1 << kWinShift;
+    uint32_t* s_pair = reinterpret_cast<uint32_t*>(es_raw);            // [8][kWin]: tile << 10 | local Gaussian
+    uint32_t* s_gidx = s_pair + kEsWarps * kWin;                       // [kEsChunk]
     uint32_t* s_base = s_gidx + kEsChunk;                              // [tiles]
     uint16_t* s_wcnt = reinterpret_cast<uint16_t*>(s_base + tiles);    // [8][tp]
     const int tp = (tiles + 1) & ~1;
@@ -294,9 +302,9 @@ __global__ void __launch_bounds__(kEsThreads) emit_scatter_kernel(
         uint32_t total_pairs;
         const uint32_t my_off = block_excl_scan_256(acc, s_scan, total_pairs);
         // warp w owns the contiguous pair range [w*per_warp, (w+1)*per_warp) of the chunk, consumed in
-        // windows of kEsWin pairs; all warps step through their windows together
+        // windows of kWin pairs; all warps step through their windows together
         const uint32_t per_warp = (total_pairs + kEsWarps - 1) / kEsWarps;
-        const uint32_t n_win = (per_warp + kEsWin - 1) / kEsWin;
+        const uint32_t n_win = (per_warp + kWin - 1) / kWin;
         const uint32_t my_lo = min(total_pairs, (uint32_t)warp * per_warp);
         const uint32_t my_n = min(total_pairs, (uint32_t)(warp + 1) * per_warp) - my_lo;
 
@@ -400,9 +408,9 @@ __global__ void __launch_bounds__(kEsThreads) emit_scatter_kernel(
                 int cx = 0, cy = 0;
                 const uint32_t li = (uint32_t)(threadIdx.x * kEsGpt + q);
                 for (uint32_t k = 0; k < cnt[q]; k++) {
-                    if ((wi >> kEsWinShift) == win) {
+                    if ((wi >> kWinShift) == win) {
                         const uint32_t tile = (uint32_t)((rminy[q] + cy) * gx + rminx[q] + cx);
-                        s_pair[owner * kEsWin + (wi & (kEsWin - 1))] = (tile << 10) | li;
+                        s_pair[owner * kWin + (wi & (kWin - 1))] = (tile << 10) | li;
                     }
                     if (++cx == rw[q]) {
                         cx = 0;
@@ -416,9 +424,9 @@ __global__ void __launch_bounds__(kEsThreads) emit_scatter_kernel(
             }
             __syncthreads();
             // my warp's window, 32 pairs per step, in pair order
-            const uint32_t w_lo = win * kEsWin;
-            const uint32_t w_n = (my_n > w_lo) ? min((uint32_t)kEsWin, my_n - w_lo) : 0u;
-            const uint32_t* wp = s_pair + warp * kEsWin;
+            const uint32_t w_lo = win * kWin;
+            const uint32_t w_n = (my_n > w_lo) ? min((uint32_t)kWin, my_n - w_lo) : 0u;
+            const uint32_t* wp = s_pair + warp * kWin;
             uint16_t* wc = s_wcnt + warp * tp;
             for (uint32_t s0 = 0; s0 < w_n; s0 += 32) {
                 const bool valid = s0 + lane < w_n;
