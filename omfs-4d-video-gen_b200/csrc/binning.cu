@@ -308,28 +308,72 @@ __global__ void __launch_bounds__(kEsThreads) emit_scatter_kernel(
         const uint32_t my_lo = min(total_pairs, (uint32_t)warp * per_warp);
         const uint32_t my_n = min(total_pairs, (uint32_t)(warp + 1) * per_warp) - my_lo;
 
-        // ---- pass A: per-warp, per-tile counts.  Order is irrelevant for counting, so every thread walks
-        // its own Gaussians' rectangles and bumps the counter of the warp that OWNS each pair.
+        // expansion of the chunk's pairs IN ORDER into the owning warps' windows (window `win` of every warp)
+        auto expand = [&](uint32_t win) {
 #pragma unroll
-        for (int q = 0; q < kEsGpt; q++) {
-            if (cnt[q] == 0) continue;
-            uint32_t j = my_off;
+            for (int q = 0; q < kEsGpt; q++) {
+                if (cnt[q] == 0) continue;
+                uint32_t j = my_off;
 #pragma unroll
-            for (int qq = 0; qq < kEsGpt; qq++)
-                if (qq < q) j += cnt[qq];
-            uint32_t owner = j / per_warp;
-            uint32_t wi = j - owner * per_warp;
-            int cx = 0, cy = 0;
-            for (uint32_t k = 0; k < cnt[q]; k++) {
-                const uint32_t tile = (uint32_t)((rminy[q] + cy) * gx + rminx[q] + cx);
-                atomicAdd(reinterpret_cast<uint32_t*>(s_wcnt + owner * tp) + (tile >> 1), 1u << (16 * (tile & 1u)));
-                if (++cx == rw[q]) {
-                    cx = 0;
-                    cy++;
+                for (int qq = 0; qq < kEsGpt; qq++)
+                    if (qq < q) j += cnt[qq];
+                uint32_t owner = j / per_warp;
+                uint32_t wi = j - owner * per_warp;
+                int cx = 0, cy = 0;
+                const uint32_t li = (uint32_t)(threadIdx.x * kEsGpt + q);
+                for (uint32_t k = 0; k < cnt[q]; k++) {
+                    if ((wi >> kWinShift) == win) {
+                        const uint32_t tile = (uint32_t)((rminy[q] + cy) * gx + rminx[q] + cx);
+                        s_pair[owner * kWin + (wi & (kWin - 1))] = (tile << 10) | li;
+                    }
+                    if (++cx == rw[q]) {
+                        cx = 0;
+                        cy++;
+                    }
+                    if (++wi == per_warp) {
+                        wi = 0;
+                        owner++;
+                    }
                 }
-                if (++wi == per_warp) {
-                    wi = 0;
-                    owner++;
+            }
+        };
+        // A chunk whose pairs fit ONE window per warp (the usual case up to 1024 tiles) is expanded once, up
+        // front, and every warp counts its own range straight from shared memory (lane-parallel, only its own
+        // counter row): the rectangles are walked once instead of twice.
+        const bool one_window = n_win <= 1;  // uniform over the CTA
+        if (one_window) {
+            expand(0);
+            __syncthreads();
+            const uint32_t* wp = s_pair + warp * kWin;
+            uint32_t* wrow = reinterpret_cast<uint32_t*>(s_wcnt + warp * tp);
+            for (uint32_t i = lane; i < my_n; i += 32) {
+                const uint32_t tile = wp[i] >> 10;
+                atomicAdd(wrow + (tile >> 1), 1u << (16 * (tile & 1u)));
+            }
+        } else {
+            // ---- pass A: per-warp, per-tile counts.  Order is irrelevant for counting, so every thread walks
+            // its own Gaussians' rectangles and bumps the counter of the warp that OWNS each pair.
+    #pragma unroll
+            for (int q = 0; q < kEsGpt; q++) {
+                if (cnt[q] == 0) continue;
+                uint32_t j = my_off;
+    #pragma unroll
+                for (int qq = 0; qq < kEsGpt; qq++)
+                    if (qq < q) j += cnt[qq];
+                uint32_t owner = j / per_warp;
+                uint32_t wi = j - owner * per_warp;
+                int cx = 0, cy = 0;
+                for (uint32_t k = 0; k < cnt[q]; k++) {
+                    const uint32_t tile = (uint32_t)((rminy[q] + cy) * gx + rminx[q] + cx);
+                    atomicAdd(reinterpret_cast<uint32_t*>(s_wcnt + owner * tp) + (tile >> 1), 1u << (16 * (tile & 1u)));
+                    if (++cx == rw[q]) {
+                        cx = 0;
+                        cy++;
+                    }
+                    if (++wi == per_warp) {
+                        wi = 0;
+                        owner++;
+                    }
                 }
             }
         }
@@ -393,36 +437,13 @@ __global__ void __launch_bounds__(kEsThreads) emit_scatter_kernel(
                 s_base[t] = __ldg(tile_start + (size_t)seg * tiles + t) + excl[g];
             }
         }
-        // ---- pass B: expand the pairs IN ORDER into the owning warp's window, rank, scatter
+        // ---- pass B: (expand the pairs IN ORDER into the owning warp's window,) rank, scatter
         for (uint32_t win = 0; win < n_win; win++) {
             __syncthreads();  // windows are free; for win 0 also: s_base / s_wcnt are final
-#pragma unroll
-            for (int q = 0; q < kEsGpt; q++) {
-                if (cnt[q] == 0) continue;
-                uint32_t j = my_off;
-#pragma unroll
-                for (int qq = 0; qq < kEsGpt; qq++)
-                    if (qq < q) j += cnt[qq];
-                uint32_t owner = j / per_warp;
-                uint32_t wi = j - owner * per_warp;
-                int cx = 0, cy = 0;
-                const uint32_t li = (uint32_t)(threadIdx.x * kEsGpt + q);
-                for (uint32_t k = 0; k < cnt[q]; k++) {
-                    if ((wi >> kWinShift) == win) {
-                        const uint32_t tile = (uint32_t)((rminy[q] + cy) * gx + rminx[q] + cx);
-                        s_pair[owner * kWin + (wi & (kWin - 1))] = (tile << 10) | li;
-                    }
-                    if (++cx == rw[q]) {
-                        cx = 0;
-                        cy++;
-                    }
-                    if (++wi == per_warp) {
-                        wi = 0;
-                        owner++;
-                    }
-                }
+            if (!one_window) {
+                expand(win);
+                __syncthreads();
             }
-            __syncthreads();
             // my warp's window, 32 pairs per step, in pair order
             const uint32_t w_lo = win * kWin;
             const uint32_t w_n = (my_n > w_lo) ? min((uint32_t)kWin, my_n - w_lo) : 0u;
