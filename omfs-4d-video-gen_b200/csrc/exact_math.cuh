@@ -129,12 +129,16 @@ OMFS_HD void ex_face_frame(const float p0[3], const float p1[3], const float p2[
     out[16] = R[6]; out[17] = R[7]; out[18] = R[8]; out[19] = 0.0f;
 }
 
-// tile rectangle of a splat centred at (px,py) with integer radius r, clamped to the grid
+// tile rectangle of a splat centred at (px,py) with integer radius r, clamped to the grid.  The quotients are
+// clamped to [-1, g+1] BEFORE the conversion to int (same rectangle: the int clamp below absorbs the ends), so
+// that a far-away centre never converts an out-of-range float — undefined in C, and different on CPU and GPU.
 OMFS_HD void ex_tile_rect(float px, float py, int radius, int gx, int gy, int& minx, int& miny, int& maxx,
                           int& maxy) {
     const float rf = (float)radius;
-    const int a = (int)((px - rf) / 16.0f), b = (int)((py - rf) / 16.0f);
-    const int c = (int)((px + rf + 16.0f - 1.0f) / 16.0f), d = (int)((py + rf + 16.0f - 1.0f) / 16.0f);
+    const float hx = (float)gx + 1.0f, hy = (float)gy + 1.0f;
+    const int a = (int)fminf(fmaxf((px - rf) / 16.0f, -1.0f), hx), b = (int)fminf(fmaxf((py - rf) / 16.0f, -1.0f), hy);
+    const int c = (int)fminf(fmaxf((px + rf + 16.0f - 1.0f) / 16.0f, -1.0f), hx);
+    const int d = (int)fminf(fmaxf((py + rf + 16.0f - 1.0f) / 16.0f, -1.0f), hy);
     minx = a < 0 ? 0 : (a > gx ? gx : a);
     miny = b < 0 ? 0 : (b > gy ? gy : b);
     maxx = c < 0 ? 0 : (c > gx ? gx : c);
@@ -211,7 +215,7 @@ OMFS_HD bool ex_bind_project(const float ff[20], float lx, float ly, float lz, f
     const float vx = Vm[0] * mx + Vm[4] * my + Vm[8] * mz + Vm[12];
     const float vy = Vm[1] * mx + Vm[5] * my + Vm[9] * mz + Vm[13];
     const float vz = Vm[2] * mx + Vm[6] * my + Vm[10] * mz + Vm[14];
-    if (vz <= 0.2f) return false;
+    if (!(vz > 0.2f)) return false;  // the published near-plane cull; written so that a NaN depth is culled too
     const float hx = Pm[0] * mx + Pm[4] * my + Pm[8] * mz + Pm[12];
     const float hy = Pm[1] * mx + Pm[5] * my + Pm[9] * mz + Pm[13];
     const float hw = Pm[3] * mx + Pm[7] * my + Pm[11] * mz + Pm[15];
@@ -252,15 +256,19 @@ OMFS_HD bool ex_bind_project(const float ff[20], float lx, float ly, float lz, f
     const float c01 = T10 * u0 + T11 * u1 + T12 * u2;
     const float c11 = (T10 * w0 + T11 * w1v + T12 * w2v) + 0.3f;
     const float det = c00 * c11 - c01 * c01;
-    if (det == 0.0f) return false;
+    if (!(fabsf(det) > 0.0f)) return false;  // published: det == 0; a NaN determinant is culled as well
     const float det_inv = 1.0f / det;
     const float conx = c11 * det_inv, cony = -c01 * det_inv, conz = c00 * det_inv;
     const float mid = 0.5f * (c00 + c11);
     const float disc = sqrtf(fmaxf(0.1f, mid * mid - det));
     const float lam1 = mid + disc, lam2 = mid - disc;
-    const int radius = (int)ceilf(3.0f * sqrtf(fmaxf(lam1, lam2)));
+    const float rad_f = ceilf(3.0f * sqrtf(fmaxf(lam1, lam2)));
     const float px = ((ppx + 1.0f) * (float)width - 1.0f) * 0.5f;
     const float py = ((ppy + 1.0f) * (float)height - 1.0f) * 0.5f;
+    // degenerate inputs (NaN / infinite parameters, a zero-area parent triangle) are culled here, explicitly: the
+    // sum is finite exactly when every term is.  Nothing below depends on it for finite inputs.
+    if (!(fabsf(px) + fabsf(py) + rad_f + fabsf(conx) + fabsf(cony) + fabsf(conz) + vz < 3.0e38f)) return false;
+    const int radius = (int)fminf(rad_f, 1.0e6f);
     int minx, miny, maxx, maxy;
     ex_tile_rect(px, py, radius, gx, gy, minx, miny, maxx, maxy);
     const uint32_t tt = (uint32_t)((maxx - minx) * (maxy - miny));
@@ -304,7 +312,7 @@ OMFS_HD int ex_blend(float gx, float gy, float ca, float cb, float cc, float lo,
     const float v = cb * dx;
     const float s = fmaf(cc, dy, v);
     const float e = fmaf(s, dy, c0);
-    if ((e > lo) | (e < kLog2Inv255)) return 0;  // one combined predicate, no short-circuit branch
+    if (!((e <= lo) & (e >= kLog2Inv255))) return 0;  // one combined predicate; a NaN exponent (NaN opacity) skips
     const float alpha = fminf(0.99f, exp2_fn(e));
     const float testT = T * (1.0f - alpha);
     if (testT < 0.0001f) return 2;

@@ -58,6 +58,61 @@ def test_product_math_is_bit_identical_to_oracle(emu, small_scene):
     assert np.array_equal(bits(img), bits(res.image))
 
 
+def _degenerate_avatar(model, seed=41, n=600):
+    """An avatar with poisoned Gaussians: NaN / infinite local positions, an exp-overflowing scale, a centre 1e30
+    away, a NaN quaternion, a NaN opacity and SH coefficient."""
+    import omfs_b200  # noqa: F401
+    from omfs_b200 import avatar, synthetic
+    av = synthetic.make_avatar(n, model.n_faces, seed=seed)
+    av.xyz[5] = np.nan
+    av.xyz[6, 1] = np.inf
+    av.scaling[7] = 120.0            # exp(120) overflows float32
+    av.xyz[8] = 1e30
+    av.rotation[9] = np.nan
+    av.opacity[10] = np.nan
+    av.sh[11, 3, 1] = np.nan
+    av.xyz[12] = -1e30
+    return av, avatar.bake(av)
+
+
+def test_degenerate_gaussians_are_culled_identically(emu, small_scene):
+    """Non-finite or absurd Gaussians never reach the binning: product math and oracle cull the same ones (explicit
+    finiteness test in ex_bind_project, float clamps before every float->int conversion), bit for bit, and the
+    rest of the frame is untouched by them."""
+    model, params, _, _, cam = small_scene
+    W, H = cam.width, cam.height
+    with np.errstate(all="ignore"):
+        av, baked = _degenerate_avatar(model)
+        N = baked["n"]
+        one = params.slice(0, 1)
+        res = oracle.render(model, one, baked, [cam.pack()], W, H)
+    assert np.isfinite(res.pre.P0).all() and np.isfinite(res.pre.P1[..., :3]).all() and np.isfinite(res.pre.P2).all()
+    assert np.isnan(res.pre.P1[0, 10, 3])                    # the NaN opacity rides along, and is never blended
+    assert np.isfinite(res.image).all()
+    for n in (5, 6, 7, 8, 9, 12):
+        assert res.pre.tiles_touched[0, n] == 0, n          # culled
+    assert res.pre.tiles_touched[0, 11] > 0 and res.pre.tiles_touched[0, 10] > 0   # NaN colour / opacity do not cull
+    assert (res.pre.tiles_touched[0] > 0).sum() > N // 2     # the healthy ones are still there
+    P = [np.zeros((N, 4), np.float32) for _ in range(3)]
+    tt = np.zeros(N, np.uint32)
+    emu.emu_bind_preprocess(N, model.n_faces, W, H, np.ascontiguousarray(res.ff[0]), baked["xyzb"], baked["scale_lo"],
+                            baked["rot"], baked["sh"], cam.pack(), P[0], P[1], P[2], tt)
+    assert np.array_equal(tt, res.pre.tiles_touched[0])
+    assert np.array_equal(bits(P[0]), bits(res.pre.P0[0])) and np.array_equal(bits(P[1]), bits(res.pre.P1[0]))
+    assert np.array_equal(bits(P[2]), bits(res.pre.P2[0]))
+    img = np.zeros_like(res.image)
+    emu.emu_composite(1, N, W, H, res.pre.P0.reshape(-1), res.pre.P1.reshape(-1), res.pre.P2.reshape(-1),
+                      res.binned.sorted_values, res.binned.ranges.reshape(-1), np.ones(3, np.float32), img.reshape(-1))
+    assert np.array_equal(bits(img), bits(res.image))
+    # the poisoned Gaussians change nothing but their own absence: same frame as an avatar without them
+    keep = np.setdiff1d(np.arange(N), [5, 6, 7, 8, 9, 10, 12])
+    from omfs_b200 import avatar as avatar_mod, synthetic
+    clean = synthetic.Avatar(av.xyz[keep], av.scaling[keep], av.rotation[keep], av.opacity[keep], av.sh[keep],
+                             av.binding[keep])
+    ref2 = oracle.render(model, one, avatar_mod.bake(clean), [cam.pack()], W, H)
+    assert np.array_equal(bits(ref2.image), bits(res.image))
+
+
 def test_oracle_binning_invariants(small_scene):
     model, params, av, baked, cam = small_scene
     W, H = cam.width, cam.height

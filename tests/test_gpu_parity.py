@@ -239,6 +239,30 @@ def test_tapered_multi_batch_call_and_dense_opaque_splats(rt):
     sess.close()
 
 
+def test_degenerate_gaussians_on_device(rt, small_scene):
+    """NaN / infinite / absurd Gaussians (tests/test_exact_math_host.py::_degenerate_avatar): the device culls exactly
+    the ones the oracle culls (tiles touched, P0 bit for bit), never blends the NaN-opacity one, and the frame is
+    finite and within tolerance of the oracle's."""
+    import oracle
+    from test_exact_math_host import _degenerate_avatar
+    model, params, _, _, cam = small_scene
+    W, H = cam.width, cam.height
+    with np.errstate(all="ignore"):
+        av, baked = _degenerate_avatar(model)
+        one = params.slice(0, 1)
+        sess, u8, img = run_session(rt, model, one, baked, [cam], W, H, max_batch=1)
+        verts = sess.tap_array("verts", (1, model.n_verts, 3), np.float32)
+        ref = oracle.render(model, one, baked, [cam.pack()], W, H, verts=verts)
+    N = baked["n"]
+    assert np.array_equal(sess.tap_array("tiles_touched", (1, N), np.uint32), ref.pre.tiles_touched)
+    assert np.array_equal(bits(sess.tap_array("P0", (1, N, 4), np.float32)), bits(ref.pre.P0))
+    R = ref.binned.n_pairs
+    assert np.array_equal(sess.tap_array("keys", (R,), np.uint64), ref.binned.sorted_keys)
+    assert np.array_equal(sess.tap_array("vals", (R,), np.uint32), ref.binned.sorted_values)
+    assert np.isfinite(img).all() and np.abs(img - ref.image).max() <= 2e-4
+    sess.close()
+
+
 def test_empty_and_fully_culled(rt, small_scene):
     """No frames -> no work; a camera looking away culls everything -> background only, zero pairs."""
     import oracle
