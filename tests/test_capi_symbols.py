@@ -44,3 +44,55 @@ def test_no_cpu_fallback_without_gpu():
     model, params, av, cam = synthetic.make_scene(n_gauss=100, n_frames=1, width=32, height=32, n_verts=162)
     with pytest.raises(runtime.OmfsError):
         runtime.Session(model, avatar.bake(av), 32, 32)
+
+
+def _header_struct_fields(name):
+    """Field names of `typedef struct <name> {...}` in include/omfs_b200.h, in declaration order."""
+    import re
+    from omfs_b200 import runtime
+    text = re.sub(r"/\*.*?\*/", "", open(runtime.HEADER_PATH).read(), flags=re.S)
+    body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (name, name), text, flags=re.S).group(1)
+    fields = []
+    for decl in body.split(";"):
+        decl = decl.strip()
+        if not decl:
+            continue
+        names = decl.split(None, 1)[1] if not decl.startswith("const") else decl.split(None, 2)[2]
+        for n in names.split(","):
+            fields.append(re.sub(r"[\*\s]|\[.*\]", "", n))
+    return fields
+
+
+def test_ctypes_structs_match_the_header_layout(tmp_path):
+    """The three structs that cross the C-ABI: field order in runtime.py and in INTEGRATION.md's stub equals the
+    header's, and gcc's sizeof / offsetof equal ctypes' (the header is compiled as plain C, as a cgo/ctypes user would)."""
+    import re
+    import subprocess
+    import omfs_b200  # noqa: F401
+    from omfs_b200 import runtime
+    pairs = [("omfs_model_desc", runtime.ModelDesc), ("omfs_session_config", runtime.SessionConfig),
+             ("omfs_frames_desc", runtime.FramesDesc)]
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    stub = open(os.path.join(root, "INTEGRATION.md")).read()
+    src = ['#include <stdio.h>', '#include <stddef.h>', '#include "omfs_b200.h"', 'int main(void) {']
+    for cname, cls in pairs:
+        fields = _header_struct_fields(cname)
+        assert fields == [f[0] for f in cls._fields_], cname
+        src.append(f'printf("{cname} %zu", sizeof({cname}));')
+        for f in fields:
+            src.append(f'printf(" %zu", offsetof({cname}, {f}));')
+        src.append('printf("\\n");')
+        # the stub in INTEGRATION.md names the same fields, in the same order
+        cls_src = re.search(r"class _\w+\(ctypes\.Structure\):\s+# %s\n(.*?)(?=\nclass |\ndef )" % cname, stub, flags=re.S).group(1)
+        quoted = re.findall(r'"([a-z_0-9]+)"', cls_src)
+        assert quoted == fields, (cname, quoted)
+    src += ['return 0; }']
+    c = tmp_path / "abi.c"
+    c.write_text("\n".join(src))
+    exe = tmp_path / "abi"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(root, "include"), str(c), "-o", str(exe)])
+    out = subprocess.check_output([str(exe)], text=True).strip().splitlines()
+    for line, (cname, cls) in zip(out, pairs):
+        nums = [int(x) for x in line.split()[1:]]
+        assert nums[0] == ctypes.sizeof(cls), cname
+        assert nums[1:] == [getattr(cls, f[0]).offset for f in cls._fields_], cname
