@@ -172,13 +172,13 @@ def _write_png(path: str, rgb_u8: np.ndarray) -> None:
     Image.fromarray(rgb_u8, mode="RGB").save(path, compress_level=1)
 
 
-def write_frames_png(renders_dir: str, frames_u8: np.ndarray, workers: int | None = None) -> list[str]:
+def write_frames_png(renders_dir: str, frames_u8: np.ndarray, workers: int | None = None, first: int = 0) -> list[str]:
     """The frame sink: uint8 [T,H,W,3] -> renders_dir/%05d.png (the names the reference's upstream renderer
     writes, render_surgery.py:324-362).  After the GPU path the PNG encode is the wall-clock bottleneck of
     render_with_gaussians, so the files are written by a thread pool (zlib releases the GIL)."""
     from concurrent.futures import ThreadPoolExecutor
     os.makedirs(renders_dir, exist_ok=True)
-    paths = [os.path.join(renders_dir, f"{i:05d}.png") for i in range(len(frames_u8))]
+    paths = [os.path.join(renders_dir, f"{first + i:05d}.png") for i in range(len(frames_u8))]  # `first`: a rank's block
     if workers is None:
         workers = min(16, len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
     if workers <= 1 or len(paths) <= 1:
@@ -190,36 +190,77 @@ def write_frames_png(renders_dir: str, frames_u8: np.ndarray, workers: int | Non
     return paths
 
 
+def _agree(agree, error: BaseException | None, what: str):
+    """Meet the other ranks; if any of them failed, every rank raises (the first failure, as RuntimeError on the
+    ranks that did not fail themselves)."""
+    entries = agree(None if error is None else f"{type(error).__name__}: {error}")
+    if error is not None:
+        raise error
+    bad = [(r, e) for r, e in enumerate(entries) if e is not None]
+    if bad:
+        raise RuntimeError(f"{what} failed on rank {bad[0][0]}:\n{bad[0][1][-2000:]}")
+
+
 def _render_dataset(model_path: str, data_dir: str, iteration: int = -1,
                     clear_old_renders: bool = True) -> tuple[str, np.ndarray]:
     """render_with_gaussians, also returning the frames it wrote (uint8 [T,H,W,3]) so that main() can hand them
-    to the encoder without reading the PNGs back."""
+    to the encoder without reading the PNGs back.
+
+    Under torchrun (WORLD_SIZE > 1, one process per GPU) every rank renders the contiguous frame
+    block `sharding.frame_block` gives it on its own GPU and writes its own PNGs; rank 0 alone purges stale
+    renders first.  No frame crosses ranks; the returned array is then the rank's block only."""
+    from . import sharding
+    rank, world, agree = sharding.host_ranks()
     train_dir = os.path.join(model_path, "train")
-    if clear_old_renders and os.path.isdir(train_dir):  # stale frames must never be picked up (:260-267)
-        for d in os.listdir(train_dir):
-            renders = os.path.join(train_dir, d, "renders")
-            if os.path.isdir(renders):
-                print(f"[render_surgery] Clearing old renders: {renders}")
-                shutil.rmtree(renders)
-    it = _pick_iteration(model_path, iteration)
-    ply = os.path.join(model_path, "point_cloud", f"iteration_{it}", "point_cloud.ply")
-    if not os.path.exists(ply):
-        raise FileNotFoundError(f"Checkpoint not found: {ply}")
-    model = flame_io.load_flame_model(_find_flame_model(model_path))
-    frames = flame_io.load_transforms(data_dir, "train")
-    if not frames:
-        raise FileNotFoundError("No rendered frames found after GaussianAvatars rendering.")
-    params = flame_io.load_dataset_params(data_dir, frames, model.n_verts)
-    av = flame_io.load_avatar_ply(ply)
-    if int(av.binding.max()) >= model.n_faces:
-        raise ValueError("avatar binding index exceeds the FLAME face count")
-    print(f"[render_surgery] Rendering {len(frames)} frames, {av.n} Gaussians, iteration {it} (in-process, B200)")
+    err = None
     try:
-        images = _render_frames(model, params, av, [f.camera for f in frames])
-    except Exception as e:  # the reference surfaces renderer failures as RuntimeError (:317-322)
-        raise RuntimeError(f"Rendering failed:\n{str(e)[-2000:]}") from e
-    renders_dir = os.path.join(train_dir, f"ours_{it}", "renders")
-    write_frames_png(renders_dir, images)
+        if rank == 0 and clear_old_renders and os.path.isdir(train_dir):  # stale frames must never be picked up (:260-267)
+            for d in os.listdir(train_dir):
+                renders = os.path.join(train_dir, d, "renders")
+                if os.path.isdir(renders):
+                    print(f"[render_surgery] Clearing old renders: {renders}")
+                    shutil.rmtree(renders)
+    except Exception as e:
+        err = e
+    if world > 1:
+        _agree(agree, err, "Clearing old renders")
+    elif err is not None:
+        raise err
+    err = None
+    renders_dir, images = "", None
+    try:
+        it = _pick_iteration(model_path, iteration)
+        ply = os.path.join(model_path, "point_cloud", f"iteration_{it}", "point_cloud.ply")
+        if not os.path.exists(ply):
+            raise FileNotFoundError(f"Checkpoint not found: {ply}")
+        model = flame_io.load_flame_model(_find_flame_model(model_path))
+        frames = flame_io.load_transforms(data_dir, "train")
+        if not frames:
+            raise FileNotFoundError("No rendered frames found after GaussianAvatars rendering.")
+        params = flame_io.load_dataset_params(data_dir, frames, model.n_verts)
+        av = flame_io.load_avatar_ply(ply)
+        if int(av.binding.max()) >= model.n_faces:
+            raise ValueError("avatar binding index exceeds the FLAME face count")
+        lo, hi = sharding.frame_block(len(frames), rank, world)
+        where = "" if world == 1 else f" [rank {rank}/{world}: frames {lo}-{hi - 1}]"
+        print(f"[render_surgery] Rendering {len(frames)} frames, {av.n} Gaussians, iteration {it} "
+              f"(in-process, B200){where}")
+        cams = [f.camera for f in frames]
+        try:
+            if hi > lo:
+                images = _render_frames(model, params.slice(lo, hi), av, cams[lo:hi])
+            else:
+                images = np.empty((0, cams[0].height, cams[0].width, 3), np.uint8)
+        except Exception as e:  # the reference surfaces renderer failures as RuntimeError (:317-322)
+            raise RuntimeError(f"Rendering failed:\n{str(e)[-2000:]}") from e
+        renders_dir = os.path.join(train_dir, f"ours_{it}", "renders")
+        write_frames_png(renders_dir, images, first=lo)
+    except Exception as e:
+        err = e
+    if world > 1:
+        _agree(agree, err, "Rendering")  # also the barrier: every rank's PNGs are on disk past this point
+    elif err is not None:
+        raise err
     print(f"[render_surgery] Frames rendered to: {renders_dir}")
     return renders_dir, images
 
@@ -377,16 +418,23 @@ def main(argv: list[str] | None = None):
     print(f"[render_surgery] Le Fort: {args.lefort_mm} mm -> offset {lefort_offset:.6f}")
     print(f"[render_surgery] BSSO:    {args.bsso_mm} mm -> offset {bsso_offset:.6f}")
     print(f"[render_surgery] Rig mode: {mode} ({reason})")
+    from . import sharding
+    rank, world, _ = sharding.host_ranks()
+    # under torchrun every rank edits its own temporary copy (the edit is cheap and keeps the ranks independent)
     modified_dir = create_modified_dataset(args.data_dir, lefort_offset, bsso_offset, deformation_map=deformation_map)
     try:
         frames_dir, frames_u8 = _render_dataset(args.model_path, modified_dir, iteration=args.iteration)
-        if args.export_frames_dir:
-            export_deterministic_frames(frames_dir, args.export_frames_dir,
-                                        index_file=args.deterministic_indices or None,
-                                        max_frames=args.deterministic_max_frames)
-        # same video as stitch_video(frames_dir, ...): the PNGs above are lossless, so the encoder gets the same
-        # pixels, without the reference's per-frame file copy and the PNG decode
-        stitch_video_frames(frames_u8, args.output, fps=args.fps)
+        if rank == 0:
+            if args.export_frames_dir:
+                export_deterministic_frames(frames_dir, args.export_frames_dir,
+                                            index_file=args.deterministic_indices or None,
+                                            max_frames=args.deterministic_max_frames)
+            if world == 1:
+                # same video as stitch_video(frames_dir, ...): the PNGs above are lossless, so the encoder gets the
+                # same pixels, without the reference's per-frame file copy and the PNG decode
+                stitch_video_frames(frames_u8, args.output, fps=args.fps)
+            else:
+                stitch_video(frames_dir, args.output, fps=args.fps)  # the other ranks' frames are on disk
     finally:
         shutil.rmtree(modified_dir, ignore_errors=True)
     print("[render_surgery] Done.")

@@ -46,6 +46,39 @@ def gather_frames(local_u8, n_total: int, rank: int, world: int, dst: int = 0):
     return None
 
 
+_HOST_GROUP = None
+
+
+def host_ranks():
+    """(rank, world, agree) of the torchrun launch this process belongs to; (0, 1, agree) in a plain process.
+
+    `agree(error)` is the host-side meeting point of the file-based drop-in (`render_with_gaussians` under
+    torchrun: every rank renders its frame block and writes its own PNGs, so no frame crosses ranks): every rank
+    passes `None` or the text of the exception it caught, and gets back the list of all ranks' entries — a rank
+    that failed makes every rank raise instead of leaving the others waiting at a barrier.  It runs on a gloo
+    group (CPU), created once from the torchrun environment if the caller has not initialised
+    torch.distributed."""
+    import os
+    global _HOST_GROUP
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world <= 1:
+        return 0, 1, (lambda error=None: [error])
+    import torch.distributed as dist
+    if not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("gloo")
+    if _HOST_GROUP is None:
+        _HOST_GROUP = dist.new_group(backend="gloo") if dist.get_backend() != "gloo" else dist.group.WORLD
+    group = _HOST_GROUP
+
+    def agree(error=None):
+        entries = [None] * dist.get_world_size(group)
+        dist.all_gather_object(entries, error, group=group)
+        return entries
+
+    return dist.get_rank(), dist.get_world_size(), agree
+
+
 class PeerFrameGather:
     """Finished frames of every rank -> one [world, slot_bytes] device buffer on rank `dst`.
 

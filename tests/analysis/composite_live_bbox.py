@@ -29,7 +29,7 @@ P0, P1 = res.pre.P0[0], res.pre.P1[0]
 vals, ranges = res.binned.sorted_values, res.binned.ranges
 L2_255 = np.float32(-7.99435343685885793770)
 gxt = W // 16
-tot = dict(A=0, E=0, Es=0, G=0, C=0, F=0, entries=0, rounds=0, rounds_changed=0, rounds_bbox_changed=0, live_hist=np.zeros(65, np.int64))
+tot = dict(A=0, E=0, Es=0, G=0, C=0, F=0, entries=0, rounds=0, rounds_changed=0, rounds_bbox_changed=0, Es_half=0, Es_le32=0, Es_le16=0, Es_live_sum=0, live_hist=np.zeros(65, np.int64))
 for tile in range(ranges.shape[0]):
     lo, hi = int(ranges[tile, 0]), int(ranges[tile, 1])
     if hi <= lo:
@@ -84,6 +84,13 @@ for tile in range(ranges.shape[0]):
             src = np.maximum((idx // 32 - 1) * 32, 0)
             hitEs = vis & lb & (gx + ex >= x0[src]) & (gx - ex <= x1[src]) & (gy + ey >= y0[src]) & (gy - ey <= y1[src])
             tot["Es"] += int(hitEs.sum())
+            # lane occupancy of what is still evaluated: live pixels per combination, and how often one of the lane's
+            # two pixel rows groups (rows 0-3 / rows 4-7) is entirely dead (a one-pixel-per-lane loop would do)
+            nl = lv[hitEs].sum(axis=(1, 2))
+            top = lv[hitEs][:, :4, :].any(axis=(1, 2)); bot = lv[hitEs][:, 4:, :].any(axis=(1, 2))
+            tot["Es_half"] += int((~top | ~bot).sum())
+            tot["Es_le32"] += int((nl <= 32).sum()); tot["Es_le16"] += int((nl <= 16).sum())
+            tot["Es_live_sum"] += int(nl.sum())
             # rounds walked while live, and rounds after which the live mask / the live box changed
             last = int(lb.sum())                       # entries walked (live is monotone)
             nr = (last + 31) // 32
@@ -105,6 +112,8 @@ h = tot.pop("live_hist")
 print(tot)
 for k in ("E", "Es", "G", "C", "F"):
     print(f"{k}/A = {tot[k] / tot['A']:.3f}")
+print("under Es: mean live pixels %.1f of 64; one row group dead %.3f; <=32 live %.3f; <=16 live %.3f"
+      % (tot["Es_live_sum"] / tot["Es"], tot["Es_half"] / tot["Es"], tot["Es_le32"] / tot["Es"], tot["Es_le16"] / tot["Es"]))
 c = np.cumsum(h) / h.sum()
 print("live pixels per evaluated (entry, block) under A: share with <=8 live %.3f, <=16 %.3f, <=32 %.3f, <=48 %.3f, 64 live %.3f"
       % (c[8], c[16], c[32], c[48], h[64] / h.sum()))

@@ -58,3 +58,64 @@ def test_gather_frames_world2_gloo(tmp_path, n_total):
     assert got.shape == (n_total, 4, 6, 3)
     for t in range(n_total):
         assert np.all(got[t] == t % 251)
+
+
+def _dropin_worker(rank, world, port, data, mdl, fail_rank):
+    """render_with_gaussians under a torchrun-like launch (env only; the function sets up its own gloo group).  The
+    GPU renderer is replaced by a stand-in that paints each frame with a value read from ITS parameters, so the
+    test sees which rank rendered which frame from the files alone."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    from omfs_b200 import render_surgery as rs
+
+    def fake_render(model, params, av, cams, plan_offset=None, device=None):
+        if rank == fail_rank:
+            raise ValueError("injected renderer failure")
+        assert len(cams) == params.n_frames
+        out = np.zeros((params.n_frames, cams[0].height, cams[0].width, 3), np.uint8)
+        out[..., 0] = np.round(params.translation[:, 0] * 1000).astype(np.uint8)[:, None, None]   # frame id
+        out[..., 1] = 10 + rank
+        return out
+
+    rs._render_frames = fake_render
+    try:
+        d = rs.render_with_gaussians(mdl, data)
+        open(os.path.join(mdl, f"result_{rank}.txt"), "w").write("ok " + d)
+    except Exception as e:
+        open(os.path.join(mdl, f"result_{rank}.txt"), "w").write(f"{type(e).__name__} {e}")
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("fail_rank", [-1, 1])
+def test_render_with_gaussians_under_torchrun_world2(tmp_path, fail_rank):
+    """Two ranks: stale renders purged once, every frame written exactly once under its global name by the rank
+    that owns its block, both ranks return the same directory; a renderer failure on one rank raises on both."""
+    from PIL import Image
+    from omfs_b200 import cameras, flame_io, synthetic
+    T, W, H, V = 7, 32, 24, 162
+    model = synthetic.make_flame_model(seed=8, n_verts=V)
+    params = synthetic.make_frame_params(T, seed=9, n_verts=V)
+    params.translation[:, 0] = np.arange(T, dtype=np.float32) / 1000.0     # frame id, carried by the parameters
+    av = synthetic.make_avatar(50, model.n_faces, seed=10)
+    c2w = cameras.look_at_c2w((0.0, 0.0, 1.0), (0.0, 0.0, 0.0))
+    data, mdl = str(tmp_path / "data"), str(tmp_path / "model")
+    flame_io.write_synthetic_dataset(data, mdl, model, params, av, c2w, 0.3, W, H, iteration=3000)
+    n_train = len(flame_io.load_transforms(data, "train"))
+    stale = os.path.join(mdl, "train", "ours_1", "renders")
+    os.makedirs(stale)
+    open(os.path.join(stale, "00000.png"), "wb").write(b"stale")
+    mp.spawn(_dropin_worker, args=(2, _free_port(), data, mdl, fail_rank), nprocs=2, join=True)
+    results = [open(os.path.join(mdl, f"result_{r}.txt")).read() for r in range(2)]
+    assert not os.path.exists(stale)
+    renders = os.path.join(mdl, "train", "ours_3000", "renders")
+    if fail_rank >= 0:
+        assert results[1].startswith("RuntimeError Rendering failed:") and "injected renderer failure" in results[1]
+        assert results[0].startswith("RuntimeError Rendering failed on rank 1") and "injected" in results[0]
+        return
+    assert results == ["ok " + renders] * 2
+    assert sorted(os.listdir(renders)) == [f"{t:05d}.png" for t in range(n_train)]
+    for t in range(n_train):
+        img = np.asarray(Image.open(os.path.join(renders, f"{t:05d}.png")))
+        assert img.shape == (H, W, 3) and (img[..., 0] == t).all()
+        lo, hi = sharding.frame_block(n_train, 0, 2)
+        assert (img[..., 1] == (10 if lo <= t < hi else 11)).all()
