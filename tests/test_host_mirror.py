@@ -276,3 +276,68 @@ def test_avatar_bake_is_the_upstream_activation():
     assert np.array_equal(avatar.binding_of(b), av.binding)
     flat = av.sh.reshape(500, 48)
     assert np.array_equal(b["sh"][5, :, 2], flat[:, 22])      # flat index 22 -> plane 5, lane 2
+
+
+def test_main_flow_with_a_stand_in_renderer(tmp_path, monkeypatch):
+    """main()'s control flow without a GPU: the renderer and ffmpeg are stand-ins; the parameter edit reaches the
+    renderer, PNGs land in the upstream layout, the encoder gets exactly those frames, the deterministic export and
+    the clean-up of the temporary dataset happen, and the renderer's errors keep the reference's exception types."""
+    import json
+    from PIL import Image
+    import omfs_b200  # noqa: F401
+    from omfs_b200 import cameras, flame_io, render_surgery as rs, synthetic
+    T, W, H, V = 5, 32, 24, 162
+    model = synthetic.make_flame_model(seed=8, n_verts=V)
+    params = synthetic.make_frame_params(T, seed=9, n_verts=V)
+    av = synthetic.make_avatar(50, model.n_faces, seed=10)
+    c2w = cameras.look_at_c2w((0.0, 0.0, 1.0), (0.0, 0.0, 0.0))
+    data, mdl = str(tmp_path / "data"), str(tmp_path / "model")
+    flame_io.write_synthetic_dataset(data, mdl, model, params, av, c2w, 0.3, W, H, iteration=3000)
+    n_train = len(flame_io.load_transforms(data, "train"))
+    seen = {}
+
+    def fake_render(model_, params_, av_, cams, plan_offset=None, device=None):
+        seen["translation"] = params_.translation.copy()
+        seen["jaw"] = params_.jaw_pose.copy()
+        out = np.zeros((params_.n_frames, H, W, 3), np.uint8)
+        out[..., 0] = np.arange(params_.n_frames, dtype=np.uint8)[:, None, None]
+        return out
+
+    fake = tmp_path / "ffmpeg"
+    fake.write_text("#!/bin/sh\nfor a in \"$@\"; do echo \"$a\" >> %s; done\ncat > %s\n" %
+                    (tmp_path / "args.txt", tmp_path / "stdin.bin"))
+    fake.chmod(0o755)
+    monkeypatch.setattr(rs, "_render_frames", fake_render)
+    monkeypatch.setattr(rs, "_get_ffmpeg_path", lambda: str(fake))
+    monkeypatch.delenv("WORLD_SIZE", raising=False)
+    made = []
+    real_create = rs.create_modified_dataset
+    monkeypatch.setattr(rs, "create_modified_dataset", lambda *a, **k: made.append(real_create(*a, **k)) or made[-1])
+    out = tmp_path / "video" / "final.mp4"
+    rs.main(["--lefort_mm", "5", "--bsso_mm", "-3", "--sensitivity", "2", "--model_path", mdl, "--data_dir", data,
+             "--output", str(out), "--fps", "24", "--export_frames_dir", str(tmp_path / "ab"),
+             "--deterministic_max_frames", "2"])
+    # R1 + R2 reached the renderer: translation y += 5 mm * 2 * 0.001, jaw x += -3 mm * 2 * 0.001
+    np.testing.assert_allclose(seen["translation"][:, 1], params.translation[:n_train, 1] + np.float32(0.01), atol=1e-7)
+    np.testing.assert_allclose(seen["jaw"][:, 0], params.jaw_pose[:n_train, 0] - np.float32(0.006), atol=1e-7)
+    renders = os.path.join(mdl, "train", "ours_3000", "renders")
+    names = sorted(os.listdir(renders))
+    assert names == [f"{i:05d}.png" for i in range(n_train)]
+    frames = np.stack([np.asarray(Image.open(os.path.join(renders, n))) for n in names])
+    assert (frames[..., 0] == np.arange(n_train)[:, None, None]).all()
+    assert (tmp_path / "stdin.bin").read_bytes() == frames.tobytes()
+    args = (tmp_path / "args.txt").read_text().split("\n")
+    assert args[args.index("-framerate") + 1] == "24" and args[args.index("-s") + 1] == f"{W}x{H}"
+    assert json.load(open(tmp_path / "ab" / "deterministic_indices_manifest.json"))["selected_indices"] == [0, n_train - 1]
+    assert made and not os.path.exists(made[0])
+
+    def broken(*a, **k):
+        raise ValueError("device lost")
+    monkeypatch.setattr(rs, "_render_frames", broken)
+    with pytest.raises(RuntimeError, match="Rendering failed:\n.*device lost"):
+        rs.render_with_gaussians(mdl, data)
+    bad = flame_io.load_avatar_ply(os.path.join(mdl, "point_cloud", "iteration_3000", "point_cloud.ply"))
+    bad.binding[:] = model.n_faces + 5
+    flame_io.save_avatar_ply(os.path.join(mdl, "point_cloud", "iteration_3000", "point_cloud.ply"), bad)
+    with pytest.raises(ValueError, match="binding"):
+        rs.render_with_gaussians(mdl, data)
