@@ -5,8 +5,9 @@
   * `flame_param.npz` / `flame_param/%05d.npz` / `canonical_flame_param.npz` records
     (/root/reference/02_Visual_Engine/flame_fitter.py:431-441, preprocess_video.py:314-354);
   * `transforms_{train,test,val}.json` (preprocess_video.py:372-401);
-  * the FLAME-like linear model as an .npz (the real pickle is licence-gated; a converter for
-    pickles that load without chumpy is included).
+  * the FLAME linear model: an .npz, or the published pickle read directly (chumpy-wrapped arrays, scipy-sparse
+    joint regressor, uint32 kinematic table) without chumpy installed (the real file is licence-gated; the tests
+    build one of the same structure).
 """
 from __future__ import annotations
 
@@ -18,7 +19,7 @@ from dataclasses import dataclass
 import numpy as np
 
 from . import cameras as cam_mod
-from .synthetic import Avatar, FlameModel, FrameParams
+from .synthetic import PARENTS, Avatar, FlameModel, FrameParams
 
 _PLY_TYPES = {
     "char": "i1", "int8": "i1", "uchar": "u1", "uint8": "u1", "short": "i2", "int16": "i2",
@@ -143,9 +144,34 @@ def save_flame_model(path: str, m: FlameModel) -> None:
              j_regressor=m.j_regressor, lbs_weights=m.lbs_weights, parents=m.parents)
 
 
+class _ChumpyArray:
+    """Stand-in for `chumpy.ch.Ch` while unpickling: the published FLAME pickles (flame2023.pkl, generic_model.pkl)
+    store v_template, shapedirs, posedirs, J and weights as chumpy objects, and chumpy is neither maintained nor
+    installed next to a renderer.  Only the wrapped ndarray (`x`) is kept."""
+
+    def __setstate__(self, state):
+        self.__dict__.update(state if isinstance(state, dict) else {"x": state})
+
+    def __array__(self, dtype=None, copy=None):
+        x = self.__dict__.get("x")
+        if x is None:  # any other chumpy node type: the first array it holds
+            x = next((v for v in self.__dict__.values() if isinstance(v, np.ndarray)), None)
+        if x is None:
+            raise ValueError("chumpy object without array data in the FLAME pickle")
+        return np.asarray(x, dtype=dtype)
+
+
+class _FlameUnpickler(pickle.Unpickler):
+    def find_class(self, module, name):
+        if module == "chumpy" or module.startswith("chumpy."):
+            return _ChumpyArray
+        return super().find_class(module, name)
+
+
 def load_flame_model(path: str) -> FlameModel:
-    """.npz written by save_flame_model, or a FLAME-style pickle whose arrays unpickle as numpy
-    (keys v_template, shapedirs [V,3,400], posedirs [V,3,36], J_regressor, weights, f, kintree_table)."""
+    """.npz written by save_flame_model, or a FLAME pickle as the reference reads it (flame_fitter.py:79-108:
+    keys v_template, shapedirs [V,3,400], posedirs [V*3... as (V,3,36)], J_regressor (scipy sparse or dense), weights,
+    f, kintree_table), with or without chumpy-wrapped arrays."""
     if not os.path.exists(path):
         raise FileNotFoundError(f"FLAME model not found: {path}")
     if path.endswith(".npz"):
@@ -153,18 +179,29 @@ def load_flame_model(path: str) -> FlameModel:
         return FlameModel(*(np.ascontiguousarray(d[k]) for k in
                             ("v_template", "faces", "shapedirs", "posedirs", "j_regressor", "lbs_weights", "parents")))
     with open(path, "rb") as f:
-        d = pickle.load(f, encoding="latin1")
+        d = _FlameUnpickler(f, encoding="latin1").load()
     v = np.asarray(d["v_template"], np.float32)
     V = v.shape[0]
     sd = np.asarray(d["shapedirs"], np.float32)            # (V,3,400)
     pd = np.asarray(d["posedirs"], np.float32)             # (V,3,36)
     jr = d["J_regressor"]
     jr = np.asarray(jr.todense() if hasattr(jr, "todense") else jr, np.float32)
+    parents = PARENTS.copy()
+    if "kintree_table" in d:                                # flame_fitter.py:104-106: parents = kintree[0], root = -1
+        parents = np.asarray(d["kintree_table"]).astype(np.int64)[0].copy()
+        parents[0] = -1
+        parents = parents.astype(np.int32)
+        if not np.array_equal(parents, PARENTS):
+            raise ValueError(f"{path}: kinematic tree {parents.tolist()} is not FLAME's {PARENTS.tolist()} "
+                             "(root, neck, jaw, two eyes); the skinning kernel is built for that chain")
+    if sd.shape[:2] != (V, 3) or pd.reshape(V * 3, -1).shape[1] != 36 or jr.shape != (5, V):
+        raise ValueError(f"{path}: not a FLAME model (v_template {v.shape}, shapedirs {sd.shape}, posedirs {pd.shape}, "
+                         f"J_regressor {jr.shape})")
     return FlameModel(
-        v_template=v, faces=np.asarray(d["f"], np.int32),
+        v_template=v, faces=np.asarray(d["f"]).astype(np.int32),
         shapedirs=np.ascontiguousarray(sd.reshape(V * 3, -1).T),
         posedirs=np.ascontiguousarray(pd.reshape(V * 3, -1).T),
-        j_regressor=np.ascontiguousarray(jr), lbs_weights=np.asarray(d["weights"], np.float32))
+        j_regressor=np.ascontiguousarray(jr), lbs_weights=np.asarray(d["weights"], np.float32), parents=parents)
 
 
 # --------------------------------------------------------------------------------------- parameters

@@ -341,3 +341,59 @@ def test_main_flow_with_a_stand_in_renderer(tmp_path, monkeypatch):
     flame_io.save_avatar_ply(os.path.join(mdl, "point_cloud", "iteration_3000", "point_cloud.ply"), bad)
     with pytest.raises(ValueError, match="binding"):
         rs.render_with_gaussians(mdl, data)
+
+
+def test_flame_pickle_with_chumpy_arrays_loads_without_chumpy(tmp_path):
+    """The published FLAME pickles wrap their arrays in chumpy objects and hold a scipy-sparse joint regressor and a
+    uint32 kinematic table (what flame_fitter.py:79-108 reads with chumpy installed).  The loader needs neither
+    chumpy nor any conversion step, gives the same model as the .npz form, and refuses another skeleton."""
+    import pickle
+    import sys
+    import types
+    import scipy.sparse as sp
+    import omfs_b200  # noqa: F401
+    from omfs_b200 import flame_io, synthetic
+    model = synthetic.make_flame_model(seed=3, n_verts=162)
+    V = model.n_verts
+
+    class Ch:                                   # pickled by reference as chumpy.ch.Ch, like the real files
+        def __init__(self, x):
+            self.x = np.asarray(x, np.float64)
+            self._dirty_vars = set()
+            self._itr = None
+    Ch.__module__, Ch.__qualname__ = "chumpy.ch", "Ch"
+    pkg, sub = types.ModuleType("chumpy"), types.ModuleType("chumpy.ch")
+    sub.Ch = Ch
+    sys.modules["chumpy"], sys.modules["chumpy.ch"] = pkg, sub
+    try:
+        record = {
+            "v_template": Ch(model.v_template),
+            "shapedirs": Ch(model.shapedirs.T.reshape(V, 3, -1)),
+            "posedirs": Ch(model.posedirs.T.reshape(V, 3, -1)),
+            "J_regressor": sp.csc_matrix(model.j_regressor.astype(np.float64)),
+            "J": Ch(np.zeros((5, 3))),
+            "weights": Ch(model.lbs_weights),
+            "f": model.faces.astype(np.uint32),
+            "kintree_table": np.array([[4294967295, 0, 1, 1, 1], [0, 1, 2, 3, 4]], dtype=np.uint32),
+            "bs_style": "lbs", "bs_type": "lrotmin",
+        }
+        path = str(tmp_path / "flame2023.pkl")
+        with open(path, "wb") as f:
+            pickle.dump(record, f, protocol=2)
+        record["kintree_table"] = np.array([[4294967295, 0, 1, 2, 2], [0, 1, 2, 3, 4]], dtype=np.uint32)
+        with open(str(tmp_path / "other.pkl"), "wb") as f:
+            pickle.dump(record, f, protocol=2)
+    finally:
+        del sys.modules["chumpy"], sys.modules["chumpy.ch"]
+    with pytest.raises(ModuleNotFoundError):     # what a plain pickle.load does here
+        pickle.load(open(path, "rb"), encoding="latin1")
+    got = flame_io.load_flame_model(path)
+    for k in ("v_template", "faces", "shapedirs", "posedirs", "j_regressor", "lbs_weights", "parents"):
+        a, b = getattr(got, k), getattr(model, k)
+        assert a.dtype == b.dtype and a.flags["C_CONTIGUOUS"] and np.array_equal(a, b), k
+    with pytest.raises(ValueError, match="kinematic tree"):
+        flame_io.load_flame_model(str(tmp_path / "other.pkl"))
+    # model_path/flame_model.pkl is picked up by the drop-in's model search
+    os.makedirs(tmp_path / "m")
+    os.replace(path, tmp_path / "m" / "flame_model.pkl")
+    assert rs._find_flame_model(str(tmp_path / "m")).endswith("flame_model.pkl")
