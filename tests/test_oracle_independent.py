@@ -1,0 +1,209 @@
+"""A second opinion on the oracle's upstream rows (U1-U6), for which the reference holds no golden vector.
+
+`oracle/omfs_oracle.c` restates the published algorithms in float32 C.  This module restates the SAME published
+formulas a second time — vectorised numpy, float64, written from the papers' equations (FLAME / SMPL linear blend
+skinning; GaussianAvatars' triangle-local Gaussians; the 3DGS EWA projection) and not from the C source — and checks
+that the two agree to float32 rounding: a transposed matrix, a wrong joint order or a swapped quaternion component
+in the oracle would show up here as an O(1) difference, not as 1e-6.
+"""
+import numpy as np
+import pytest
+
+import oracle
+
+
+def _rodrigues(r):
+    """[...,3] axis-angle -> [...,3,3]; the SMPL-family form: angle = |r + 1e-8|, axis = r / angle."""
+    r = np.asarray(r, np.float64)
+    angle = np.linalg.norm(r + 1e-8, axis=-1, keepdims=True)
+    k = r / angle
+    c, s = np.cos(angle)[..., None], np.sin(angle)[..., None]
+    K = np.zeros(r.shape[:-1] + (3, 3))
+    K[..., 0, 1], K[..., 0, 2] = -k[..., 2], k[..., 1]
+    K[..., 1, 0], K[..., 1, 2] = k[..., 2], -k[..., 0]
+    K[..., 2, 0], K[..., 2, 1] = -k[..., 1], k[..., 0]
+    return np.eye(3) + s * K + (1.0 - c) * (K @ K)
+
+
+def flame_lbs_f64(model, params):
+    """FLAME forward as published: blendshapes, personal offsets, pose correctives, joint regression, the
+    kinematic chain root -> neck -> {jaw, eye, eye}, linear blend skinning, global translation."""
+    f8 = lambda a: np.asarray(a, np.float64)
+    T, V = params.expr.shape[0], model.v_template.shape[0]
+    n_expr = params.expr.shape[1]
+    dirs = f8(model.shapedirs).reshape(-1, V, 3)                       # [400, V, 3]
+    v = f8(model.v_template)[None] + np.einsum("k,kvc->vc", f8(params.shape), dirs[:300])[None] \
+        + np.einsum("tk,kvc->tvc", f8(params.expr), dirs[300:300 + n_expr])
+    v = v + f8(params.static_offset).reshape(1, V, 3) + f8(params.dynamic_offset).reshape(T, V, 3)
+    J = np.einsum("jv,tvc->tjc", f8(model.j_regressor), v)             # [T,5,3] from the un-posed, offset mesh
+    pose = np.concatenate([f8(params.rotation), f8(params.neck_pose), f8(params.jaw_pose), f8(params.eyes_pose)],
+                          axis=1).reshape(T, 5, 3)
+    R = _rodrigues(pose)                                               # [T,5,3,3]
+    feat = (R[:, 1:] - np.eye(3)).reshape(T, 36)
+    v_posed = v + (feat @ f8(model.posedirs)).reshape(T, V, 3)
+    parents = [-1, 0, 1, 1, 1]
+    G = np.zeros((T, 5, 4, 4))
+    for j in range(5):
+        local = np.zeros((T, 4, 4))
+        local[:, :3, :3] = R[:, j]
+        local[:, :3, 3] = J[:, j] - (J[:, parents[j]] if j else 0.0)
+        local[:, 3, 3] = 1.0
+        G[:, j] = local if j == 0 else G[:, parents[j]] @ local
+    A = G.copy()                                                       # remove the rest pose: x -> G (x - J)
+    A[:, :, :3, 3] -= np.einsum("tjab,tjb->tja", G[:, :, :3, :3], J)
+    Tv = np.einsum("vj,tjab->tvab", f8(model.lbs_weights), A)
+    out = np.einsum("tvab,tvb->tva", Tv[..., :3, :3], v_posed) + Tv[..., :3, 3]
+    return out + f8(params.translation)[:, None, :], J
+
+
+def face_frames_f64(verts, faces):
+    """Triangle frames of GaussianAvatars: centre, orthonormal (a0, a1, a2) as COLUMNS, isotropic scale."""
+    p0, p1, p2 = (np.asarray(verts, np.float64)[:, faces[:, k]] for k in range(3))
+    nrm = lambda a: a / np.linalg.norm(a, axis=-1, keepdims=True)
+    a0 = nrm(p1 - p0)
+    a1 = nrm(np.cross(a0, p2 - p0))
+    a2 = -nrm(np.cross(a1, a0))
+    scale = 0.5 * (np.linalg.norm(p1 - p0, axis=-1) + np.abs(np.sum(a2 * (p2 - p0), axis=-1)))
+    return (p0 + p1 + p2) / 3.0, np.stack([a0, a1, a2], axis=-1), scale
+
+
+def _quat_to_mat(q):
+    w, x, y, z = (q[..., k] for k in range(4))
+    return np.stack([
+        np.stack([1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)], -1),
+        np.stack([2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)], -1),
+        np.stack([2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)], -1)], -2)
+
+
+def _sh_deg3(d, sh):
+    """Real spherical harmonics up to degree 3 with the 3DGS sign conventions; sh [N,16,3], d [N,3] unit."""
+    x, y, z = d[:, 0:1], d[:, 1:2], d[:, 2:3]
+    xx, yy, zz, xy, yz, xz = x * x, y * y, z * z, x * y, y * z, x * z
+    C1 = 0.4886025119029199
+    C2 = (1.0925484305920792, -1.0925484305920792, 0.31539156525252005, -1.0925484305920792, 0.5462742152960396)
+    C3 = (-0.5900435899266435, 2.890611442640554, -0.4570457994644658, 0.3731763325901154, -0.4570457994644658,
+          1.445305721320277, -0.5900435899266435)
+    basis = [0.28209479177387814 + 0 * x, -C1 * y, C1 * z, -C1 * x,
+             C2[0] * xy, C2[1] * yz, C2[2] * (2 * zz - xx - yy), C2[3] * xz, C2[4] * (xx - yy),
+             C3[0] * y * (3 * xx - yy), C3[1] * xy * z, C3[2] * y * (4 * zz - xx - yy),
+             C3[3] * z * (2 * zz - 3 * xx - 3 * yy), C3[4] * x * (4 * zz - xx - yy), C3[5] * z * (xx - yy),
+             C3[6] * x * (xx - 3 * yy)]
+    return sum(b * sh[:, k, :] for k, b in enumerate(basis))
+
+
+def splat_f64(centre, frame, fscale, av, cam, W, H):
+    """GaussianAvatars binding followed by the 3DGS preprocess (cull, EWA projection, conic, radius, SH colour)."""
+    f8 = lambda a: np.asarray(a, np.float64)
+    b = av.binding
+    Rf, sf, cf = frame[b], fscale[b][:, None], centre[b]
+    mu = np.einsum("nab,nb->na", Rf, f8(av.xyz)) * sf + cf
+    s = np.exp(f8(av.scaling)) * sf
+    ql = f8(av.rotation) / np.linalg.norm(f8(av.rotation), axis=1, keepdims=True)
+    Rg = Rf @ _quat_to_mat(ql)                                          # q_face (x) q_local, as matrices
+    cov3 = np.einsum("nab,nb,ncb->nac", Rg, s * s, Rg)
+    view = f8(cam.viewmatrix).reshape(4, 4).T                           # stored column-major
+    proj = f8(cam.projmatrix).reshape(4, 4).T
+    t = mu @ view[:3, :3].T + view[:3, 3]
+    hom = np.concatenate([mu, np.ones((len(mu), 1))], 1) @ proj.T
+    ndc = hom[:, :2] / (hom[:, 3:4] + 1e-7)
+    fx, fy = W / (2.0 * cam.tanfovx), H / (2.0 * cam.tanfovy)
+    tz = t[:, 2]
+    tx = np.clip(t[:, 0] / tz, -1.3 * cam.tanfovx, 1.3 * cam.tanfovx) * tz
+    ty = np.clip(t[:, 1] / tz, -1.3 * cam.tanfovy, 1.3 * cam.tanfovy) * tz
+    Jm = np.zeros((len(mu), 2, 3))
+    Jm[:, 0, 0], Jm[:, 0, 2] = fx / tz, -fx * tx / (tz * tz)
+    Jm[:, 1, 1], Jm[:, 1, 2] = fy / tz, -fy * ty / (tz * tz)
+    M = Jm @ view[:3, :3]
+    cov2 = M @ cov3 @ np.transpose(M, (0, 2, 1))
+    A, B, C = cov2[:, 0, 0] + 0.3, cov2[:, 0, 1], cov2[:, 1, 1] + 0.3
+    det = A * C - B * B
+    conic = np.stack([C / det, -B / det, A / det], 1)
+    mid = 0.5 * (A + C)
+    lam = mid + np.sqrt(np.maximum(0.1, mid * mid - det))
+    radius = np.ceil(3.0 * np.sqrt(lam))
+    px = ((ndc[:, 0] + 1.0) * W - 1.0) * 0.5
+    py = ((ndc[:, 1] + 1.0) * H - 1.0) * 0.5
+    d = mu - f8(cam.campos)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rgb = np.maximum(_sh_deg3(d, f8(av.sh)) + 0.5, 0.0)
+    opacity = 1.0 / (1.0 + np.exp(-f8(av.opacity)))
+    gx, gy = (W + 15) // 16, (H + 15) // 16
+    x0 = np.clip(np.floor((px - radius) / 16), 0, gx); x1 = np.clip(np.floor((px + radius + 15) / 16), 0, gx)
+    y0 = np.clip(np.floor((py - radius) / 16), 0, gy); y1 = np.clip(np.floor((py + radius + 15) / 16), 0, gy)
+    # (trunc == floor wherever it matters: negative quotients clamp to 0 either way)
+    tiles = (x1 - x0) * (y1 - y0)
+    visible = (tz > 0.2) & (tiles > 0)
+    return dict(mu=mu, px=px, py=py, depth=tz, conic=conic, radius=radius, rgb=rgb, opacity=opacity, tiles=tiles,
+                visible=visible, margin=np.abs(3.0 * np.sqrt(lam) - np.round(3.0 * np.sqrt(lam))))
+
+
+@pytest.fixture(scope="module")
+def scene():
+    import omfs_b200  # noqa: F401
+    from omfs_b200 import avatar, synthetic
+    model, params, av, cam = synthetic.make_scene(n_gauss=5000, n_frames=3, width=160, height=112, n_verts=1202,
+                                                  dynamic=True)
+    return model, params, av, avatar.bake(av), cam
+
+
+def test_flame_forward_agrees_with_float64_lbs(scene):
+    model, params, av, baked, cam = scene
+    assert np.any(params.dynamic_offset) and np.any(params.static_offset)
+    verts, joints = oracle.flame_forward(model, params, return_joints=True)
+    want, J = flame_lbs_f64(model, params)
+    assert np.abs(verts - want).max() < 2e-6          # metres; the head is ~0.2 m across
+    assert np.abs(joints - J).max() < 2e-6
+    # the articulation is really exercised: jaw and neck rotations move vertices by centimetres
+    still = flame_lbs_f64(model, type(params)(params.shape, params.expr, params.rotation * 0, params.neck_pose * 0,
+                                              params.jaw_pose * 0, params.eyes_pose * 0, params.translation,
+                                              params.static_offset, params.dynamic_offset))[0]
+    assert np.abs(still - want).max() > 5e-3
+
+
+def test_face_frames_agree_with_float64(scene):
+    model, params, av, baked, cam = scene
+    verts = oracle.flame_forward(model, params)
+    ff = oracle.face_frames(verts, model.faces)
+    centre, frame, scale = face_frames_f64(verts, model.faces)
+    assert np.abs(ff[..., 0:3] - centre).max() < 1e-6
+    assert np.abs(ff[..., 3] - scale).max() < 1e-6 * scale.max() + 1e-8
+    R = np.stack([ff[..., 8:11], ff[..., 12:15], ff[..., 16:19]], axis=-2)      # rows
+    assert np.abs(R - frame).max() < 2e-5
+    assert np.abs(np.linalg.det(frame) - 1.0).max() < 1e-9                       # right-handed, orthonormal
+    q = ff[..., 4:8].astype(np.float64)
+    assert np.abs(np.linalg.norm(q, axis=-1) - 1.0).max() < 1e-5
+    assert np.abs(_quat_to_mat(q) - frame).max() < 3e-5                          # wxyz, same rotation
+
+
+def test_bind_and_preprocess_agree_with_float64(scene):
+    model, params, av, baked, cam = scene
+    W, H = cam.width, cam.height
+    verts = oracle.flame_forward(model, params)
+    ff = oracle.face_frames(verts, model.faces)
+    pre = oracle.bind_preprocess(ff, baked, [cam.pack()] * 3, W, H)
+    log2e = 1.4426950408889634
+    for t in range(3):
+        centre, frame, scale = face_frames_f64(verts[t:t + 1], model.faces)
+        w = splat_f64(centre[0], frame[0], scale[0], av, cam, W, H)
+        got_vis = pre.tiles_touched[t] > 0
+        assert (got_vis != w["visible"]).mean() < 1e-3
+        m = got_vis & w["visible"]
+        assert m.sum() > 0.9 * len(m)
+        assert np.abs(pre.mu[t][m] - w["mu"][m]).max() < 1e-6
+        assert np.abs(pre.P0[t][m, 0] - w["px"][m]).max() < 2e-3 and np.abs(pre.P0[t][m, 1] - w["py"][m]).max() < 2e-3
+        assert np.abs(pre.P0[t][m, 2] - w["depth"][m]).max() < 1e-6
+        # conic, in the oracle's pre-scaled form: e = lo + ca dx^2 + cb dx dy + cc dy^2 (log2 units)
+        want = np.stack([-0.5 * log2e * w["conic"][:, 0], -log2e * w["conic"][:, 1], -0.5 * log2e * w["conic"][:, 2]], 1)
+        rel = np.abs(pre.P1[t][m, :3] - want[m]) / (np.abs(want[m]).max(axis=1, keepdims=True) + 1e-12)
+        assert rel.max() < 2e-3 and np.median(rel) < 1e-5
+        assert np.abs(np.exp2(pre.P1[t][m, 3].astype(np.float64)) - w["opacity"][m]).max() < 1e-6
+        assert np.abs(pre.P2[t][m, :3] - w["rgb"][m]).max() < 1e-5
+        # integer outputs: identical except where 3 sqrt(lambda) sits on an integer to within float32 rounding
+        safe = m & (w["margin"] > 1e-3)
+        assert np.array_equal(pre.radii[t][safe], w["radius"][safe].astype(np.int32))
+        near_edge = np.minimum(np.abs(((w["px"] - w["radius"]) / 16) % 1 - 0.5), np.abs(((w["py"] - w["radius"]) / 16) % 1 - 0.5))
+        near_edge = np.minimum(near_edge, np.minimum(np.abs(((w["px"] + w["radius"] + 15) / 16) % 1 - 0.5),
+                                                     np.abs(((w["py"] + w["radius"] + 15) / 16) % 1 - 0.5)))
+        safe &= near_edge < 0.499                                               # rectangle corners not on a tile line
+        assert safe.sum() > 0.9 * m.sum()
+        assert np.array_equal(pre.tiles_touched[t][safe], w["tiles"][safe].astype(np.uint32))
