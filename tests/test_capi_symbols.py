@@ -96,3 +96,38 @@ def test_ctypes_structs_match_the_header_layout(tmp_path):
         nums = [int(x) for x in line.split()[1:]]
         assert nums[0] == ctypes.sizeof(cls), cname
         assert nums[1:] == [getattr(cls, f[0]).offset for f in cls._fields_], cname
+
+
+def test_the_product_never_touches_the_oracle():
+    """oracle/ is the checker: nothing in the product package or its C/CUDA sources imports, loads or links it, and
+    bench.py reaches it only inside its two CPU-baseline functions."""
+    import ast
+    import glob
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "omfs-4d-video-gen_b200")
+
+    def oracle_imports(path):
+        hits = []
+        for node in ast.walk(ast.parse(open(path).read())):
+            names = []
+            if isinstance(node, ast.Import):
+                names = [a.name for a in node.names]
+            elif isinstance(node, ast.ImportFrom):
+                names = [node.module or ""]
+            elif isinstance(node, ast.Constant) and isinstance(node.value, str) and "liboracle" in node.value:
+                names = ["oracle"]
+            hits += [(node.lineno, n) for n in names if n.split(".")[0] == "oracle"]
+        return hits
+
+    for path in glob.glob(os.path.join(pkg, "*.py")) + [os.path.join(root, "omfs_b200.py")]:
+        assert oracle_imports(path) == [], path
+    for path in glob.glob(os.path.join(pkg, "csrc", "*")) + glob.glob(os.path.join(root, "include", "*")):
+        text = open(path).read()
+        assert "omfs_oracle" not in text and "liboracle" not in text and "orc_" not in text, path
+    # bench.py: the imports sit inside cpu_oracle_fps / run_reference (the cpu_baseline leg and --impl reference) only
+    tree = ast.parse(open(os.path.join(root, "bench.py")).read())
+    allowed = set()
+    for fn in [n for n in ast.walk(tree) if isinstance(n, ast.FunctionDef) and n.name in ("cpu_oracle_fps", "run_reference")]:
+        allowed |= {n.lineno for n in ast.walk(fn) if isinstance(n, (ast.Import, ast.ImportFrom))}
+    lines = {ln for ln, _ in oracle_imports(os.path.join(root, "bench.py"))}
+    assert lines and lines <= allowed, (lines, allowed)
