@@ -167,9 +167,38 @@ def _find_flame_model(model_path: str) -> str:
     raise FileNotFoundError(f"FLAME model not found: set ${FLAME_MODEL_ENV} or put flame_model.npz in {model_path}")
 
 
+def encode_png(rgb_u8: np.ndarray) -> bytes:
+    """uint8 [H,W,3] -> the bytes of an 8-bit RGB PNG (lossless, any decoder).
+
+    Written for the frame sink, where the encode is what the caller waits for once the frames come off the GPU in
+    milliseconds: every row uses the Up filter (one vectorised subtraction for the whole image; rendered frames are
+    smooth vertically and have a flat background) and the stream is deflated at level 1 with zlib's run-length
+    strategy.  On the 512x512 bench frames that is 7 ms and 135 KB per frame against 29 ms and 148 KB for PIL at
+    compress_level=1, which tries all five filters per row (both release the GIL, so the thread pool scales)."""
+    import struct
+    import zlib
+    img = np.ascontiguousarray(rgb_u8, dtype=np.uint8)
+    if img.ndim != 3 or img.shape[2] != 3 or img.shape[0] == 0 or img.shape[1] == 0:
+        raise ValueError(f"expected a non-empty uint8 [H,W,3] frame, got {img.shape}")
+    h, w, _ = img.shape
+    flat = img.reshape(h, w * 3)
+    raw = np.empty((h, 1 + w * 3), np.uint8)
+    raw[:, 0] = 2                                   # filter type Up (the row above the first one is all zeros)
+    raw[0, 1:] = flat[0]
+    np.subtract(flat[1:], flat[:-1], out=raw[1:, 1:])  # modulo 256, as the format specifies
+    z = zlib.compressobj(1, zlib.DEFLATED, 15, 9, zlib.Z_RLE)
+    idat = z.compress(raw.tobytes()) + z.flush()
+
+    def chunk(tag: bytes, data: bytes) -> bytes:
+        return struct.pack(">I", len(data)) + tag + data + struct.pack(">I", zlib.crc32(data, zlib.crc32(tag)))
+
+    return (b"\x89PNG\r\n\x1a\n" + chunk(b"IHDR", struct.pack(">IIBBBBB", w, h, 8, 2, 0, 0, 0)) +
+            chunk(b"IDAT", idat) + chunk(b"IEND", b""))
+
+
 def _write_png(path: str, rgb_u8: np.ndarray) -> None:
-    from PIL import Image
-    Image.fromarray(rgb_u8, mode="RGB").save(path, compress_level=1)
+    with open(path, "wb") as f:
+        f.write(encode_png(rgb_u8))
 
 
 def write_frames_png(renders_dir: str, frames_u8: np.ndarray, workers: int | None = None, first: int = 0) -> list[str]:

@@ -4,6 +4,7 @@ import json
 import os
 
 import numpy as np
+import pytest
 from hypothesis import given, settings, strategies as st
 
 import omfs_b200  # noqa: F401
@@ -91,3 +92,39 @@ def test_report_metrics_from_moments(h, w, seed):
     af, bf = a[1].astype(np.float32), b[1].astype(np.float32)
     assert abs(p[1] - rr.psnr(af, bf)) <= 1e-4
     assert abs(s[1] - rr.ssim_global(af, bf)) <= 1e-9
+
+
+@settings(max_examples=40, deadline=None)
+@given(st.integers(1, 40), st.integers(1, 40), st.integers(0, 2**31 - 1), st.sampled_from(["noise", "flat", "ramp"]))
+def test_png_encoder_round_trips_through_independent_decoders(h, w, seed, kind):
+    """render_surgery.encode_png (the frame sink's own encoder: Up filter + run-length deflate) writes standard PNGs:
+    PIL and OpenCV decode every size and content back to the same pixels, and the header says 8-bit RGB."""
+    import io
+    import struct
+    from PIL import Image
+    from omfs_b200 import render_surgery as rs
+    rng = np.random.default_rng(seed)
+    if kind == "noise":
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    elif kind == "flat":
+        img = np.full((h, w, 3), rng.integers(0, 256), dtype=np.uint8)
+    else:
+        img = ((np.arange(h)[:, None, None] * 7 + np.arange(w)[None, :, None] * 3 + np.arange(3)) % 256).astype(np.uint8)
+    data = rs.encode_png(img)
+    assert data[:8] == b"\x89PNG\r\n\x1a\n" and data[12:16] == b"IHDR"
+    assert struct.unpack(">IIBBBBB", data[16:29]) == (w, h, 8, 2, 0, 0, 0)
+    pil = Image.open(io.BytesIO(data))
+    pil.verify()                                                   # chunk CRCs
+    assert np.array_equal(np.asarray(Image.open(io.BytesIO(data))), img)
+    try:
+        import cv2
+    except ImportError:
+        return
+    assert np.array_equal(cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_COLOR)[..., ::-1], img)
+
+
+def test_png_encoder_rejects_other_layouts():
+    from omfs_b200 import render_surgery as rs
+    for bad in (np.zeros((4, 4), np.uint8), np.zeros((4, 4, 4), np.uint8), np.zeros((0, 4, 3), np.uint8)):
+        with pytest.raises(ValueError):
+            rs.encode_png(bad)
