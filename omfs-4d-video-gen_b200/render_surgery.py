@@ -31,6 +31,7 @@ from .synthetic import FrameParams
 SCALE_FACTOR = 0.001  # mm -> FLAME units (reference :35)
 FLAME_MODEL_ENV = "OMFS_FLAME_MODEL"
 BATCH_ENV = "OMFS_RENDER_BATCH"
+MATERIALISE_ENV = "OMFS_MATERIALISE_DATASET"  # "1": main() writes the edited dataset copy, as the reference does
 
 
 # ----------------------------------------------------------------------------- R1 (reference :40-42)
@@ -231,13 +232,16 @@ def _agree(agree, error: BaseException | None, what: str):
 
 
 def _render_dataset(model_path: str, data_dir: str, iteration: int = -1,
-                    clear_old_renders: bool = True) -> tuple[str, np.ndarray]:
+                    clear_old_renders: bool = True, edit=None) -> tuple[str, np.ndarray]:
     """render_with_gaussians, also returning the frames it wrote (uint8 [T,H,W,3]) so that main() can hand them
     to the encoder without reading the PNGs back.
 
     Under torchrun (WORLD_SIZE > 1, one process per GPU) every rank renders the contiguous frame
     block `sharding.frame_block` gives it on its own GPU and writes its own PNGs; rank 0 alone purges stale
-    renders first.  No frame crosses ranks; the returned array is then the rank's block only."""
+    renders first.  No frame crosses ranks; the returned array is then the rank's block only.
+
+    `edit`, if given, maps the dataset's FrameParams to the ones to render (main()'s in-memory form of the
+    reference's modified dataset)."""
     from . import sharding
     rank, world, agree = sharding.host_ranks()
     train_dir = os.path.join(model_path, "train")
@@ -267,6 +271,8 @@ def _render_dataset(model_path: str, data_dir: str, iteration: int = -1,
         if not frames:
             raise FileNotFoundError("No rendered frames found after GaussianAvatars rendering.")
         params = flame_io.load_dataset_params(data_dir, frames, model.n_verts)
+        if edit is not None:
+            params = edit(params)
         av = flame_io.load_avatar_ply(ply)
         if int(av.binding.max()) >= model.n_faces:
             raise ValueError("avatar binding index exceeds the FLAME face count")
@@ -412,7 +418,8 @@ def stitch_video_frames(frames_u8: np.ndarray, output_path: str, fps: int = 30):
     _, h, w, _ = frames_u8.shape
     cmd = [ffmpeg_bin, "-y", "-f", "rawvideo", "-pix_fmt", "rgb24", "-s", f"{w}x{h}", "-framerate", str(fps),
            "-i", "-", "-c:v", "libx264", "-pix_fmt", "yuv420p", "-preset", "medium", "-crf", "18", output_path]
-    result = subprocess.run(cmd, input=frames_u8.tobytes(), capture_output=True)
+    # a flat byte view, not .tobytes(): a 300-frame 512x512 clip is 236 MB that need not be copied before the pipe
+    result = subprocess.run(cmd, input=memoryview(frames_u8.reshape(-1)), capture_output=True)
     if result.returncode != 0:
         raise RuntimeError(f"ffmpeg failed:\n{result.stderr.decode(errors='replace')}")
     print(f"[render_surgery] Video saved to {output_path}")
@@ -449,10 +456,21 @@ def main(argv: list[str] | None = None):
     print(f"[render_surgery] Rig mode: {mode} ({reason})")
     from . import sharding
     rank, world, _ = sharding.host_ranks()
-    # under torchrun every rank edits its own temporary copy (the edit is cheap and keeps the ranks independent)
-    modified_dir = create_modified_dataset(args.data_dir, lefort_offset, bsso_offset, deformation_map=deformation_map)
+    # The reference materialises an edited copy of the dataset (T+1 npz round trips), renders it and deletes it
+    # (:503-539).  The same edit applied in memory to the parameters read from the caller's dataset gives the same
+    # frames without the copy; OMFS_MATERIALISE_DATASET=1 keeps the on-disk route.
+    materialise = os.environ.get(MATERIALISE_ENV, "0") == "1"
+    modified_dir = None
     try:
-        frames_dir, frames_u8 = _render_dataset(args.model_path, modified_dir, iteration=args.iteration)
+        if materialise:
+            modified_dir = create_modified_dataset(args.data_dir, lefort_offset, bsso_offset,
+                                                   deformation_map=deformation_map)
+            frames_dir, frames_u8 = _render_dataset(args.model_path, modified_dir, iteration=args.iteration)
+        else:
+            def edit(params: FrameParams) -> FrameParams:
+                rec = _edit_record(params.as_dict(), lefort_offset, bsso_offset, deformation_map)
+                return FrameParams.from_dict(rec, n_verts=params.static_offset.shape[1])
+            frames_dir, frames_u8 = _render_dataset(args.model_path, args.data_dir, iteration=args.iteration, edit=edit)
         if rank == 0:
             if args.export_frames_dir:
                 export_deterministic_frames(frames_dir, args.export_frames_dir,
@@ -465,7 +483,8 @@ def main(argv: list[str] | None = None):
             else:
                 stitch_video(frames_dir, args.output, fps=args.fps)  # the other ranks' frames are on disk
     finally:
-        shutil.rmtree(modified_dir, ignore_errors=True)
+        if modified_dir is not None:
+            shutil.rmtree(modified_dir, ignore_errors=True)
     print("[render_surgery] Done.")
 
 

@@ -60,9 +60,10 @@ def test_render_with_gaussians_from_disk_matches_oracle(tmp_path):
 
 
 def test_main_cli_flow(tmp_path, monkeypatch):
-    """render_surgery.main with the reference's flags: modified dataset -> in-process render -> PNGs in the upstream
+    """render_surgery.main with the reference's flags: parameter edit (in memory by default, through the reference's
+    temporary dataset copy with OMFS_MATERIALISE_DATASET=1: same frames) -> in-process render -> PNGs in the upstream
     layout -> deterministic export -> encoder.  A stand-in ffmpeg records the raw frames it is handed: they are the
-    frames of the PNGs, in order; the temporary dataset is removed afterwards."""
+    frames of the PNGs, in order; the temporary dataset, when written, is removed afterwards."""
     from PIL import Image
     from omfs_b200 import render_surgery as rs
     data, mdl, model, params, av, cam = _dataset(tmp_path, T=4)
@@ -86,7 +87,15 @@ def test_main_cli_flow(tmp_path, monkeypatch):
     args = (tmp_path / "args.txt").read_text().split("\n")
     assert args[args.index("-framerate") + 1] == "24" and args[args.index("-s") + 1] == f"{cam.width}x{cam.height}"
     assert json.load(open(tmp_path / "ab" / "deterministic_indices_manifest.json"))["selected_indices"] == [0, 3]
+    assert made == []                                       # the plan was applied in memory: no dataset copy written
+    # the reference's on-disk route (edited copy written, rendered, deleted: :503-539) renders the same frames
+    monkeypatch.setenv("OMFS_MATERIALISE_DATASET", "1")
+    rs.main(["--lefort_mm", "5", "--bsso_mm", "-3", "--sensitivity", "1.5", "--model_path", mdl, "--data_dir", data,
+             "--output", str(out), "--fps", "24"])
+    monkeypatch.delenv("OMFS_MATERIALISE_DATASET")
     assert made and not os.path.exists(made[0])            # the caller's temporary dataset is cleaned up (:537-539)
+    again = np.stack([np.asarray(Image.open(os.path.join(renders, n))) for n in sorted(os.listdir(renders))])
+    assert np.array_equal(again, frames)
     # the plan moved the face: frames differ from a zero-offset render of the same dataset
     zero = rs.render_surgery_frames(model, params, av, [cam] * 4, 0.0, 0.0)
     assert not np.array_equal(zero, frames)

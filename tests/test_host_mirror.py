@@ -329,7 +329,16 @@ def test_main_flow_with_a_stand_in_renderer(tmp_path, monkeypatch):
     args = (tmp_path / "args.txt").read_text().split("\n")
     assert args[args.index("-framerate") + 1] == "24" and args[args.index("-s") + 1] == f"{W}x{H}"
     assert json.load(open(tmp_path / "ab" / "deterministic_indices_manifest.json"))["selected_indices"] == [0, n_train - 1]
-    assert made and not os.path.exists(made[0])
+    assert made == []                                       # the edit happened in memory: no dataset copy was written
+    in_memory = {k: v.copy() for k, v in seen.items()}
+    # the reference's on-disk route (edited copy written, rendered, deleted) hands the renderer the same bits
+    monkeypatch.setenv("OMFS_MATERIALISE_DATASET", "1")
+    rs.main(["--lefort_mm", "5", "--bsso_mm", "-3", "--sensitivity", "2", "--model_path", mdl, "--data_dir", data,
+             "--output", str(out)])
+    monkeypatch.delenv("OMFS_MATERIALISE_DATASET")
+    assert made and not os.path.exists(made[0])            # the temporary dataset is cleaned up (:537-539)
+    for k in in_memory:
+        assert np.array_equal(in_memory[k].view(np.uint32), seen[k].view(np.uint32)), k
 
     def broken(*a, **k):
         raise ValueError("device lost")
@@ -397,3 +406,22 @@ def test_flame_pickle_with_chumpy_arrays_loads_without_chumpy(tmp_path):
     os.makedirs(tmp_path / "m")
     os.replace(path, tmp_path / "m" / "flame_model.pkl")
     assert rs._find_flame_model(str(tmp_path / "m")).endswith("flame_model.pkl")
+
+
+def test_read_npz_equals_numpy_load(tmp_path):
+    """flame_io.read_npz (headers matched, not evaluated) returns what np.load returns — for the FLAME records
+    np.savez writes, and, through its fallback, for members it does not fast-path."""
+    import omfs_b200  # noqa: F401
+    from omfs_b200 import flame_io, synthetic
+    p = str(tmp_path / "rec.npz")
+    flame_io.save_flame_params(p, synthetic.make_frame_params(3, n_verts=162))
+    odd = str(tmp_path / "odd.npz")
+    np.savez_compressed(odd, x=np.arange(5), s=np.array("txt"), be=np.array([1, 2], dtype=">f4"),
+                        empty=np.zeros((0, 3), np.float32), scalar=np.float32(2.5), f=np.asfortranarray(np.ones((2, 3))))
+    for path in (p, odd):
+        got, want = flame_io.read_npz(path), dict(np.load(path))
+        assert set(got) == set(want)
+        for k in want:
+            assert got[k].shape == want[k].shape and np.array_equal(got[k], want[k]), (path, k)
+            assert got[k].dtype.newbyteorder("=") == want[k].dtype.newbyteorder("="), (path, k)
+    assert all(v.flags.writeable for v in flame_io.read_npz(p).values())
