@@ -60,8 +60,14 @@ def host_ranks():
     torch.distributed."""
     import os
     global _HOST_GROUP
+    import sys
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    if world <= 1:
+    # a launcher's full environment, or a group the caller already set up; a stray WORLD_SIZE alone is not a launch
+    # (and a plain process never pays for importing torch here)
+    launched = world > 1 and "RANK" in os.environ and "MASTER_PORT" in os.environ
+    dist = sys.modules.get("torch.distributed")
+    grouped = dist is not None and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+    if not launched and not grouped:
         return 0, 1, (lambda error=None: [error])
     import torch.distributed as dist
     if not dist.is_initialized():
