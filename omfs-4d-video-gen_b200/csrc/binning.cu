@@ -112,6 +112,19 @@ __global__ void __launch_bounds__(256) tile_count_kernel(int N, int width, int h
 // pair), the tile ranges (U9; untouched tiles stay (0,0)), the pair count and the overflow flag.
 // 8 counters per thread per round (8192 per round), so a 60-segment batch takes 8 rounds.
 constexpr int kTsItems = 8;
+__device__ __forceinline__ unsigned long long warp_incl_scan64(unsigned long long v) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long n = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d) v += n;
+    }
+    return v;
+}
+// The running total is carried in 64 bits: a close-up at 1024^2 (128 segments x 500k Gaussians x ~67 tiles)
+// sums past 2^32, and a wrapped 32-bit total would pass the capacity test below and let emit_scatter write
+// outside the value buffer.  Positions are truncated to 32 bits only when stored; they are meaningful only
+// when total <= capacity < 2^30, which is exactly when nothing was truncated.
 __global__ void __launch_bounds__(1024) tile_scan_kernel(int n_tiles_total, const uint32_t* __restrict__ cnt,
                                                          uint32_t* __restrict__ tile_start,
                                                          uint32_t* __restrict__ ranges,
@@ -120,8 +133,8 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(int n_tiles_total, cons
                                                          uint32_t* __restrict__ sort_count,
                                                          unsigned long long* __restrict__ pair_accum,
                                                          uint32_t* __restrict__ pair_max) {
-    __shared__ uint32_t s_warp[32];
-    __shared__ uint32_t s_carry;
+    __shared__ unsigned long long s_warp[32];
+    __shared__ unsigned long long s_carry;
     if (threadIdx.x == 0) s_carry = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -129,7 +142,7 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(int n_tiles_total, cons
         const int first = base + threadIdx.x * kTsItems;
         const bool full = first + kTsItems <= n_tiles_total;
         uint32_t v[kTsItems];
-        uint32_t acc = 0;
+        unsigned long long acc = 0;
         if (full) {
             // this CTA is alone on its SM: 16-byte accesses keep every request fully coalesced
             const uint4 a = *reinterpret_cast<const uint4*>(cnt + first);
@@ -142,22 +155,22 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(int n_tiles_total, cons
         }
 #pragma unroll
         for (int k = 0; k < kTsItems; k++) acc += v[k];
-        const uint32_t inc = warp_incl_scan(acc);
+        const unsigned long long inc = warp_incl_scan64(acc);
         if (lane == 31) s_warp[warp] = inc;
         __syncthreads();
         if (warp == 0) {
-            const uint32_t w = s_warp[lane];
-            const uint32_t winc = warp_incl_scan(w);
+            const unsigned long long w = s_warp[lane];
+            const unsigned long long winc = warp_incl_scan64(w);
             s_warp[lane] = winc - w;
         }
         __syncthreads();
-        uint32_t run = s_carry + s_warp[warp] + inc - acc;
+        unsigned long long run = s_carry + s_warp[warp] + inc - acc;
         uint32_t st[kTsItems], r0[kTsItems], r1[kTsItems];
 #pragma unroll
         for (int k = 0; k < kTsItems; k++) {
-            st[k] = run;
-            r0[k] = v[k] ? run : 0u;
-            r1[k] = v[k] ? run + v[k] : 0u;
+            st[k] = (uint32_t)run;
+            r0[k] = v[k] ? (uint32_t)run : 0u;
+            r1[k] = v[k] ? (uint32_t)(run + v[k]) : 0u;
             run += v[k];
         }
         if (full) {
@@ -180,11 +193,13 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(int n_tiles_total, cons
         if (threadIdx.x == 1023) s_carry = run;
         __syncthreads();
     }
-    const bool overflow = (unsigned long long)s_carry > capacity;
+    const unsigned long long total64 = s_carry;
+    const bool overflow = total64 > capacity;
     if (threadIdx.x == 0) {
-        const uint32_t total = s_carry;
+        // what the caller sees is saturated, never wrapped: the auto-grow retry then asks for "as much as allowed"
+        const uint32_t total = total64 > 0xffffffffull ? 0xffffffffu : (uint32_t)total64;
         *num_pairs = total;
-        if (pair_accum) *pair_accum += total;  // running total over the batches of one render call
+        if (pair_accum) *pair_accum += total64;  // running total over the batches of one render call
         if (pair_max && total > *pair_max) *pair_max = total;  // largest batch: what the capacity must hold
         if (overflow) {
             // flag it and emit nothing; the caller re-runs with more capacity
@@ -764,20 +779,13 @@ static BinningWs carve(void* base, int S, int N, int width, int height, size_t c
 }
 
 static int set_kernel_attrs(int tiles) {
-    static bool rs_set = false;
-    if (!rs_set) {
-        OMFS_CUDA(cudaFuncSetAttribute(rs_onesweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)sizeof(RsSmem)));
-        rs_set = true;
-    }
-    static int es_bytes = 0;
+    static DeviceOnce rs_once, es10_once, es12_once, es22_once;
+    int rc;
+    if ((rc = ensure_dyn_smem(rs_once, rs_onesweep_kernel, (int)sizeof(RsSmem)))) return rc;
     const int need = (int)emit_scatter_smem(tiles);
-    if (need > es_bytes) {
-        OMFS_CUDA(cudaFuncSetAttribute(emit_scatter_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, need));
-        OMFS_CUDA(cudaFuncSetAttribute(emit_scatter_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, need));
-        OMFS_CUDA(cudaFuncSetAttribute(emit_scatter_kernel<22>, cudaFuncAttributeMaxDynamicSharedMemorySize, need));
-        es_bytes = need;
-    }
+    if ((rc = ensure_dyn_smem(es10_once, emit_scatter_kernel<10>, need))) return rc;
+    if ((rc = ensure_dyn_smem(es12_once, emit_scatter_kernel<12>, need))) return rc;
+    if ((rc = ensure_dyn_smem(es22_once, emit_scatter_kernel<22>, need))) return rc;
     return OMFS_OK;
 }
 

@@ -204,6 +204,11 @@ struct omfs_session {
 
 enum Stage { kStFlame = 0, kStFaceFrames, kStBindPre, kStDepthSort, kStTileRanges, kStEmitScatter, kStComposite, kStCount };
 
+__global__ void tile_cams_kernel(const float* __restrict__ in, int n_in, int n_out, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_out) out[i] = in[i % n_in];
+}
+
 static int upload(DevBuf& b, const void* h, size_t bytes, cudaStream_t st) {
     int rc = b.ensure(bytes);
     if (rc) return rc;
@@ -255,6 +260,24 @@ extern "C" int omfs_session_create(const omfs_model_desc* m, const omfs_session_
                      m->xyzb && m->scale_lo && m->rot && m->sh,
                  "null model array");
     OMFS_REQUIRE(cfg->width > 0 && cfg->height > 0 && cfg->max_batch > 0 && cfg->max_batch <= 65535, "bad config");
+    // The kernels index device memory with these arrays (face_frames: verts[faces[..]], bind_preprocess:
+    // ff[binding]): an avatar or mesh from an untrusted file must be rejected here, not discovered as a fault.
+    for (long long i = 0; i < 3ll * m->n_faces; i++)
+        if (m->faces[i] < 0 || m->faces[i] >= m->n_verts) {
+            set_error("omfs_session_create: faces[%lld] = %d is not a vertex index (n_verts = %d)", i / 3,
+                      (int)m->faces[i], (int)m->n_verts);
+            return OMFS_ERR_INVALID;
+        }
+    for (long long n = 0; n < m->n_gauss; n++) {
+        int32_t b;
+        memcpy(&b, &m->xyzb[4 * n + 3], 4);  // binding index rides as raw bits
+        if (b < 0 || b >= m->n_faces) {
+            set_error("omfs_session_create: Gaussian %lld is bound to face %d, the mesh has %d faces (a GaussianAvatars "
+                      "PLY binds to the teeth-augmented FLAME mesh: load the matching model)",
+                      n, (int)b, (int)m->n_faces);
+            return OMFS_ERR_INVALID;
+        }
+    }
     int rc = omfs_device_check(cfg->device);
     if (rc) return rc;
     OMFS_CUDA(cudaSetDevice(cfg->device));
@@ -438,11 +461,15 @@ static int render_core(omfs_session* s, int T, int n_views, const float* p_expr,
             s->seg_table_fpb = fpb;
             s->seg_table_views = n_views;
         }
-        // cameras tiled per frame of the batch
+        // cameras tiled per frame of the batch: one launch (it was one device-to-device copy per frame of the
+        // batch — 60 copy-engine round trips in front of every call)
         if ((rc = s->cams.ensure(sizeof(float) * kCam * Sb))) return rc;
-        for (int f = 0; f < fpb; f++)
-            OMFS_CUDA(cudaMemcpyAsync(s->cams.as<float>() + (size_t)f * n_views * kCam, p_cams,
-                                      sizeof(float) * kCam * n_views, cudaMemcpyDeviceToDevice, st));
+        {
+            const int n_in = kCam * n_views, n_out = n_in * fpb;
+            tile_cams_kernel<<<ceil_div(n_out, 256), 256, 0, st>>>(p_cams, n_in, n_out, s->cams.as<float>());
+            count_launch();
+            OMFS_LAUNCH_CHECK();
+        }
     }
     uint32_t* d_num_pairs = s->counters.as<uint32_t>();
     int* d_flag = s->counters.as<int>() + 1;

@@ -4,6 +4,8 @@
 #include <stdint.h>
 #include <stdio.h>
 
+#include <mutex>
+
 #include "../../include/omfs_b200.h"
 
 #if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
@@ -37,6 +39,27 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
     } while (0)
 
 inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is a PER-DEVICE setting: a process that opens sessions on two
+// GPUs must set it on both, and two host threads may get here at once.  One DeviceOnce per kernel (or kernel
+// family) remembers what has been granted on each device.
+constexpr int kMaxDevices = 64;
+struct DeviceOnce {
+    std::mutex mu;
+    int granted[kMaxDevices] = {0};
+};
+template <typename F>
+inline int ensure_dyn_smem(DeviceOnce& once, F* func, int bytes) {
+    int dev = 0;
+    OMFS_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> guard(once.mu);
+    const bool tracked = dev >= 0 && dev < kMaxDevices;
+    if (!tracked || once.granted[dev] < bytes) {
+        OMFS_CUDA(cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes));
+        if (tracked) once.granted[dev] = bytes;
+    }
+    return OMFS_OK;
+}
 
 // launch counter (gpu_launches in bench.py is read from here)
 extern unsigned long long g_launches;

@@ -409,24 +409,16 @@ int launch_blend_gemm_tc(int T, int kpad, int npad, const float* d_acoef, const 
         if ((rc = make_map(&al, d_acoef + 2 * kpad, (uint64_t)T, (uint64_t)kpad, (uint64_t)K3, BKP, BM))) return rc;
         if ((rc = make_map(&bh, d_bt, (uint64_t)npad, (uint64_t)kpad, (uint64_t)K3, BKP, BN))) return rc;
         if ((rc = make_map(&bl, d_bt + kpad, (uint64_t)npad, (uint64_t)kpad, (uint64_t)K3, BKP, BN))) return rc;
-        static bool attr_p = false;
-        if (!attr_p) {
-            OMFS_CUDA(cudaFuncSetAttribute(flame_blend_tc_panels_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)kGemmSmemP));
-            attr_p = true;
-        }
+        static DeviceOnce once_p;
+        if ((rc = ensure_dyn_smem(once_p, flame_blend_tc_panels_kernel, (int)kGemmSmemP))) return rc;
         flame_blend_tc_panels_kernel<<<grid, kGemmThreads, kGemmSmemP, stream>>>(ah, al, bh, bl, T, kpad, npad, d_base,
                                                                                  d_vp);
     } else {
         CUtensorMap map_a, map_b;
         if ((rc = make_map(&map_a, d_acoef, (uint64_t)T, (uint64_t)K3, (uint64_t)K3, BK, BM))) return rc;
         if ((rc = make_map(&map_b, d_bt, (uint64_t)npad, (uint64_t)K3, (uint64_t)K3, BK, BN))) return rc;
-        static bool attr_set = false;
-        if (!attr_set) {
-            OMFS_CUDA(cudaFuncSetAttribute(flame_blend_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)kGemmSmem));
-            attr_set = true;
-        }
+        static DeviceOnce once_s;
+        if ((rc = ensure_dyn_smem(once_s, flame_blend_tc_kernel, (int)kGemmSmem))) return rc;
         flame_blend_tc_kernel<<<grid, kGemmThreads, kGemmSmem, stream>>>(map_a, map_b, T, K3, npad, d_base, d_vp);
     }
     count_launch();

@@ -206,6 +206,30 @@ def load_flame_model(path: str) -> FlameModel:
         j_regressor=np.ascontiguousarray(jr), lbs_weights=np.asarray(d["weights"], np.float32), parents=parents)
 
 
+def check_subject_matches_model(model: FlameModel, params: "FrameParams", avatar) -> None:
+    """The three inputs of a render must describe ONE mesh.  The reference's records and a GaussianAvatars
+    checkpoint are written for the 5143-vertex FLAME-with-teeth mesh (static_offset (1,5143,3), dynamic_offset
+    (T,5143,3): flame_fitter.py:439, preprocess_video.py:329); the licence-gated flame2023.pkl holds the raw
+    5023-vertex mesh.  Upstream grafts the teeth on at load time from its own mask asset, which is not
+    redistributable and not under the reference tree, so the augmented model has to be exported once
+    (tools/export_flame_with_teeth.py, run inside the upstream checkout) — a mismatch is named here instead of
+    surfacing as an out-of-range binding or a failed size check deep in the session."""
+    rec_v = int(params.static_offset.shape[1])
+    problems = []
+    if rec_v != model.n_verts:
+        problems.append(f"the FLAME records cover {rec_v} vertices, the model has {model.n_verts}")
+    if avatar.n and (int(avatar.binding.max()) >= model.n_faces or int(avatar.binding.min()) < 0):
+        problems.append(f"the avatar binds Gaussians to faces {int(avatar.binding.min())}..{int(avatar.binding.max())}, "
+                        f"the model has {model.n_faces} faces")
+    if problems:
+        hint = ""
+        if model.n_verts == 5023:
+            hint = (" — this is the raw FLAME mesh; records and checkpoints of the reference pipeline use the "
+                    "5143-vertex FLAME-with-teeth mesh: export it with tools/export_flame_with_teeth.py and point "
+                    "$OMFS_FLAME_MODEL at the resulting flame_model.npz")
+        raise ValueError("FLAME model does not match the dataset/checkpoint: " + "; ".join(problems) + hint)
+
+
 # --------------------------------------------------------------------------------------- parameters
 PARAM_KEYS = ("shape", "expr", "rotation", "neck_pose", "jaw_pose", "eyes_pose", "translation",
               "static_offset", "dynamic_offset")

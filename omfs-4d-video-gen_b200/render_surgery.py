@@ -220,6 +220,53 @@ def write_frames_png(renders_dir: str, frames_u8: np.ndarray, workers: int | Non
     return paths
 
 
+def write_gt_frames(gt_dir: str, data_dir: str, frames, first: int = 0, bg=(255, 255, 255)) -> list[str]:
+    """The sibling `gt/%05d.png` folder of a render (upstream render.py saves the ground-truth image of every view
+    beside its render; the validation report pairs the two folders by name, validation_reporting.py:60-63, 121-123).
+    Each frame's dataset image (`file_path` of transforms_train.json) becomes gt/<index>.png: an 8-bit RGB PNG of the
+    render size is copied byte for byte, anything else is decoded, flattened onto the white background the pipeline
+    trains with (train_ghost.py:239-241), resized to the render size and re-encoded losslessly.  A dataset without
+    images (a parameters-only test fixture) leaves the folder empty and says so once."""
+    os.makedirs(gt_dir, exist_ok=True)
+    written, missing = [], 0
+    for i, fr in enumerate(frames):
+        src = os.path.join(data_dir, fr.file_path)
+        if not os.path.exists(src) and os.path.exists(src + ".png"):
+            src += ".png"  # transforms may carry extension-less paths
+        if not os.path.exists(src):
+            missing += 1
+            continue
+        dst = os.path.join(gt_dir, f"{first + i:05d}.png")
+        w, h = fr.camera.width, fr.camera.height
+        copied = False
+        if src.lower().endswith(".png"):
+            with open(src, "rb") as f:
+                head = f.read(26)
+            # signature + IHDR: width, height, bit depth 8, colour type 2 (RGB)
+            if head[:8] == b"\x89PNG\r\n\x1a\n" and head[12:16] == b"IHDR" and \
+                    int.from_bytes(head[16:20], "big") == w and int.from_bytes(head[20:24], "big") == h and \
+                    head[24] == 8 and head[25] == 2:
+                shutil.copyfile(src, dst)
+                copied = True
+        if not copied:
+            from PIL import Image
+            im = Image.open(src)
+            if im.mode in ("RGBA", "LA", "P"):
+                rgba = im.convert("RGBA")
+                flat = Image.new("RGBA", rgba.size, tuple(bg) + (255,))
+                flat.alpha_composite(rgba)
+                im = flat
+            im = im.convert("RGB")
+            if im.size != (w, h):
+                im = im.resize((w, h), Image.BILINEAR)
+            _write_png(dst, np.asarray(im))
+        written.append(dst)
+    if missing:
+        print(f"[render_surgery] {missing} of {len(frames)} dataset images not found under {data_dir}: "
+              f"their gt/ frames were not written")
+    return written
+
+
 def _agree(agree, error: BaseException | None, what: str):
     """Meet the other ranks; if any of them failed, every rank raises (the first failure, as RuntimeError on the
     ranks that did not fail themselves)."""
@@ -249,10 +296,12 @@ def _render_dataset(model_path: str, data_dir: str, iteration: int = -1,
     try:
         if rank == 0 and clear_old_renders and os.path.isdir(train_dir):  # stale frames must never be picked up (:260-267)
             for d in os.listdir(train_dir):
-                renders = os.path.join(train_dir, d, "renders")
-                if os.path.isdir(renders):
-                    print(f"[render_surgery] Clearing old renders: {renders}")
-                    shutil.rmtree(renders)
+                # gt/ goes with renders/: a stale gt/ of an older run must never be scored against new frames
+                for sub in ("renders", "gt"):
+                    old = os.path.join(train_dir, d, sub)
+                    if os.path.isdir(old):
+                        print(f"[render_surgery] Clearing old {sub}: {old}")
+                        shutil.rmtree(old)
     except Exception as e:
         err = e
     if world > 1:
@@ -274,8 +323,7 @@ def _render_dataset(model_path: str, data_dir: str, iteration: int = -1,
         if edit is not None:
             params = edit(params)
         av = flame_io.load_avatar_ply(ply)
-        if int(av.binding.max()) >= model.n_faces:
-            raise ValueError("avatar binding index exceeds the FLAME face count")
+        flame_io.check_subject_matches_model(model, params, av)
         lo, hi = sharding.frame_block(len(frames), rank, world)
         where = "" if world == 1 else f" [rank {rank}/{world}: frames {lo}-{hi - 1}]"
         print(f"[render_surgery] Rendering {len(frames)} frames, {av.n} Gaussians, iteration {it} "
@@ -290,6 +338,7 @@ def _render_dataset(model_path: str, data_dir: str, iteration: int = -1,
             raise RuntimeError(f"Rendering failed:\n{str(e)[-2000:]}") from e
         renders_dir = os.path.join(train_dir, f"ours_{it}", "renders")
         write_frames_png(renders_dir, images, first=lo)
+        write_gt_frames(os.path.join(train_dir, f"ours_{it}", "gt"), data_dir, frames[lo:hi], first=lo)
     except Exception as e:
         err = e
     if world > 1:

@@ -178,9 +178,13 @@ class Session:
             j_regressor=_f32(model.j_regressor), lbs_weights=_f32(model.lbs_weights),
             faces=np.ascontiguousarray(model.faces, dtype=np.int32),
             xyzb=_f32(baked["xyzb"]), scale_lo=_f32(baked["scale_lo"]), rot=_f32(baked["rot"]), sh=_f32(baked["sh"]))
-        assert keep["shapedirs"].shape == (300 + self.n_expr, 3 * self.n_verts), keep["shapedirs"].shape
-        assert keep["posedirs"].shape == (36, 3 * self.n_verts)
-        assert keep["sh"].shape == (12, self.n_gauss, 4)
+        for name, want in (("shapedirs", (300 + self.n_expr, 3 * self.n_verts)), ("posedirs", (36, 3 * self.n_verts)),
+                           ("j_regressor", (5, self.n_verts)), ("lbs_weights", (self.n_verts, 5)),
+                           ("faces", (self.n_faces, 3)), ("xyzb", (self.n_gauss, 4)), ("scale_lo", (self.n_gauss, 4)),
+                           ("rot", (self.n_gauss, 4)), ("sh", (12, self.n_gauss, 4))):
+            if keep[name].shape != want:
+                raise OmfsError(f"Session: {name} has shape {keep[name].shape}, expected {want} for a model of "
+                                f"{self.n_verts} vertices / {self.n_faces} faces and {self.n_gauss} Gaussians")
         md = ModelDesc(self.n_verts, self.n_faces, self.n_expr, self.n_gauss,
                        *[_ptr(keep[k]) for k in ("v_template", "shapedirs", "posedirs", "j_regressor",
                                                  "lbs_weights", "faces", "xyzb", "scale_lo", "rot", "sh")])
@@ -211,18 +215,26 @@ class Session:
     # -- subject
     def set_subject(self, shape300, static_offset=None, plan_offset=None):
         sh = _f32(shape300).reshape(-1)
-        assert sh.size == 300
+        if sh.size != 300:
+            raise OmfsError(f"set_subject: shape has {sh.size} coefficients, the FLAME record carries 300")
         so = None if static_offset is None else _f32(static_offset).reshape(-1)
         po = None if plan_offset is None else _f32(plan_offset).reshape(-1)
-        for a in (so, po):
-            assert a is None or a.size == 3 * self.n_verts
+        for name, a in (("static_offset", so), ("plan_offset", po)):
+            if a is not None and a.size != 3 * self.n_verts:
+                raise OmfsError(
+                    f"set_subject: {name} covers {a.size // 3} vertices but the FLAME model has {self.n_verts}. "
+                    "The reference's records are written for the 5143-vertex FLAME-with-teeth mesh "
+                    "(flame_fitter.py:439, preprocess_video.py:329); a raw 5023-vertex flame2023.pkl does not match "
+                    "them — export the teeth-augmented model with tools/export_flame_with_teeth.py")
         check(self._L.omfs_session_set_subject(self._h, _ptr(sh), _ptr(so), _ptr(po)))
 
     # -- rendering
     def _frames_desc(self, params, cams, keep: list):
         T = int(params.expr.shape[0])
         expr = _f32(params.expr)
-        assert expr.shape[1] == self.n_expr, (expr.shape, self.n_expr)
+        if expr.ndim != 2 or expr.shape[1] != self.n_expr:
+            raise OmfsError(f"frames: expr has shape {expr.shape}, the session was created for {self.n_expr} "
+                            "expression coefficients")
         cam_arr = _f32(np.stack([c.pack() if isinstance(c, cam_mod.Camera) else np.asarray(c) for c in cams]))
         dyn = params.dynamic_offset
         if dyn is not None and not np.any(dyn):
