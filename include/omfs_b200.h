@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define OMFS_ABI_VERSION 1
+#define OMFS_ABI_VERSION 2
 #define OMFS_TILE 16          /* compositing tile edge, pixels */
 #define OMFS_FF_STRIDE 20     /* floats per face-frame record */
 #define OMFS_CAM_FLOATS 40    /* floats per camera record (cameras.py: Camera.pack) */
@@ -129,6 +129,18 @@ int omfs_composite(int S, int N, int width, int height,
                    const uint32_t* d_sorted_vals, const uint32_t* d_ranges, const float* bg3,
                    float* d_image, uint8_t* d_image_u8, void* d_tickets, void* stream);
 
+/* Frame sink on the device: S uint8 frames [S,H,W,3] in HBM -> S complete 8-bit RGB PNG files
+ * packed back to back in d_png, frame i at d_png[d_offsets[i] .. d_offsets[i+1]) (d_offsets: S+1 uint64 on the
+ * device).  Lossless; every decoder reads them (Up filter on every row, one deflate block per strip of rows —
+ * dynamic Huffman with one of 8 fixed code tables chosen per strip by exact cost, run-length matches, or stored —
+ * one IDAT chunk per strip with its CRC-32, Adler-32 combined over the strips; csrc/png_core.cuh describes the
+ * stream).  png_capacity must be >= S * omfs_png_max_bytes(width, height); scratch comes from d_workspace
+ * (omfs_png_workspace_bytes).  Width up to 5450 pixels (0 is returned by the size queries beyond that). */
+size_t omfs_png_max_bytes(int width, int height);
+size_t omfs_png_workspace_bytes(int S, int width, int height);
+int omfs_png_encode(int S, int width, int height, const uint8_t* d_frames_u8, uint8_t* d_png, size_t png_capacity,
+                    uint64_t* d_offsets, void* d_workspace, size_t workspace_bytes, void* stream);
+
 /* R9 on device (02_Visual_Engine/validation_reporting.py:16-37): the moments behind PSNR and the global SSIM
  * of T pairs of uint8 frames [T,H,W,3] resident in HBM, one pass over both sets.
  *   d_moments[T][6] (float64) = sum (a-b)^2 over all channel values (exact), then with x, y the float32
@@ -213,6 +225,16 @@ typedef struct omfs_frames_desc {
  * makes the copies asynchronous.  Blocks until the frames are in host memory. */
 int omfs_session_render_host(omfs_session* s, const omfs_frames_desc* frames,
                              uint8_t* h_out_u8, float* h_out_f32);
+
+/* Host in, PNG files out (replaces the frame sink behind
+ * 02_Visual_Engine/render_surgery.py:289-315 — upstream's save_image per frame — and the PNG round trip of
+ * stitch_video, :412-449).  The frames are filtered, deflated and framed ON THE DEVICE (omfs_png_encode), so only
+ * the compressed streams cross PCIe.  h_png receives the S complete PNG files back to back, frame i being
+ * h_png[h_offsets[i] .. h_offsets[i+1]); h_offsets has S+1 entries.  h_png_capacity >= S * omfs_png_max_bytes()
+ * always suffices; a smaller buffer is accepted and OMFS_ERR_CAPACITY is returned if the streams do not fit.
+ * h_out_u8 (optional) also returns the raw uint8 frames [S,H,W,3].  Blocks until everything is in host memory. */
+int omfs_session_render_host_png(omfs_session* s, const omfs_frames_desc* frames, uint8_t* h_png,
+                                 size_t h_png_capacity, uint64_t* h_offsets, uint8_t* h_out_u8);
 
 /* Device in, device out (inputs already resident; same field meaning, device pointers).
  * d_out_u8 / d_out_f32 may be NULL.  Asynchronous on `stream`. */

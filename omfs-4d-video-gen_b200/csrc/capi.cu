@@ -43,6 +43,10 @@ extern "C" int omfs_flame_fold_subject(int V, int n_shape, int npad, const float
                                        const float* d_shapedirs, const float* d_shape, const float* d_static,
                                        const float* d_plan, const float* d_jreg, float* d_base, void* stream);
 extern "C" int omfs_to_uint8(int S, int width, int height, const float* d_image, uint8_t* d_out, void* stream);
+namespace omfs {
+int png_encode_launch(int S, int width, int height, const uint8_t* d_frames, uint8_t* d_png, size_t png_capacity,
+                      unsigned long long* d_offsets, void* d_workspace, size_t workspace_bytes, cudaStream_t stream);
+}
 
 extern "C" const char* omfs_last_error(void) { return g_err; }
 extern "C" int omfs_abi_version(void) { return OMFS_ABI_VERSION; }
@@ -198,6 +202,20 @@ struct omfs_session {
     uint32_t last_pairs = 0, max_batch_pairs = 0;
     bool capacity_auto = true;   // pair_capacity == 0 at create: the host entry point grows it on overflow
     cudaStream_t user_stream = nullptr;   // stream of the last render_device call
+    // device frame sink (png.cu): a ring of packed-PNG buffers, so that the encode of batch b, the device->host copy
+    // of batch b-1 and the rendering of batch b+1 overlap.  A slot is reused only after the host has issued (and the
+    // copy engine finished) the copy of the batch that used it.
+    static constexpr int kPngRing = 4;
+    cudaStream_t png_stream = nullptr;
+    DevBuf png_ws, png_buf[kPngRing], png_off[kPngRing];
+    unsigned long long* png_off_host[kPngRing]{};   // pinned: frame offsets of the slot's batch, [S+1]
+    cudaEvent_t ev_png_off[kPngRing]{}, ev_png_copied[kPngRing]{};
+    struct PngSlot {
+        bool active = false;
+        size_t seg0 = 0;
+        int S = 0;
+    } png_slot[kPngRing];
+    size_t png_frame_cap = 0, png_ws_bytes = 0;
     std::vector<int32_t> seg_frame_host;
     int seg_table_fpb = -1, seg_table_views = -1;
 };
@@ -245,6 +263,16 @@ extern "C" void omfs_session_destroy(omfs_session* s) {
         if (s->ev_front[i]) cudaEventDestroy(s->ev_front[i]);
         if (s->ev_comp[i]) cudaEventDestroy(s->ev_comp[i]);
     }
+    if (s->png_stream) cudaStreamSynchronize(s->png_stream);
+    s->png_ws.release();
+    for (int i = 0; i < omfs_session::kPngRing; i++) {
+        s->png_buf[i].release();
+        s->png_off[i].release();
+        if (s->png_off_host[i]) cudaFreeHost(s->png_off_host[i]);
+        if (s->ev_png_off[i]) cudaEventDestroy(s->ev_png_off[i]);
+        if (s->ev_png_copied[i]) cudaEventDestroy(s->ev_png_copied[i]);
+    }
+    if (s->png_stream) cudaStreamDestroy(s->png_stream);
     for (cudaEvent_t e : s->prof_pool) cudaEventDestroy(e);
     if (s->comp_stream) cudaStreamDestroy(s->comp_stream);
     if (s->stream) cudaStreamDestroy(s->stream);
@@ -430,13 +458,70 @@ extern "C" int omfs_session_set_subject(omfs_session* s, const float* h_shape300
     return OMFS_OK;
 }
 
+// Host destination of the device frame sink for one call: packed PNG streams and their offsets.
+struct PngSink {
+    uint8_t* h_png = nullptr;
+    size_t capacity = 0;
+    uint64_t* h_offsets = nullptr;   // [segments + 1]
+    size_t written = 0;              // bytes handed to the copy engine so far
+};
+
+// Lazily created state of the device frame sink (streams, ring buffers) for batches of up to max_batch frames.
+static int png_prepare(omfs_session* s) {
+    if (s->png_stream) return OMFS_OK;
+    const int Sb = s->cfg.max_batch, W = s->cfg.width, H = s->cfg.height;
+    s->png_frame_cap = omfs_png_max_bytes(W, H);
+    s->png_ws_bytes = omfs_png_workspace_bytes(Sb, W, H);
+    if (!s->png_frame_cap || !s->png_ws_bytes) {
+        set_error("png sink: image size %dx%d is not supported", W, H);
+        return OMFS_ERR_UNSUPPORTED;
+    }
+    int rc;
+    if ((rc = s->png_ws.ensure(s->png_ws_bytes))) return rc;
+    for (int i = 0; i < omfs_session::kPngRing; i++) {
+        if ((rc = s->png_buf[i].ensure(s->png_frame_cap * (size_t)Sb))) return rc;
+        if ((rc = s->png_off[i].ensure(sizeof(unsigned long long) * ((size_t)Sb + 1)))) return rc;
+        OMFS_CUDA(cudaMallocHost((void**)&s->png_off_host[i], sizeof(unsigned long long) * ((size_t)Sb + 1)));
+        OMFS_CUDA(cudaEventCreateWithFlags(&s->ev_png_off[i], cudaEventDisableTiming));
+        OMFS_CUDA(cudaEventCreateWithFlags(&s->ev_png_copied[i], cudaEventDisableTiming));
+    }
+    OMFS_CUDA(cudaStreamCreateWithFlags(&s->png_stream, cudaStreamNonBlocking));
+    return OMFS_OK;
+}
+
+// The batch in ring slot r has been encoded (or will be shortly): wait for its frame offsets, hand exactly the bytes
+// it produced to the copy engine, publish the offsets to the caller.
+static int png_drain(omfs_session* s, int r, PngSink* sink) {
+    omfs_session::PngSlot& slot = s->png_slot[r];
+    if (!slot.active) return OMFS_OK;
+    slot.active = false;
+    OMFS_CUDA(cudaEventSynchronize(s->ev_png_off[r]));
+    const unsigned long long* off = s->png_off_host[r];
+    const size_t total = (size_t)off[slot.S];
+    if (sink->written + total > sink->capacity) {
+        set_error("png sink: the caller's buffer (%zu bytes) is too small: %zu bytes needed so far (size it with "
+                  "omfs_png_max_bytes per frame)", sink->capacity, sink->written + total);
+        return OMFS_ERR_CAPACITY;
+    }
+    OMFS_CUDA(cudaMemcpyAsync(sink->h_png + sink->written, s->png_buf[r].p, total, cudaMemcpyDeviceToHost, s->copy_stream));
+    OMFS_CUDA(cudaEventRecord(s->ev_png_copied[r], s->copy_stream));
+    for (int i = 0; i <= slot.S; i++) sink->h_offsets[slot.seg0 + i] = (uint64_t)(sink->written + off[i]);
+    sink->written += total;
+    return OMFS_OK;
+}
+
 // Core loop.  All `p_*` pointers are DEVICE pointers valid on s->stream.
 static int render_core(omfs_session* s, int T, int n_views, const float* p_expr, const float* p_rot,
                        const float* p_neck, const float* p_jaw, const float* p_eyes, const float* p_transl,
                        const float* p_dyn, const float* p_cams, uint8_t* out_u8, float* out_f32, bool out_on_host,
-                       cudaStream_t st) {
+                       cudaStream_t st, PngSink* png = nullptr) {
     const int V = s->V, F = s->F, N = s->N, W = s->cfg.width, H = s->cfg.height;
     const size_t hw = (size_t)W * H;
+    if (png) {
+        int prc = png_prepare(s);
+        if (prc) return prc;
+        for (auto& slot : s->png_slot) slot.active = false;
+    }
     const unsigned long long launches0 = g_launches;
     s->stats[0] = s->stats[2] = s->stats[3] = 0;
     int rc;
@@ -596,7 +681,15 @@ static int render_core(omfs_session* s, int T, int n_views, const float* p_expr,
             const size_t seg0 = (size_t)(g0 + b0) * n_views;
             const bool direct = !out_on_host;  // device output: composite straight into the caller's buffers
             float* dst_f = direct ? (out_f32 ? out_f32 + seg0 * 3 * hw : nullptr) : (out_f32 ? img : nullptr);
-            uint8_t* dst_8 = direct ? (out_u8 ? out_u8 + seg0 * 3 * hw : nullptr) : (out_u8 ? img8 : nullptr);
+            uint8_t* dst_8 = direct ? (out_u8 ? out_u8 + seg0 * 3 * hw : nullptr) : ((out_u8 || png) ? img8 : nullptr);
+            // The sink keeps two batches in flight: before batch b is enqueued the host waits for the frame offsets
+            // of batch b-2 and hands its streams to the copy engine (the GPU still has batch b-1 queued meanwhile),
+            // so the copies overlap the rendering of the following batches and a ring slot is always drained long
+            // before it comes round again.
+            const int pr = batch_index % omfs_session::kPngRing;
+            if (png && batch_index >= 2 &&
+                (rc = png_drain(s, (batch_index - 2) % omfs_session::kPngRing, png)))
+                return rc;
             if (!dst_f && !dst_8) dst_f = img;  // nothing requested: still render (debug taps)
             if ((rc = mark(kStComposite))) return rc;
             // Pipelined: the persistent compositing warps leave 12 of the 32 warp slots per SM to the front end of
@@ -615,17 +708,46 @@ static int render_core(omfs_session* s, int T, int n_views, const float* p_expr,
             if (out_on_host) {
                 OMFS_CUDA(cudaEventRecord(s->ev_done[ib], cst));
                 OMFS_CUDA(cudaStreamWaitEvent(s->copy_stream, s->ev_done[ib], 0));
+                if (png) {
+                    // encode on the sink's own stream: beside the next batch's compositing, after this batch's
+                    // frames are complete and after the copy engine has drained the slot's previous contents
+                    OMFS_CUDA(cudaStreamWaitEvent(s->png_stream, s->ev_done[ib], 0));
+                    OMFS_CUDA(cudaStreamWaitEvent(s->png_stream, s->ev_png_copied[pr], 0));
+                    if ((rc = png_encode_launch(S, W, H, img8, s->png_buf[pr].as<uint8_t>(), s->png_buf[pr].bytes,
+                                                s->png_off[pr].as<unsigned long long>(), s->png_ws.p, s->png_ws_bytes,
+                                                s->png_stream)))
+                        return rc;
+                    OMFS_CUDA(cudaMemcpyAsync(s->png_off_host[pr], s->png_off[pr].p,
+                                              sizeof(unsigned long long) * ((size_t)S + 1), cudaMemcpyDeviceToHost,
+                                              s->png_stream));
+                    OMFS_CUDA(cudaEventRecord(s->ev_png_off[pr], s->png_stream));
+                    s->png_slot[pr].active = true;
+                    s->png_slot[pr].seg0 = seg0;
+                    s->png_slot[pr].S = S;
+                }
                 if (out_u8)
                     OMFS_CUDA(cudaMemcpyAsync(out_u8 + seg0 * 3 * hw, img8, (size_t)S * 3 * hw,
                                               cudaMemcpyDeviceToHost, s->copy_stream));
                 if (out_f32)
                     OMFS_CUDA(cudaMemcpyAsync(out_f32 + seg0 * 3 * hw, img, sizeof(float) * S * 3 * hw,
                                               cudaMemcpyDeviceToHost, s->copy_stream));
-                OMFS_CUDA(cudaEventRecord(s->ev_copied[ib], s->copy_stream));
+                // ev_copied = "this buffer set's images may be overwritten": after the raw copies and, with the
+                // sink, after the encoder has read the uint8 frames.  Sink alone: recorded on the sink's stream, so
+                // that the copy stream never queues a later batch's stream copy behind this batch's encode.
+                if (png && !out_u8 && !out_f32) {
+                    OMFS_CUDA(cudaEventRecord(s->ev_copied[ib], s->png_stream));
+                } else {
+                    if (png) OMFS_CUDA(cudaStreamWaitEvent(s->copy_stream, s->ev_png_off[pr], 0));
+                    OMFS_CUDA(cudaEventRecord(s->ev_copied[ib], s->copy_stream));
+                }
             }
             batch_index++;
         }
     }
+    // the sink's remaining batches, oldest first
+    if (png)
+        for (int k = 0; k < omfs_session::kPngRing; k++)
+            if ((rc = png_drain(s, (batch_index + k) % omfs_session::kPngRing, png))) return rc;
     // everything this call launched is complete when the caller's stream is: join the compositing stream
     for (int ib = 0; ib < 2; ib++)
         if (s->ev_comp_pending[ib]) {
@@ -738,6 +860,62 @@ extern "C" int omfs_session_render_host(omfs_session* s, const omfs_frames_desc*
         // A session created with pair_capacity = 0 sizes itself: an overflowing batch emitted nothing, the
         // scan still counted what it needs, so grow once to that (plus headroom) and render the call again.
         if (rc == OMFS_ERR_CAPACITY && s->capacity_auto && attempt == 0 && s->max_batch_pairs > 0) {
+            uint64_t want = (uint64_t)s->max_batch_pairs + (uint64_t)s->max_batch_pairs / 8 + 4096;
+            if (want >= (1ull << 30)) want = (1ull << 30) - 1;
+            if (want > s->capacity && omfs_session_reserve_pairs(s, want) == OMFS_OK) continue;
+        }
+        break;
+    }
+    return rc;
+}
+
+// Host in, PNG streams out: the frames are encoded on the device (png.cu) and only the compressed streams (plus,
+// optionally, the raw uint8 frames) cross PCIe.
+extern "C" int omfs_session_render_host_png(omfs_session* s, const omfs_frames_desc* fr, uint8_t* h_png,
+                                            size_t h_png_capacity, uint64_t* h_offsets, uint8_t* h_out_u8) {
+    OMFS_REQUIRE(s && fr && h_png && h_offsets, "null argument");
+    OMFS_REQUIRE(s->subject_set, "omfs_session_set_subject must be called first");
+    OMFS_REQUIRE(fr->n_frames >= 0 && fr->n_views > 0 && fr->n_views <= s->cfg.max_batch, "bad frame/view counts");
+    OMFS_REQUIRE(fr->expr && fr->rotation && fr->neck_pose && fr->jaw_pose && fr->eyes_pose && fr->translation &&
+                     fr->cams,
+                 "null frame array");
+    OMFS_CUDA(cudaSetDevice(s->cfg.device));
+    const int T = fr->n_frames;
+    h_offsets[0] = 0;
+    if (T == 0) return OMFS_OK;
+    cudaStream_t st = s->stream;
+    int rc;
+    if ((rc = upload(s->expr, fr->expr, sizeof(float) * (size_t)T * s->n_expr, st))) return rc;
+    if ((rc = upload(s->rotation, fr->rotation, sizeof(float) * 3 * T, st))) return rc;
+    if ((rc = upload(s->neck, fr->neck_pose, sizeof(float) * 3 * T, st))) return rc;
+    if ((rc = upload(s->jaw, fr->jaw_pose, sizeof(float) * 3 * T, st))) return rc;
+    if ((rc = upload(s->eyes, fr->eyes_pose, sizeof(float) * 6 * T, st))) return rc;
+    if ((rc = upload(s->transl, fr->translation, sizeof(float) * 3 * T, st))) return rc;
+    if (fr->dynamic_offset &&
+        (rc = upload(s->dyn, fr->dynamic_offset, sizeof(float) * 3 * (size_t)s->V * T, st)))
+        return rc;
+    if ((rc = upload(s->cams_in, fr->cams, sizeof(float) * kCam * fr->n_views, st))) return rc;
+    for (int attempt = 0;; attempt++) {
+        PngSink sink;
+        sink.h_png = h_png;
+        sink.capacity = h_png_capacity;
+        sink.h_offsets = h_offsets;
+        rc = render_core(s, T, fr->n_views, s->expr.as<float>(), s->rotation.as<float>(), s->neck.as<float>(),
+                         s->jaw.as<float>(), s->eyes.as<float>(), s->transl.as<float>(),
+                         fr->dynamic_offset ? s->dyn.as<float>() : nullptr, s->cams_in.as<float>(), h_out_u8, nullptr,
+                         true, st, &sink);
+        cudaError_t e1 = cudaStreamSynchronize(st);
+        cudaError_t e3 = s->png_stream ? cudaStreamSynchronize(s->png_stream) : cudaSuccess;
+        cudaError_t e2 = cudaStreamSynchronize(s->copy_stream);
+        if (rc == OMFS_OK && e1 != cudaSuccess) rc = cuda_fail(e1, "stream sync", __FILE__, __LINE__);
+        if (rc == OMFS_OK && e3 != cudaSuccess) rc = cuda_fail(e3, "sink stream sync", __FILE__, __LINE__);
+        if (rc == OMFS_OK && e2 != cudaSuccess) rc = cuda_fail(e2, "copy stream sync", __FILE__, __LINE__);
+        if (rc != OMFS_OK) {   // a failed call must not leave events of a half-run pipeline pending
+            cudaDeviceSynchronize();
+            for (auto& slot : s->png_slot) slot.active = false;
+        }
+        if (rc == OMFS_OK) rc = finish_stats(s);
+        if (rc == OMFS_ERR_CAPACITY && s->stats[3] && s->capacity_auto && attempt == 0 && s->max_batch_pairs > 0) {
             uint64_t want = (uint64_t)s->max_batch_pairs + (uint64_t)s->max_batch_pairs / 8 + 4096;
             if (want >= (1ull << 30)) want = (1ull << 30) - 1;
             if (want > s->capacity && omfs_session_reserve_pairs(s, want) == OMFS_OK) continue;

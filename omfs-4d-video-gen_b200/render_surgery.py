@@ -278,10 +278,24 @@ def _agree(agree, error: BaseException | None, what: str):
         raise RuntimeError(f"{what} failed on rank {bad[0][0]}:\n{bad[0][1][-2000:]}")
 
 
+def write_png_files(renders_dir: str, pngs: list, first: int = 0) -> list[str]:
+    """Encoded frames (the device sink's PNG streams) -> renders_dir/%05d.png: the host only writes bytes."""
+    os.makedirs(renders_dir, exist_ok=True)
+    paths = []
+    for i, data in enumerate(pngs):
+        q = os.path.join(renders_dir, f"{first + i:05d}.png")
+        with open(q, "wb") as f:
+            f.write(data)
+        paths.append(q)
+    return paths
+
+
 def _render_dataset(model_path: str, data_dir: str, iteration: int = -1,
-                    clear_old_renders: bool = True, edit=None) -> tuple[str, np.ndarray]:
-    """render_with_gaussians, also returning the frames it wrote (uint8 [T,H,W,3]) so that main() can hand them
-    to the encoder without reading the PNGs back.
+                    clear_old_renders: bool = True, edit=None, need_frames: bool = True) -> tuple[str, np.ndarray]:
+    """render_with_gaussians, also returning the frames it wrote (uint8 [T,H,W,3]) when `need_frames` is set, so
+    that main() can hand them to the video encoder without reading the PNGs back.  The PNG files themselves come
+    from the device frame sink (filter + deflate + framing on the GPU): without `need_frames` only compressed
+    streams cross PCIe and the host just writes them out.
 
     Under torchrun (WORLD_SIZE > 1, one process per GPU) every rank renders the contiguous frame
     block `sharding.frame_block` gives it on its own GPU and writes its own PNGs; rank 0 alone purges stale
@@ -331,13 +345,14 @@ def _render_dataset(model_path: str, data_dir: str, iteration: int = -1,
         cams = [f.camera for f in frames]
         try:
             if hi > lo:
-                images = _render_frames(model, params.slice(lo, hi), av, cams[lo:hi])
+                images, pngs = _render_frames(model, params.slice(lo, hi), av, cams[lo:hi], want_png=True,
+                                              want_u8=need_frames)
             else:
-                images = np.empty((0, cams[0].height, cams[0].width, 3), np.uint8)
+                images, pngs = np.empty((0, cams[0].height, cams[0].width, 3), np.uint8), []
         except Exception as e:  # the reference surfaces renderer failures as RuntimeError (:317-322)
             raise RuntimeError(f"Rendering failed:\n{str(e)[-2000:]}") from e
         renders_dir = os.path.join(train_dir, f"ours_{it}", "renders")
-        write_frames_png(renders_dir, images, first=lo)
+        write_png_files(renders_dir, pngs, first=lo)
         write_gt_frames(os.path.join(train_dir, f"ours_{it}", "gt"), data_dir, frames[lo:hi], first=lo)
     except Exception as e:
         err = e
@@ -355,11 +370,13 @@ def render_with_gaussians(model_path: str, data_dir: str, iteration: int = -1,
 
     Writes `model_path/train/ours_<iter>/renders/%05d.png` (the layout the reference's caller and
     validation report expect, :324-362) and returns that directory."""
-    return _render_dataset(model_path, data_dir, iteration, clear_old_renders)[0]
+    return _render_dataset(model_path, data_dir, iteration, clear_old_renders, need_frames=False)[0]
 
 
-def _render_frames(model, params: FrameParams, av, cams, plan_offset=None, device: int | None = None) -> np.ndarray:
-    """uint8 [T,H,W,3].  Frames may have different cameras (one per frame) but one image size."""
+def _render_frames(model, params: FrameParams, av, cams, plan_offset=None, device: int | None = None,
+                   want_png: bool = False, want_u8: bool = True):
+    """uint8 [T,H,W,3]; with `want_png`, the pair (frames or None, list of PNG files as bytes) — the PNGs are
+    encoded on the device.  Frames may have different cameras (one per frame) but one image size."""
     from . import runtime
     sizes = {(c.width, c.height) for c in cams}
     if len(sizes) != 1:
@@ -370,7 +387,8 @@ def _render_frames(model, params: FrameParams, av, cams, plan_offset=None, devic
     if device is None:
         device = int(os.environ.get("LOCAL_RANK", "0"))
     batch = int(os.environ.get(BATCH_ENV, "32"))
-    out = np.empty((T, H, W, 3), np.uint8)
+    out = np.empty((T, H, W, 3), np.uint8) if (want_u8 or not want_png) else None
+    pngs: list = []
     with runtime.Session(model, baked, W, H, max_batch=batch, device=device,
                          n_expr=params.expr.shape[1]) as sess:
         sess.set_subject(params.shape, params.static_offset, plan_offset)
@@ -381,10 +399,16 @@ def _render_frames(model, params: FrameParams, av, cams, plan_offset=None, devic
             t1 = t0 + 1
             while t1 < T and keys[t1] == keys[t0]:
                 t1 += 1
-            u8, _ = sess.render_host(params.slice(t0, t1), [cams[t0]], want_u8=True)
-            out[t0:t1] = u8
+            if want_png:
+                res = sess.render_host_png(params.slice(t0, t1), [cams[t0]], want_u8=out is not None,
+                                           out_u8=None if out is None else out[t0:t1])
+                data, off = res[0], res[1]
+                view = memoryview(data)
+                pngs.extend(bytes(view[int(off[i]):int(off[i + 1])]) for i in range(t1 - t0))
+            else:
+                sess.render_host(params.slice(t0, t1), [cams[t0]], want_u8=True, out_u8=out[t0:t1])
             t0 = t1
-    return out
+    return (out, pngs) if want_png else out
 
 
 def render_surgery_frames(model, params: FrameParams, av, cams, lefort_mm: float, bsso_mm: float,

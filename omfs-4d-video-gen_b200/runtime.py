@@ -75,6 +75,13 @@ def load_library():
     L.omfs_session_set_subject.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p]
     L.omfs_session_render_host.argtypes = [c_void_p, POINTER(FramesDesc), c_void_p, c_void_p]
     L.omfs_session_render_device.argtypes = [c_void_p, POINTER(FramesDesc), c_void_p, c_void_p, c_void_p]
+    L.omfs_session_render_host_png.argtypes = [c_void_p, POINTER(FramesDesc), c_void_p, c_size_t, c_void_p, c_void_p]
+    L.omfs_png_max_bytes.restype = c_size_t
+    L.omfs_png_max_bytes.argtypes = [c_int, c_int]
+    L.omfs_png_workspace_bytes.restype = c_size_t
+    L.omfs_png_workspace_bytes.argtypes = [c_int, c_int, c_int]
+    L.omfs_png_encode.argtypes = [c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_size_t,
+                                  c_void_p]
     L.omfs_session_sync.argtypes = [c_void_p]
     L.omfs_session_reserve_pairs.argtypes = [c_void_p, c_uint64]
     L.omfs_session_stats.argtypes = [c_void_p, POINTER(c_uint64)]
@@ -256,6 +263,24 @@ class Session:
                                                _ptr(out_f32) if want_f32 else None))
         return (out_u8 if want_u8 else None), (out_f32 if want_f32 else None)
 
+    def render_host_png(self, params, cams, out_png=None, out_offsets=None, out_u8=None, want_u8: bool = False):
+        """Host parameters in, PNG files out: the frames are encoded on the device and only the compressed streams
+        cross PCIe.  Returns (png, offsets[, u8]): frame i is png[offsets[i]:offsets[i+1]] (uint8 / uint64 arrays;
+        pass pinned `out_png` / `out_offsets` to reuse buffers across calls)."""
+        keep: list = []
+        fd, S = self._frames_desc(params, cams, keep)
+        if out_png is None:
+            out_png = np.empty(S * int(self._L.omfs_png_max_bytes(self.width, self.height)), np.uint8)
+        if out_offsets is None:
+            out_offsets = np.zeros(S + 1, np.uint64)
+        if out_offsets.size < S + 1:
+            raise OmfsError(f"render_host_png: offsets array has {out_offsets.size} entries, {S + 1} needed")
+        if want_u8 and out_u8 is None:
+            out_u8 = np.empty((S, self.height, self.width, 3), np.uint8)
+        check(self._L.omfs_session_render_host_png(self._h, ctypes.byref(fd), _ptr(out_png), out_png.nbytes,
+                                                   _ptr(out_offsets), _ptr(out_u8) if want_u8 else None))
+        return (out_png, out_offsets[:S + 1], out_u8) if want_u8 else (out_png, out_offsets[:S + 1])
+
     def render_device(self, d_params: dict, n_frames: int, n_views: int, d_out_u8=0, d_out_f32=0, stream=0):
         """Device pointers in (ints), device pointers out.  Asynchronous; call sync()."""
         fd = FramesDesc(int(n_frames), int(n_views), d_params["expr"], d_params["rotation"],
@@ -364,6 +389,34 @@ class DeviceArray:
             self.free()
         except Exception:
             pass
+
+
+def png_encode_device(frames_u8: np.ndarray) -> list[bytes]:
+    """uint8 [S,H,W,3] host frames -> S PNG files, encoded by the device sink (upload, omfs_png_encode, download).
+    The level-1 form of the frame sink, for callers that already hold frames."""
+    L = load_library()
+    frames_u8 = np.ascontiguousarray(frames_u8, dtype=np.uint8)
+    if frames_u8.ndim != 4 or frames_u8.shape[3] != 3:
+        raise OmfsError(f"png_encode_device: expected uint8 [S,H,W,3], got {frames_u8.shape}")
+    S, H, W, _ = frames_u8.shape
+    if S == 0:
+        return []
+    cap = int(L.omfs_png_max_bytes(W, H))
+    ws_bytes = int(L.omfs_png_workspace_bytes(S, W, H))
+    if not cap or not ws_bytes:
+        raise OmfsError(f"png_encode_device: image size {W}x{H} is not supported by the device sink")
+    d_in, d_png = DeviceArray.from_numpy(frames_u8), DeviceArray((S * cap,), np.uint8)
+    d_off, d_ws = DeviceArray((S + 1,), np.uint64), DeviceArray((ws_bytes,), np.uint8)
+    try:
+        check(L.omfs_png_encode(S, W, H, c_void_p(d_in.ptr), c_void_p(d_png.ptr), S * cap, c_void_p(d_off.ptr),
+                                c_void_p(d_ws.ptr), ws_bytes, None))
+        off = d_off.numpy()
+        png = np.empty(int(off[S]), np.uint8)
+        check(L.omfs_memcpy_d2h(png.ctypes.data_as(c_void_p), c_void_p(d_png.ptr), png.nbytes))
+    finally:
+        for a in (d_in, d_png, d_off, d_ws):
+            a.free()
+    return [png[int(off[i]):int(off[i + 1])].tobytes() for i in range(S)]
 
 
 IPC_HANDLE_BYTES = 64

@@ -17,7 +17,7 @@ def test_library_exports_every_declared_symbol():
     L = runtime.load_library()
     for n in names:
         assert hasattr(L, n), n
-    assert L.omfs_abi_version() == 1
+    assert L.omfs_abi_version() == 2
 
 
 def test_argument_errors_do_not_need_a_gpu():

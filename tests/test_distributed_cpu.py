@@ -68,14 +68,15 @@ def _dropin_worker(rank, world, port, data, mdl, fail_rank):
                       LOCAL_RANK=str(rank))
     from omfs_b200 import render_surgery as rs
 
-    def fake_render(model, params, av, cams, plan_offset=None, device=None):
+    def fake_render(model, params, av, cams, plan_offset=None, device=None, want_png=False, want_u8=True):
         if rank == fail_rank:
             raise ValueError("injected renderer failure")
         assert len(cams) == params.n_frames
         out = np.zeros((params.n_frames, cams[0].height, cams[0].width, 3), np.uint8)
         out[..., 0] = np.round(params.translation[:, 0] * 1000).astype(np.uint8)[:, None, None]   # frame id
         out[..., 1] = 10 + rank
-        return out
+        # the stand-in for the device sink: the host encoder of the same package
+        return (out if want_u8 else None, [rs.encode_png(f) for f in out]) if want_png else out
 
     rs._render_frames = fake_render
     try:

@@ -296,12 +296,13 @@ def test_main_flow_with_a_stand_in_renderer(tmp_path, monkeypatch):
     n_train = len(flame_io.load_transforms(data, "train"))
     seen = {}
 
-    def fake_render(model_, params_, av_, cams, plan_offset=None, device=None):
+    def fake_render(model_, params_, av_, cams, plan_offset=None, device=None, want_png=False, want_u8=True):
         seen["translation"] = params_.translation.copy()
         seen["jaw"] = params_.jaw_pose.copy()
         out = np.zeros((params_.n_frames, H, W, 3), np.uint8)
         out[..., 0] = np.arange(params_.n_frames, dtype=np.uint8)[:, None, None]
-        return out
+        # the stand-in for the device sink: the host encoder of the same package
+        return (out if want_u8 else None, [rs.encode_png(f) for f in out]) if want_png else out
 
     fake = tmp_path / "ffmpeg"
     fake.write_text("#!/bin/sh\nfor a in \"$@\"; do echo \"$a\" >> %s; done\ncat > %s\n" %
@@ -348,7 +349,7 @@ def test_main_flow_with_a_stand_in_renderer(tmp_path, monkeypatch):
     bad = flame_io.load_avatar_ply(os.path.join(mdl, "point_cloud", "iteration_3000", "point_cloud.ply"))
     bad.binding[:] = model.n_faces + 5
     flame_io.save_avatar_ply(os.path.join(mdl, "point_cloud", "iteration_3000", "point_cloud.ply"), bad)
-    with pytest.raises(ValueError, match="binding"):
+    with pytest.raises(ValueError, match="binds Gaussians to faces"):
         rs.render_with_gaussians(mdl, data)
 
 
