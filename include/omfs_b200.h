@@ -273,6 +273,7 @@ int omfs_device_alloc(void** p, size_t bytes);
 int omfs_device_free(void* p);
 int omfs_memcpy_h2d(void* d_dst, const void* h_src, size_t bytes);
 int omfs_memcpy_d2h(void* h_dst, const void* d_src, size_t bytes); /* synchronises the device first */
+int omfs_device_memset(void* d_dst, int value, size_t bytes);
 int omfs_device_sync(void);
 unsigned long long omfs_launch_count(void);    /* kernels launched by this library so far */
 

@@ -95,6 +95,11 @@ extern "C" int omfs_memcpy_d2h(void* h_dst, const void* d_src, size_t bytes) {
     OMFS_CUDA(cudaMemcpy(h_dst, d_src, bytes, cudaMemcpyDeviceToHost));
     return OMFS_OK;
 }
+extern "C" int omfs_device_memset(void* d_dst, int value, size_t bytes) {
+    OMFS_REQUIRE(d_dst != nullptr || bytes == 0, "null pointer");
+    OMFS_CUDA(cudaMemset(d_dst, value, bytes));
+    return OMFS_OK;
+}
 extern "C" int omfs_device_sync(void) {
     OMFS_CUDA(cudaDeviceSynchronize());
     return OMFS_OK;

@@ -95,6 +95,7 @@ def load_library():
     L.omfs_device_free.argtypes = [c_void_p]
     L.omfs_memcpy_h2d.argtypes = [c_void_p, c_void_p, c_size_t]
     L.omfs_memcpy_d2h.argtypes = [c_void_p, c_void_p, c_size_t]
+    L.omfs_device_memset.argtypes = [c_void_p, c_int, c_size_t]
     vp = c_void_p
     L.omfs_flame_pose_prep.argtypes = [c_int, c_int, c_int, vp, vp, vp, vp, vp, vp, vp, vp]
     L.omfs_flame_blend_gemm.argtypes = [c_int, c_int, c_int, vp, vp, vp, vp, c_int, vp]

@@ -49,12 +49,21 @@ def lib():
         L.orc_composite.argtypes = [c_int, c_int, c_int, c_int, _f, _f, _f, _u32, _u32, _f, _f, vp]
         L.orc_to_uint8.argtypes = [c_int, c_int, c_int, _f, _u8]
         L.orc_num_threads.restype = c_int
+        L.orc_set_num_threads.argtypes = [c_int]
+        L.orc_set_num_threads.restype = None
         _lib = L
     return _lib
 
 
 def num_threads() -> int:
     return int(lib().orc_num_threads())
+
+
+def set_num_threads(n: int) -> int:
+    """Set the OpenMP thread count of the oracle's loops (a torchrun rank inherits OMP_NUM_THREADS=1); returns the
+    count now in effect."""
+    lib().orc_set_num_threads(int(n))
+    return num_threads()
 
 
 def _opt(a):
