@@ -267,6 +267,8 @@ int omfs_session_stage_ms(omfs_session* s, double* out_ms8, uint64_t* out_calls8
 /* ------------------------------------------------------------------------------------------
  * Helpers for callers without a CUDA runtime of their own (ctypes, cgo, JNI ...).
  * ---------------------------------------------------------------------------------------- */
+int omfs_device_count(void);                    /* CUDA devices visible to this process (0 if none) */
+int omfs_set_device(int dev);                  /* device the helpers below allocate on (one process per GPU) */
 int omfs_host_alloc(void** p, size_t bytes);   /* page-locked host memory */
 int omfs_host_free(void* p);
 int omfs_device_alloc(void** p, size_t bytes);

@@ -68,6 +68,17 @@ extern "C" int omfs_device_check(int dev) {
     return OMFS_OK;
 }
 
+extern "C" int omfs_device_count(void) {
+    int count = 0;
+    return cudaGetDeviceCount(&count) == cudaSuccess ? count : 0;
+}
+extern "C" int omfs_set_device(int dev) {
+    int rc = omfs_device_check(dev);
+    if (rc) return rc;
+    OMFS_CUDA(cudaSetDevice(dev));
+    return OMFS_OK;
+}
+
 extern "C" int omfs_host_alloc(void** p, size_t bytes) {
     OMFS_REQUIRE(p != nullptr, "null pointer");
     OMFS_CUDA(cudaMallocHost(p, bytes));

@@ -111,6 +111,7 @@ def load_library():
     L.omfs_frame_metrics.argtypes = [c_int, c_int, c_int, vp, vp, vp, vp]
     L.omfs_displace_points.argtypes = [c_int, vp, POINTER(c_double), POINTER(c_double), vp, c_int, vp, vp, vp, vp]
     L.omfs_device_check.argtypes = [c_int]
+    L.omfs_set_device.argtypes = [c_int]
     L.omfs_ipc_export.argtypes = [c_void_p, c_void_p]
     L.omfs_ipc_open.argtypes = [c_void_p, POINTER(c_void_p)]
     L.omfs_ipc_close.argtypes = [c_void_p]

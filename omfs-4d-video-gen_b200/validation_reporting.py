@@ -18,63 +18,92 @@ import numpy as np
 
 C1 = (0.01 * 255) ** 2
 C2 = (0.03 * 255) ** 2
+LUMA = (0.299, 0.587, 0.114)            # BT.601 weights the reference applies to RGB inputs (:24-27)
+VIEW_BANDS = ("front", "profile", "rear")
+
+
+# One implementation serves the host and the device path: both reduce a frame pair to the same moments —
+#   [0] sum (a-b)^2 over every channel value, then with x, y the luma of a, b: [1] sum x, [2] sum y,
+#   [3] sum x^2, [4] sum y^2, [5] sum xy — and `metrics_from_moments` finishes PSNR and the global SSIM from them.
+# On the device the moments come from omfs_frame_metrics (one pass over frames in HBM); on the host from numpy.
+def _luma(img: np.ndarray) -> np.ndarray:
+    """Grey image the global SSIM is computed on: RGB inputs are weighted in their own dtype (the reference keeps
+    float32 there), grey inputs pass through; the moments are then taken in float64."""
+    img = np.asarray(img)
+    if img.ndim == 3:
+        img = LUMA[0] * img[:, :, 0] + LUMA[1] * img[:, :, 1] + LUMA[2] * img[:, :, 2]
+    return img.astype(np.float64)
+
+
+def frame_moments(a: np.ndarray, b: np.ndarray) -> tuple[np.ndarray, int, int]:
+    """(moments[6], number of channel values, number of pixels) of one frame pair, in float64."""
+    a, b = np.asarray(a), np.asarray(b)
+    d = a.astype(np.float64) - b.astype(np.float64)
+    x, y = _luma(a).ravel(), _luma(b).ravel()
+    m = np.array([np.dot(d.ravel(), d.ravel()), x.sum(), y.sum(), np.dot(x, x), np.dot(y, y), np.dot(x, y)], np.float64)
+    return m, int(d.size), int(x.size)
+
+
+def metrics_from_moments(moments: np.ndarray, n_pixels: int, n_values: int | None = None) -> tuple[np.ndarray, np.ndarray]:
+    """PSNR and global SSIM per frame pair from moments [T,6] (layout above).  `n_values` is the number of channel
+    values behind moment 0 (3 per pixel for RGB frames, the default).  PSNR is 20 log10(255 / sqrt(MSE)) on the
+    0-255 scale and 99.0 for identical frames (reference :16-20); SSIM is the single-window form with the usual
+    constants (:23-37), written with E[x^2] - mu^2 for the variances."""
+    m = np.atleast_2d(np.asarray(moments, dtype=np.float64))
+    n = float(n_pixels)
+    mse = m[:, 0] / float(3 * n_pixels if n_values is None else n_values)
+    same = mse == 0.0
+    p = np.where(same, 99.0, 20.0 * np.log10(255.0 / np.sqrt(np.where(same, 1.0, mse))))
+    mu_x, mu_y = m[:, 1] / n, m[:, 2] / n
+    var_x = m[:, 3] / n - mu_x * mu_x
+    var_y = m[:, 4] / n - mu_y * mu_y
+    cov = m[:, 5] / n - mu_x * mu_y
+    s = ((2 * mu_x * mu_y + C1) * (2 * cov + C2)) / ((mu_x * mu_x + mu_y * mu_y + C1) * (var_x + var_y + C2))
+    return p, s
 
 
 def psnr(a: np.ndarray, b: np.ndarray) -> float:
-    """20 log10(255 / sqrt(MSE)) on 0-255 float arrays; 99.0 when the images are identical."""
-    mse = float(np.mean((a - b) ** 2))
-    if mse == 0.0:
-        return 99.0
-    return 20.0 * math.log10(255.0 / math.sqrt(mse))
+    """Reference :16-20: PSNR of two 0-255 arrays, 99.0 when they are identical."""
+    m, n_values, n_pix = frame_moments(a, b)
+    return float(metrics_from_moments(m, n_pix, n_values)[0][0])
 
 
 def ssim_global(a: np.ndarray, b: np.ndarray) -> float:
-    """One SSIM over the whole image (no windows), on the BT.601 luma of RGB inputs."""
-    if a.ndim == 3:
-        a = (0.299 * a[:, :, 0] + 0.587 * a[:, :, 1] + 0.114 * a[:, :, 2])
-    if b.ndim == 3:
-        b = (0.299 * b[:, :, 0] + 0.587 * b[:, :, 1] + 0.114 * b[:, :, 2])
-    a = a.astype(np.float64)
-    b = b.astype(np.float64)
-    mu_x = a.mean()
-    mu_y = b.mean()
-    sig_x = ((a - mu_x) ** 2).mean()
-    sig_y = ((b - mu_y) ** 2).mean()
-    sig_xy = ((a - mu_x) * (b - mu_y)).mean()
-    return float(((2 * mu_x * mu_y + C1) * (2 * sig_xy + C2)) / ((mu_x * mu_x + mu_y * mu_y + C1) * (sig_x + sig_y + C2)))
+    """Reference :23-37: one SSIM over the whole image (no windows), on the luma of RGB inputs."""
+    m, n_values, n_pix = frame_moments(a, b)
+    return float(metrics_from_moments(m, n_pix, n_values)[1][0])
 
 
 def _bucket(progress: float) -> str:
-    if progress < 0.20 or progress > 0.80:
-        return "front"
+    """View band of a frame at `progress` in [0, 1] of the clip (reference :40-45): the middle third-ish of the turn
+    is the profile, the two ends are frontal, what lies between is called rear."""
     if 0.35 <= progress <= 0.65:
         return "profile"
-    return "rear"
+    return "rear" if 0.20 <= progress <= 0.80 else "front"
 
 
 def _find_latest_train_dir(model_path: Path) -> Path:
+    """`train/ours_<N>` with the largest N (reference :48-55)."""
     train_dir = Path(model_path) / "train"
     if not train_dir.exists():
         raise FileNotFoundError(f"Missing train directory: {train_dir}")
-    dirs = [p for p in train_dir.iterdir() if p.is_dir() and p.name.startswith("ours_")]
-    if not dirs:
+    runs = {int(p.name.rsplit("_", 1)[1]): p for p in train_dir.iterdir() if p.is_dir() and p.name.startswith("ours_")}
+    if not runs:
         raise FileNotFoundError(f"No ours_* directories in {train_dir}")
-    return sorted(dirs, key=lambda p: int(p.name.split("_")[-1]), reverse=True)[0]
+    return runs[max(runs)]
 
 
 def _summarise(metrics: list[dict]) -> dict:
-    summary = {"count": len(metrics), "by_bucket": {}}
-    for bucket in ("front", "profile", "rear"):
-        vals = [m for m in metrics if m["bucket"] == bucket]
-        if not vals:
-            summary["by_bucket"][bucket] = {"count": 0, "psnr": None, "ssim": None}
-            continue
-        summary["by_bucket"][bucket] = {
-            "count": len(vals),
-            "psnr": float(np.mean([v["psnr"] for v in vals])),
-            "ssim": float(np.mean([v["ssim"] for v in vals])),
-        }
-    return summary
+    """Row count and per-band mean PSNR / SSIM (reference :95-106); an empty band reports nulls."""
+    bands: dict[str, list[dict]] = {name: [] for name in VIEW_BANDS}
+    for row in metrics:
+        bands[row["bucket"]].append(row)
+    by_bucket = {}
+    for name, rows in bands.items():
+        by_bucket[name] = {"count": len(rows)}
+        for key in ("psnr", "ssim"):
+            by_bucket[name][key] = float(np.mean([r[key] for r in rows])) if rows else None
+    return {"count": len(metrics), "by_bucket": by_bucket}
 
 
 CHECKLIST = """# Human Review Checklist
@@ -141,22 +170,6 @@ def generate_report(model_path: Path, deterministic_frames_dir: Path, output_dir
 
 
 # ----------------------------------------------------------------------------- device path
-def metrics_from_moments(moments: np.ndarray, n_pixels: int) -> tuple[np.ndarray, np.ndarray]:
-    """PSNR and global SSIM per frame pair from omfs_frame_metrics' moments [T,6] =
-    (sum (a-b)^2 over 3*n_pixels channel values, sum x, sum y, sum x^2, sum y^2, sum xy), x/y = luma."""
-    m = np.asarray(moments, dtype=np.float64)
-    n = float(n_pixels)
-    mse = m[:, 0] / (3.0 * n)
-    with np.errstate(divide="ignore"):
-        p = np.where(mse == 0.0, 99.0, 20.0 * np.log10(255.0 / np.sqrt(np.where(mse == 0.0, 1.0, mse))))
-    mu_x, mu_y = m[:, 1] / n, m[:, 2] / n
-    sig_x = m[:, 3] / n - mu_x * mu_x
-    sig_y = m[:, 4] / n - mu_y * mu_y
-    sig_xy = m[:, 5] / n - mu_x * mu_y
-    s = ((2 * mu_x * mu_y + C1) * (2 * sig_xy + C2)) / ((mu_x * mu_x + mu_y * mu_y + C1) * (sig_x + sig_y + C2))
-    return p, s
-
-
 def frame_metrics_device(d_a_u8: int, d_b_u8: int, n_frames: int, height: int, width: int, stream: int = 0):
     """PSNR / SSIM of two uint8 [T,H,W,3] frame sets resident in HBM (device pointers).  Returns (psnr[T], ssim[T])."""
     from . import runtime
