@@ -43,8 +43,15 @@ def test_config2_single_frame_and_batch_consistency(full_scene):
     # an alpha within rounding of 1/255 flips a <= 4e-3 contribution); count and bound them
     diff = np.abs(img[sample] - full.image)
     assert rr.psnr(img[sample] * 255.0, full.image * 255.0) > 50.0
-    print("independent chains: max", diff.max(), "frac>1e-3", (diff > 1e-3).mean(), "psnr",
-          rr.psnr(img[sample] * 255.0, full.image * 255.0))
+    from conftest import record_parity
+    record_parity("512x512_100k_3_frames",
+                  handoff_max_abs=np.abs(img[sample] - ref.image).max(),
+                  handoff_uint8_mismatch_fraction=(oracle.to_uint8(ref.image) != u8[sample]).mean(),
+                  independent_chain_max_abs=diff.max(), independent_chain_fraction_above_1e_3=(diff > 1e-3).mean(),
+                  independent_chain_psnr_db=rr.psnr(img[sample] * 255.0, full.image * 255.0),
+                  verts_max_abs_m=np.abs(verts[sample] - full.verts).max(), tile_pairs_per_frame=pairs_per_frame,
+                  bar="north_star: max abs 1e-3 per channel, PSNR > 50 dB; the 1e-3 bar is asserted on the shared-vertex "
+                      "hand-off, knife-edge alpha < 1/255 flips between independent chains are counted and bounded")
     assert (diff > 1e-3).mean() < 2e-3
     assert diff.max() < 2.0 / 255.0 + 1e-3
     # batch invariance
@@ -145,6 +152,19 @@ def test_config4_multiview_1024_500k():
     segs = [f * n_views + v for f, v in sample]
     assert np.abs(img[segs] - ref.image).max() <= 2e-4
     assert (oracle.to_uint8(ref.image) != u8[segs]).mean() < 1e-5
+    # fully independent chains at this size as well (oracle's own fp32 vertices): recorded, PSNR bar asserted
+    from conftest import record_parity
+    from oracle import reference_rows as rr
+    full = oracle.render(model, params, baked, packed, W, H, seg_frame=seg_frame)
+    diff = np.abs(img[segs] - full.image)
+    assert rr.psnr(img[segs] * 255.0, full.image * 255.0) > 50.0
+    assert (diff > 1e-3).mean() < 2e-3 and diff.max() < 2.0 / 255.0 + 1e-3
+    record_parity("1024x1024_500k_3_views",
+                  handoff_max_abs=np.abs(img[segs] - ref.image).max(),
+                  handoff_uint8_mismatch_fraction=(oracle.to_uint8(ref.image) != u8[segs]).mean(),
+                  independent_chain_max_abs=diff.max(), independent_chain_fraction_above_1e_3=(diff > 1e-3).mean(),
+                  independent_chain_psnr_db=rr.psnr(img[segs] * 255.0, full.image * 255.0),
+                  verts_max_abs_m=np.abs(verts - full.verts).max(), tile_pairs_per_image=pairs / S)
     # last batch = frame 1, all 16 views: preprocess outputs bit-exact for the sampled views of that frame
     P0 = sess.tap_array("P0", (n_views, N, 4), np.float32)
     tt = sess.tap_array("tiles_touched", (n_views, N), np.uint32)
