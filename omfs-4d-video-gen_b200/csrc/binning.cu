@@ -791,17 +791,31 @@ static int set_kernel_attrs(int tiles) {
 
 // ---- stage 1: depth sort of the Gaussians of every segment.  4 passes: the result is in perm[0]
 // (or in perm[1] with counters[6] set, when the exponent-byte pass was the identity and got skipped).
-int binning_depth_sort(int S, int N, int width, int height, size_t capacity, const uint32_t* d_depth_keys,
-                       void* d_workspace, cudaStream_t stream) {
+// ---- stage 0: zero the per-batch counters.  With `fused` the producer of the depth keys (bind_preprocess) fills
+// the digit histograms and the tile counts itself: the pointers it accumulates into are returned.
+int binning_prepare(int S, int N, int width, int height, size_t capacity, void* d_workspace, uint32_t** d_hist_depth,
+                    uint32_t** d_tile_cnt, cudaStream_t stream) {
     BinningWs w = carve(d_workspace, S, N, width, height, capacity);
     OMFS_CUDA(cudaMemsetAsync(d_workspace, 0, w.zero_bytes, stream));
+    if (d_hist_depth) *d_hist_depth = w.hist_depth;
+    if (d_tile_cnt) *d_tile_cnt = w.tile_cnt;
+    return OMFS_OK;
+}
+
+int binning_depth_sort(int S, int N, int width, int height, size_t capacity, const uint32_t* d_depth_keys,
+                       void* d_workspace, cudaStream_t stream, bool prepared_and_histogrammed) {
+    BinningWs w = carve(d_workspace, S, N, width, height, capacity);
     int rc = set_kernel_attrs(w.tiles);
     if (rc) return rc;
-    // the depth exponent byte (bits 24..31) is nearly constant inside a warp's 32 keys
-    rs_histogram_kernel<<<dim3(8, S), 256, 0, stream>>>(d_depth_keys, nullptr, (uint32_t)N, 4, 0x8u, w.hist_depth);
+    if (!prepared_and_histogrammed) {
+        OMFS_CUDA(cudaMemsetAsync(d_workspace, 0, w.zero_bytes, stream));
+        // the depth exponent byte (bits 24..31) is nearly constant inside a warp's 32 keys
+        rs_histogram_kernel<<<dim3(8, S), 256, 0, stream>>>(d_depth_keys, nullptr, (uint32_t)N, 4, 0x8u, w.hist_depth);
+        count_launch();
+    }
     // counters[5] = "top-byte pass is not trivial", counters[6] = "top-byte pass was skipped"
     rs_scan_hist_kernel<<<S * 4, 256, 0, stream>>>(w.hist_depth, 4, 3, (uint32_t)N, w.counters + 5);
-    count_launch(2);
+    count_launch();
     const uint32_t* kin = d_depth_keys;
     const uint32_t* vin = nullptr;  // identity
     for (int p = 0; p < 4; p++) {
@@ -823,19 +837,22 @@ int binning_depth_sort(int S, int N, int width, int height, size_t capacity, con
 int binning_tile_ranges(int S, int N, int width, int height, size_t capacity, const float* d_P0,
                         const uint32_t* d_tiles_touched, uint32_t* d_ranges, uint32_t* d_num_pairs,
                         int* d_status_flag, unsigned long long* d_pair_accum, uint32_t* d_pair_max,
-                        void* d_workspace, cudaStream_t stream) {
+                        void* d_workspace, cudaStream_t stream, bool counted) {
     BinningWs w = carve(d_workspace, S, N, width, height, capacity);
     if (w.tiles > 12288) {
         set_error("binning: %d tiles per frame exceed the shared-memory histogram (max 12288)", w.tiles);
         return OMFS_ERR_INVALID;
     }
-    tile_count_kernel<<<dim3(32, S), 256, sizeof(uint32_t) * w.tiles, stream>>>(N, width, height, w.tiles,
-                                                                              (const float4*)d_P0, d_tiles_touched,
-                                                                              w.tile_cnt);
+    if (!counted) {
+        tile_count_kernel<<<dim3(32, S), 256, sizeof(uint32_t) * w.tiles, stream>>>(N, width, height, w.tiles,
+                                                                                  (const float4*)d_P0, d_tiles_touched,
+                                                                                  w.tile_cnt);
+        count_launch();
+    }
     tile_scan_kernel<<<1, 1024, 0, stream>>>(S * w.tiles, w.tile_cnt, w.tile_start, d_ranges, d_num_pairs,
                                              (unsigned long long)capacity, d_status_flag, w.sort_count,
                                              d_pair_accum, d_pair_max);
-    count_launch(2);
+    count_launch();
     OMFS_LAUNCH_CHECK();
     return OMFS_OK;
 }

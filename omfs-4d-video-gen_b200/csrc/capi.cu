@@ -191,6 +191,11 @@ struct omfs_session {
     // prepares batch b+1 (geometry, binning): ev_front = "batch's lists are ready", ev_comp = "batch's
     // buffers may be overwritten"
     cudaStream_t comp_stream = nullptr;
+    // side stream of the front end (tile-range scan beside the depth sort) and its two events
+    cudaStream_t aux_stream = nullptr;
+    cudaEvent_t ev_pre = nullptr, ev_scan = nullptr;
+    bool fuse_front = true;   // OMFS_FUSE_FRONT=0: the separate histogram / tile-count kernels (A/B, debugging)
+    bool last_batch_full = true;   // OMFS_COMP_LAST_FULL=0: the last batch keeps the pipelined warp count (A/B)
     cudaEvent_t ev_done[2]{}, ev_copied[2]{}, ev_front[2]{}, ev_comp[2]{};
     bool ev_comp_pending[2]{};
     bool subject_set = false;
@@ -265,6 +270,12 @@ extern "C" void omfs_session_destroy(omfs_session* s) {
     if (s->stream) cudaStreamSynchronize(s->stream);
     if (s->copy_stream) cudaStreamSynchronize(s->copy_stream);
     if (s->comp_stream) cudaStreamSynchronize(s->comp_stream);
+    if (s->aux_stream) {
+        cudaStreamSynchronize(s->aux_stream);
+        cudaStreamDestroy(s->aux_stream);
+    }
+    if (s->ev_pre) cudaEventDestroy(s->ev_pre);
+    if (s->ev_scan) cudaEventDestroy(s->ev_scan);
     DevBuf* all[] = {&s->template_, &s->shapedirs, &s->bt, &s->jreg, &s->weights, &s->faces, &s->xyzb,
                      &s->scale_lo, &s->rot, &s->sh, &s->base, &s->shape, &s->static_off, &s->plan_off,
                      &s->expr, &s->rotation, &s->neck, &s->jaw, &s->eyes, &s->transl, &s->dyn, &s->jdyn,
@@ -363,6 +374,15 @@ extern "C" int omfs_session_create(const omfs_model_desc* m, const omfs_session_
         int prio_least = 0, prio_greatest = 0;
         TRY_CUDA(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
         TRY_CUDA(cudaStreamCreateWithPriority(&s->comp_stream, cudaStreamNonBlocking, prio_least));
+    }
+    TRY_CUDA(cudaStreamCreateWithFlags(&s->aux_stream, cudaStreamNonBlocking));
+    TRY_CUDA(cudaEventCreateWithFlags(&s->ev_pre, cudaEventDisableTiming));
+    TRY_CUDA(cudaEventCreateWithFlags(&s->ev_scan, cudaEventDisableTiming));
+    {
+        const char* e = getenv("OMFS_FUSE_FRONT");
+        s->fuse_front = !(e && e[0] == '0');
+        e = getenv("OMFS_COMP_LAST_FULL");
+        s->last_batch_full = !(e && e[0] == '0');
     }
     for (int i = 0; i < 2; i++) {
         TRY_CUDA(cudaEventCreateWithFlags(&s->ev_done[i], cudaEventDisableTiming));
@@ -664,18 +684,38 @@ static int render_core(omfs_session* s, int T, int n_views, const float* p_expr,
                                        s->ff.as<float>(), st)))
                 return rc;
             if ((rc = mark(kStBindPre))) return rc;
-            if ((rc = omfs_bind_preprocess(S, N, F, W, H, s->ff.as<float>(), s->seg_frame.as<int32_t>(),
-                                           s->cams.as<float>(), s->xyzb.as<float>(), s->scale_lo.as<float>(),
-                                           s->rot.as<float>(), s->sh.as<float>(), P0, P1, P2, s->tt.as<uint32_t>(),
-                                           s->depth_keys.as<uint32_t>(), st)))
+            // the binning's counters are zeroed first: the fused bind + preprocess kernel fills the depth-digit
+            // histograms and the tile counts from the values it holds in registers
+            uint32_t *d_hist = nullptr, *d_tcnt = nullptr;
+            const bool fused = s->fuse_front;
+            if (fused && (rc = binning_prepare(S, N, W, H, s->capacity, s->ws.p, &d_hist, &d_tcnt, st))) return rc;
+            if ((rc = bind_preprocess_launch(S, N, F, W, H, s->ff.as<float>(), s->seg_frame.as<int32_t>(),
+                                             s->cams.as<float>(), s->xyzb.as<float>(), s->scale_lo.as<float>(),
+                                             s->rot.as<float>(), s->sh.as<float>(), P0, P1, P2, s->tt.as<uint32_t>(),
+                                             s->depth_keys.as<uint32_t>(), d_hist, d_tcnt, st)))
                 return rc;
+            // The tile-range scan (ONE CTA, ~35 us of latency) needs only the tile counts: with the fused front end it
+            // runs on a side stream beside the depth sort instead of between it and the emission.  Stage timing keeps
+            // everything on one stream so that its intervals mean one stage each.
+            const bool side_scan = fused && pipelined;
+            if (side_scan) {
+                OMFS_CUDA(cudaEventRecord(s->ev_pre, st));
+                OMFS_CUDA(cudaStreamWaitEvent(s->aux_stream, s->ev_pre, 0));
+                if ((rc = binning_tile_ranges(S, N, W, H, s->capacity, P0, s->tt.as<uint32_t>(), ranges, d_num_pairs,
+                                              d_flag, d_pair_accum, d_pair_max, s->ws.p, s->aux_stream, true)))
+                    return rc;
+                OMFS_CUDA(cudaEventRecord(s->ev_scan, s->aux_stream));
+            }
             if ((rc = mark(kStDepthSort))) return rc;
-            if ((rc = binning_depth_sort(S, N, W, H, s->capacity, s->depth_keys.as<uint32_t>(), s->ws.p, st)))
+            if ((rc = binning_depth_sort(S, N, W, H, s->capacity, s->depth_keys.as<uint32_t>(), s->ws.p, st, fused)))
                 return rc;
             if ((rc = mark(kStTileRanges))) return rc;
-            if ((rc = binning_tile_ranges(S, N, W, H, s->capacity, P0, s->tt.as<uint32_t>(), ranges, d_num_pairs,
-                                          d_flag, d_pair_accum, d_pair_max, s->ws.p, st)))
+            if (side_scan) {
+                OMFS_CUDA(cudaStreamWaitEvent(st, s->ev_scan, 0));
+            } else if ((rc = binning_tile_ranges(S, N, W, H, s->capacity, P0, s->tt.as<uint32_t>(), ranges, d_num_pairs,
+                                                 d_flag, d_pair_accum, d_pair_max, s->ws.p, st, fused))) {
                 return rc;
+            }
             if ((rc = mark(kStEmitScatter))) return rc;
             if ((rc = binning_emit_scatter(S, N, W, H, s->capacity, P0, s->tt.as<uint32_t>(), vals, s->ws.p, st)))
                 return rc;
@@ -710,8 +750,11 @@ static int render_core(omfs_session* s, int T, int n_views, const float* p_expr,
             if ((rc = mark(kStComposite))) return rc;
             // Pipelined: the persistent compositing warps leave 12 of the 32 warp slots per SM to the front end of
             // the next batch (measured on the 512^2 / 100k clip: 20 -> 32.0k frames/s, 32 -> 31.4k, 16 -> 30.5k).
+            // The LAST batch of a call has no front end beside it (the call joins its streams at the end): it gets the
+            // whole SM.
+            const bool last_batch = (g0 + gT >= T) && (bi + 1 == sizes.size());
             if ((rc = composite_launch(S, N, W, H, P0, P1, P2, vals, ranges, s->cfg.bg, dst_f, dst_8, s->tickets.p,
-                                       pipelined ? kCompPipelinedWarps : 0, cst)))
+                                       (pipelined && !(last_batch && s->last_batch_full)) ? kCompPipelinedWarps : 0, cst)))
                 return rc;
             if ((rc = mark(-1))) return rc;
             if (pipelined) {

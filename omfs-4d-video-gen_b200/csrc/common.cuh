@@ -66,12 +66,22 @@ extern unsigned long long g_launches;
 inline void count_launch(int n = 1) { g_launches += (unsigned long long)n; }
 
 // binning stages (binning.cu), called separately by the session so that it can time them
+// binning_prepare zeroes the per-batch counters and returns where a fused producer (bind_preprocess_launch) is to
+// accumulate the depth-digit histograms and the tile counts; depth_sort / tile_ranges are then told that this
+// has happened (`prepared_and_histogrammed`, `counted`) and skip their own memset / histogram / count kernels.
+int binning_prepare(int S, int N, int width, int height, size_t capacity, void* d_workspace, uint32_t** d_hist_depth,
+                    uint32_t** d_tile_cnt, cudaStream_t stream);
 int binning_depth_sort(int S, int N, int width, int height, size_t capacity, const uint32_t* d_depth_keys,
-                       void* d_workspace, cudaStream_t stream);
+                       void* d_workspace, cudaStream_t stream, bool prepared_and_histogrammed = false);
 int binning_tile_ranges(int S, int N, int width, int height, size_t capacity, const float* d_P0,
                         const uint32_t* d_tiles_touched, uint32_t* d_ranges, uint32_t* d_num_pairs,
                         int* d_status_flag, unsigned long long* d_pair_accum, uint32_t* d_pair_max,
-                        void* d_workspace, cudaStream_t stream);
+                        void* d_workspace, cudaStream_t stream, bool counted = false);
+// U5+U6 (exact_geom.cu); d_hist_depth / d_tile_cnt non-null = the fused form (see binning_prepare)
+int bind_preprocess_launch(int S, int N, int F, int width, int height, const float* d_ff, const int32_t* d_seg_frame,
+                           const float* d_cams, const float* d_xyzb, const float* d_scale_lo, const float* d_rot,
+                           const float* d_sh, float* d_P0, float* d_P1, float* d_P2, uint32_t* d_tiles_touched,
+                           uint32_t* d_depth_keys, uint32_t* d_hist_depth, uint32_t* d_tile_cnt, cudaStream_t stream);
 int binning_emit_scatter(int S, int N, int width, int height, size_t capacity, const float* d_P0,
                          const uint32_t* d_tiles_touched, uint32_t* d_sorted_vals, void* d_workspace,
                          cudaStream_t stream);

@@ -63,80 +63,173 @@ __global__ void __launch_bounds__(256) face_frames_kernel(int T, int V, int F, c
 }
 
 // ------------------------------------------------------------------------------------- U5+U6
-// grid = (ceil(N/kBindThreads), S).  One thread per (segment, Gaussian).
+// grid = (blocks per segment, S).  One thread per (segment, Gaussian); a block walks `per_block` consecutive
+// Gaussians of its segment.
+//
+// FUSED (the session's form): the kernel also accumulates what the binning needs from the values it has in
+// registers anyway — the four digit histograms of the depth key (onesweep's upfront histogram) and the per-tile
+// Gaussian counts (input of the tile-range scan) — in shared-memory counters flushed once per block.  That removes
+// two kernels that re-read S*N keys and S*N (tiles_touched, P0) records (rs_histogram, tile_count: ~90 us per
+// 60-frame batch) at the price of ~7.6 shared-memory atomics per Gaussian here.
 #ifndef OMFS_BIND_THREADS
 #define OMFS_BIND_THREADS 128  // 56 registers; small CTAs also fit beside the persistent compositing warps of the previous batch
 #endif
 constexpr int kBindThreads = OMFS_BIND_THREADS;
+template <bool FUSED>
 __global__ void __launch_bounds__(kBindThreads) bind_preprocess_kernel(
     int N, int F, int width, int height, const float4* __restrict__ ff, const int32_t* __restrict__ seg_frame,
     const float* __restrict__ cams, const float4* __restrict__ xyzb, const float4* __restrict__ scale_lo,
     const float4* __restrict__ rot, const float4* __restrict__ sh, float4* __restrict__ P0,
     float4* __restrict__ P1, float4* __restrict__ P2, uint32_t* __restrict__ tiles_touched,
-    uint32_t* __restrict__ depth_keys) {
+    uint32_t* __restrict__ depth_keys, int per_block, uint32_t* __restrict__ hist_depth /*[S][4][256]*/,
+    uint32_t* __restrict__ tile_cnt /*[S][tiles]*/, int tiles) {
     __shared__ float s_cam[kCam];
+    extern __shared__ uint32_t s_fused[];   // FUSED: [4][256] depth-digit counters, then [tiles] tile counters
     const int seg = blockIdx.y;
     if (threadIdx.x < kCam) s_cam[threadIdx.x] = __ldg(cams + (size_t)seg * kCam + threadIdx.x);
+    if (FUSED)
+        for (int i = threadIdx.x; i < 1024 + tiles; i += blockDim.x) s_fused[i] = 0;
     __syncthreads();
-    const int n = blockIdx.x * blockDim.x + threadIdx.x;
-    if (n >= N) return;
     const int frame = __ldg(seg_frame + seg);
     const int gx = (width + kTile - 1) / kTile, gy = (height + kTile - 1) / kTile;
+    const int n_begin = blockIdx.x * per_block, n_end = min(N, n_begin + per_block);
+    const int lane = threadIdx.x & 31;
 
-    const float4 a = ldg4(xyzb + n);
-    const float4 s = ldg4(scale_lo + n);
-    const float4 q = ldg4(rot + n);
-    const int b = __float_as_int(a.w);
-    const float4* fr = ff + ((size_t)frame * F + b) * 5;
-    float frec[20];
+    for (int base = n_begin; base < n_end; base += blockDim.x) {
+        const int n = base + threadIdx.x;
+        const bool valid = n < n_end;
+        bool ok = false;
+        BindPre o;
+        o.px = o.py = o.depth = 0.f;
+        o.radius = 0;
+        if (valid) {
+            const float4 a = ldg4(xyzb + n);
+            const float4 s = ldg4(scale_lo + n);
+            const float4 q = ldg4(rot + n);
+            const int b = __float_as_int(a.w);
+            const float4* fr = ff + ((size_t)frame * F + b) * 5;
+            float frec[20];
 #pragma unroll
-    for (int k = 0; k < 5; k++) {
-        const float4 v = ldg4(fr + k);
-        frec[4 * k] = v.x;
-        frec[4 * k + 1] = v.y;
-        frec[4 * k + 2] = v.z;
-        frec[4 * k + 3] = v.w;
-    }
-    BindPre o;
-    const bool ok = ex_bind_project(frec, a.x, a.y, a.z, s.x, s.y, s.z, q.x, q.y, q.z, q.w, s_cam, width, height,
-                                    gx, gy, o);
-    const size_t oi = (size_t)seg * N + n;
-    if (!ok) {
-        P0[oi] = make_float4(0.f, 0.f, 0.f, __int_as_float(0));
-        P1[oi] = make_float4(0.f, 0.f, 0.f, 0.f);
-        P2[oi] = make_float4(0.f, 0.f, 0.f, 0.f);
-        tiles_touched[oi] = 0;
-        if (depth_keys) depth_keys[oi] = 0u;
-        return;
-    }
-    float dx, dy, dz;
-    ex_view_dir(o.mx, o.my, o.mz, s_cam, dx, dy, dz);
-    float bs[16];
-    ex_sh_basis(dx, dy, dz, bs);
-    // 12 float4 planes; flat index k*3+c lives in plane (flat>>2), lane (flat&3)
-    float coef[48];
+            for (int k = 0; k < 5; k++) {
+                const float4 v = ldg4(fr + k);
+                frec[4 * k] = v.x;
+                frec[4 * k + 1] = v.y;
+                frec[4 * k + 2] = v.z;
+                frec[4 * k + 3] = v.w;
+            }
+            ok = ex_bind_project(frec, a.x, a.y, a.z, s.x, s.y, s.z, q.x, q.y, q.z, q.w, s_cam, width, height, gx, gy, o);
+            const size_t oi = (size_t)seg * N + n;
+            if (!ok) {
+                P0[oi] = make_float4(0.f, 0.f, 0.f, __int_as_float(0));
+                P1[oi] = make_float4(0.f, 0.f, 0.f, 0.f);
+                P2[oi] = make_float4(0.f, 0.f, 0.f, 0.f);
+                tiles_touched[oi] = 0;
+                if (depth_keys) depth_keys[oi] = 0u;
+            } else {
+                float dx, dy, dz;
+                ex_view_dir(o.mx, o.my, o.mz, s_cam, dx, dy, dz);
+                float bs[16];
+                ex_sh_basis(dx, dy, dz, bs);
+                // 12 float4 planes; flat index k*3+c lives in plane (flat>>2), lane (flat&3)
+                float coef[48];
 #pragma unroll
-    for (int j = 0; j < 12; j++) {
-        const float4 v = ldg4(sh + (size_t)j * N + n);
-        coef[4 * j] = v.x;
-        coef[4 * j + 1] = v.y;
-        coef[4 * j + 2] = v.z;
-        coef[4 * j + 3] = v.w;
-    }
-    float rgb[3];
+                for (int j = 0; j < 12; j++) {
+                    const float4 v = ldg4(sh + (size_t)j * N + n);
+                    coef[4 * j] = v.x;
+                    coef[4 * j + 1] = v.y;
+                    coef[4 * j + 2] = v.z;
+                    coef[4 * j + 3] = v.w;
+                }
+                float rgb[3];
 #pragma unroll
-    for (int c = 0; c < 3; c++) {
-        float acc = bs[0] * coef[c];
+                for (int c = 0; c < 3; c++) {
+                    float acc = bs[0] * coef[c];
 #pragma unroll
-        for (int k = 1; k < 16; k++) acc = acc + bs[k] * coef[k * 3 + c];
-        acc = acc + 0.5f;
-        rgb[c] = fmaxf(acc, 0.0f);
+                    for (int k = 1; k < 16; k++) acc = acc + bs[k] * coef[k * 3 + c];
+                    acc = acc + 0.5f;
+                    rgb[c] = fmaxf(acc, 0.0f);
+                }
+                P0[oi] = make_float4(o.px, o.py, o.depth, __int_as_float(o.radius));
+                P1[oi] = make_float4(o.ca, o.cb, o.cc, s.w);
+                P2[oi] = make_float4(rgb[0], rgb[1], rgb[2], pack_cull_extents(o.ca, o.cb, o.cc, s.w));
+                tiles_touched[oi] = o.tiles;
+                if (depth_keys) depth_keys[oi] = __float_as_uint(o.depth);  // sort key of the depth sort (binning.cu)
+            }
+        }
+        if (FUSED) {
+            // depth-key digits: bytes 0..2 straight to the counters; the exponent byte is almost always the same for a
+            // warp's 32 Gaussians and is then counted with one add
+            const uint32_t key = ok ? __float_as_uint(o.depth) : 0u;
+            if (valid) {
+                atomicAdd(&s_fused[key & 0xffu], 1u);
+                atomicAdd(&s_fused[256 + ((key >> 8) & 0xffu)], 1u);
+                atomicAdd(&s_fused[512 + ((key >> 16) & 0xffu)], 1u);
+            }
+            const uint32_t top = key >> 24;
+            const uint32_t top0 = __shfl_sync(0xffffffffu, top, 0);
+            const uint32_t vmask = __ballot_sync(0xffffffffu, valid);
+            if (__all_sync(0xffffffffu, !valid || top == top0)) {
+                if (lane == 0 && vmask) atomicAdd(&s_fused[768 + top0], (uint32_t)__popc(vmask));
+            } else if (valid) {
+                atomicAdd(&s_fused[768 + top], 1u);
+            }
+            if (ok) {
+                int minx, miny, maxx, maxy;
+                ex_tile_rect(o.px, o.py, o.radius, gx, gy, minx, miny, maxx, maxy);
+                for (int y = miny; y < maxy; y++)
+                    for (int x = minx; x < maxx; x++) atomicAdd(&s_fused[1024 + y * gx + x], 1u);
+            }
+        }
     }
-    P0[oi] = make_float4(o.px, o.py, o.depth, __int_as_float(o.radius));
-    P1[oi] = make_float4(o.ca, o.cb, o.cc, s.w);
-    P2[oi] = make_float4(rgb[0], rgb[1], rgb[2], pack_cull_extents(o.ca, o.cb, o.cc, s.w));
-    tiles_touched[oi] = o.tiles;
-    if (depth_keys) depth_keys[oi] = __float_as_uint(o.depth);  // sort key of the depth sort (binning.cu)
+    if (FUSED) {
+        __syncthreads();
+        uint32_t* h = hist_depth + (size_t)seg * 1024;
+        for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
+            const uint32_t v = s_fused[i];
+            if (v) atomicAdd(h + i, v);
+        }
+        uint32_t* c = tile_cnt + (size_t)seg * tiles;
+        for (int i = threadIdx.x; i < tiles; i += blockDim.x) {
+            const uint32_t v = s_fused[1024 + i];
+            if (v) atomicAdd(c + i, v);
+        }
+    }
+}
+
+int bind_preprocess_launch(int S, int N, int F, int width, int height, const float* d_ff, const int32_t* d_seg_frame,
+                           const float* d_cams, const float* d_xyzb, const float* d_scale_lo, const float* d_rot,
+                           const float* d_sh, float* d_P0, float* d_P1, float* d_P2, uint32_t* d_tiles_touched,
+                           uint32_t* d_depth_keys, uint32_t* d_hist_depth, uint32_t* d_tile_cnt, cudaStream_t stream) {
+    const int tiles = ((width + kTile - 1) / kTile) * ((height + kTile - 1) / kTile);
+    const bool fused = d_hist_depth && d_tile_cnt;
+    if (!fused) {
+        dim3 grid(ceil_div(N, kBindThreads), S);
+        bind_preprocess_kernel<false><<<grid, kBindThreads, 0, stream>>>(
+            N, F, width, height, (const float4*)d_ff, d_seg_frame, d_cams, (const float4*)d_xyzb, (const float4*)d_scale_lo,
+            (const float4*)d_rot, (const float4*)d_sh, (float4*)d_P0, (float4*)d_P1, (float4*)d_P2, d_tiles_touched,
+            d_depth_keys, kBindThreads, nullptr, nullptr, tiles);
+    } else {
+        // blocks walk ~4096 Gaussians each (32 rounds): long enough that the counter flush (1024 + tiles global atomics
+        // per block) is ~0.5 per Gaussian, short enough that the grid is many waves of 128-thread blocks
+        const size_t smem = sizeof(uint32_t) * (1024 + (size_t)tiles);
+        if (smem > 200 * 1024) {
+            set_error("bind_preprocess: %d tiles per frame exceed the fused tile counters", tiles);
+            return OMFS_ERR_INVALID;
+        }
+        static DeviceOnce once;
+        int rc = ensure_dyn_smem(once, bind_preprocess_kernel<true>, (int)smem);
+        if (rc) return rc;
+        int per_block = 32 * kBindThreads;
+        if (tiles > 1024) per_block = 64 * kBindThreads;
+        dim3 grid(ceil_div(N, per_block), S);
+        bind_preprocess_kernel<true><<<grid, kBindThreads, smem, stream>>>(
+            N, F, width, height, (const float4*)d_ff, d_seg_frame, d_cams, (const float4*)d_xyzb, (const float4*)d_scale_lo,
+            (const float4*)d_rot, (const float4*)d_sh, (float4*)d_P0, (float4*)d_P1, (float4*)d_P2, d_tiles_touched,
+            d_depth_keys, per_block, d_hist_depth, d_tile_cnt, tiles);
+    }
+    count_launch();
+    OMFS_LAUNCH_CHECK();
+    return OMFS_OK;
 }
 
 }  // namespace omfs
@@ -168,12 +261,6 @@ extern "C" int omfs_bind_preprocess(int S, int N, int F, int width, int height, 
     OMFS_REQUIRE(d_ff && d_seg_frame && d_cams && d_xyzb && d_scale_lo && d_rot && d_sh, "null input");
     OMFS_REQUIRE(d_P0 && d_P1 && d_P2 && d_tiles_touched, "null output");
     if (S == 0) return OMFS_OK;
-    dim3 grid(ceil_div(N, kBindThreads), S);
-    bind_preprocess_kernel<<<grid, kBindThreads, 0, (cudaStream_t)stream>>>(
-        N, F, width, height, (const float4*)d_ff, d_seg_frame, d_cams, (const float4*)d_xyzb,
-        (const float4*)d_scale_lo, (const float4*)d_rot, (const float4*)d_sh, (float4*)d_P0, (float4*)d_P1,
-        (float4*)d_P2, d_tiles_touched, d_depth_keys);
-    count_launch();
-    OMFS_LAUNCH_CHECK();
-    return OMFS_OK;
+    return bind_preprocess_launch(S, N, F, width, height, d_ff, d_seg_frame, d_cams, d_xyzb, d_scale_lo, d_rot, d_sh, d_P0,
+                                  d_P1, d_P2, d_tiles_touched, d_depth_keys, nullptr, nullptr, (cudaStream_t)stream);
 }
