@@ -534,14 +534,20 @@ __global__ void __launch_bounds__(256) rs_histogram_kernel(const uint32_t* __res
 }
 
 // exclusive scan of each (segment, pass) histogram: counts -> digit start offsets.  grid = n_seg*passes.
-// If `nontrivial` is given, blocks of pass `watch_pass` raise it when their segment's keys do not all
-// share one digit: a pass whose digit is constant in every segment is the identity and gets skipped.
+// If `nontrivial` is given, blocks of pass `watch_pass` (the top byte of the depth key) raise it when their
+// segment's VISIBLE keys do not all share one digit.  Culled Gaussians carry key 0 (top byte 0; a visible depth is
+// > 0.2, top byte >= 0x3e): they emit no pairs, so where they land relative to the visible ones is irrelevant, and a
+// pass whose digit is constant over the visible keys of every segment only moves culled entries — it is skipped.
 __global__ void __launch_bounds__(256) rs_scan_hist_kernel(uint32_t* __restrict__ hist, int passes, int watch_pass,
                                                            uint32_t seg_len, uint32_t* __restrict__ nontrivial) {
     __shared__ uint32_t s_warp[8];
     uint32_t* h = hist + (size_t)blockIdx.x * kRadix;
     const uint32_t v = h[threadIdx.x];
-    if (nontrivial && (int)(blockIdx.x % passes) == watch_pass && v != 0u && v != seg_len) atomicOr(nontrivial, 1u);
+    (void)seg_len;
+    if (nontrivial && (int)(blockIdx.x % passes) == watch_pass) {
+        const int distinct = __syncthreads_count(threadIdx.x != 0 && v != 0u);
+        if (threadIdx.x == 0 && distinct > 1) atomicOr(nontrivial, 1u);
+    }
     uint32_t total;
     h[threadIdx.x] = block_excl_scan_256(v, s_warp, total);
 }

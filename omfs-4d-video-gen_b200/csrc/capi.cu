@@ -954,6 +954,9 @@ extern "C" int omfs_session_render_host_png(omfs_session* s, const omfs_frames_d
         (rc = upload(s->dyn, fr->dynamic_offset, sizeof(float) * 3 * (size_t)s->V * T, st)))
         return rc;
     if ((rc = upload(s->cams_in, fr->cams, sizeof(float) * kCam * fr->n_views, st))) return rc;
+    static const bool trace = getenv("OMFS_TRACE") != nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
+    auto us = [&]() { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t0).count(); };
     for (int attempt = 0;; attempt++) {
         PngSink sink;
         sink.h_png = h_png;
@@ -963,9 +966,14 @@ extern "C" int omfs_session_render_host_png(omfs_session* s, const omfs_frames_d
                          s->jaw.as<float>(), s->eyes.as<float>(), s->transl.as<float>(),
                          fr->dynamic_offset ? s->dyn.as<float>() : nullptr, s->cams_in.as<float>(), h_out_u8, nullptr,
                          true, st, &sink);
+        const double t_enq = us();
         cudaError_t e1 = cudaStreamSynchronize(st);
+        const double t_st = us();
         cudaError_t e3 = s->png_stream ? cudaStreamSynchronize(s->png_stream) : cudaSuccess;
         cudaError_t e2 = cudaStreamSynchronize(s->copy_stream);
+        if (trace)
+            fprintf(stderr, "[omfs trace] render_host_png T=%d: enqueued+drained %.0f us, kernels done %.0f us, sink and "
+                            "copies done %.0f us, %zu bytes\n", T, t_enq, t_st, us(), sink.written);
         if (rc == OMFS_OK && e1 != cudaSuccess) rc = cuda_fail(e1, "stream sync", __FILE__, __LINE__);
         if (rc == OMFS_OK && e3 != cudaSuccess) rc = cuda_fail(e3, "sink stream sync", __FILE__, __LINE__);
         if (rc == OMFS_OK && e2 != cudaSuccess) rc = cuda_fail(e2, "copy stream sync", __FILE__, __LINE__);

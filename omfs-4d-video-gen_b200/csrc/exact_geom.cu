@@ -63,8 +63,11 @@ __global__ void __launch_bounds__(256) face_frames_kernel(int T, int V, int F, c
 }
 
 // ------------------------------------------------------------------------------------- U5+U6
-// grid = (blocks per segment, S).  One thread per (segment, Gaussian); a block walks `per_block` consecutive
-// Gaussians of its segment.
+// One thread per (segment, Gaussian).  A block owns a range of `per_block` consecutive (segment, Gaussian) pairs:
+//   unfused  grid = (blocks per segment, S): the range lies inside segment blockIdx.y;
+//   fused    a 1-D grid of ONE resident wave over the flat S*N index space, so every block does the same amount
+//            of work (a grid of whole segments' pieces left the last wave a quarter full: +50 % on the kernel).  A
+//            range that crosses a segment boundary is walked piece by piece, counters flushed at the boundary.
 //
 // FUSED (the session's form): the kernel also accumulates what the binning needs from the values it has in
 // registers anyway — the four digit histograms of the depth key (onesweep's upfront histogram) and the per-tile
@@ -81,19 +84,31 @@ __global__ void __launch_bounds__(kBindThreads) bind_preprocess_kernel(
     const float* __restrict__ cams, const float4* __restrict__ xyzb, const float4* __restrict__ scale_lo,
     const float4* __restrict__ rot, const float4* __restrict__ sh, float4* __restrict__ P0,
     float4* __restrict__ P1, float4* __restrict__ P2, uint32_t* __restrict__ tiles_touched,
-    uint32_t* __restrict__ depth_keys, int per_block, uint32_t* __restrict__ hist_depth /*[S][4][256]*/,
+    uint32_t* __restrict__ depth_keys, int S, int per_block, uint32_t* __restrict__ hist_depth /*[S][4][256]*/,
     uint32_t* __restrict__ tile_cnt /*[S][tiles]*/, int tiles) {
     __shared__ float s_cam[kCam];
     extern __shared__ uint32_t s_fused[];   // FUSED: [4][256] depth-digit counters, then [tiles] tile counters
-    const int seg = blockIdx.y;
+    const int gx = (width + kTile - 1) / kTile, gy = (height + kTile - 1) / kTile;
+    const int lane = threadIdx.x & 31;
+    long long flat_lo, flat_hi;
+    if (FUSED) {
+        flat_lo = (long long)blockIdx.x * per_block;
+        flat_hi = min(flat_lo + per_block, (long long)S * N);
+    } else {
+        flat_lo = (long long)blockIdx.y * N + (long long)blockIdx.x * per_block;
+        flat_hi = min(flat_lo + per_block, (long long)(blockIdx.y + 1) * N);
+    }
+    while (flat_lo < flat_hi) {   // one piece per segment the range touches (uniform over the block)
+    const int seg = (int)(flat_lo / N);
+    const int n_begin = (int)(flat_lo - (long long)seg * N);
+    const int n_end = (int)min((long long)N, flat_hi - (long long)seg * N);
+    flat_lo += n_end - n_begin;
+    __syncthreads();   // the previous piece's counters are flushed, its camera no longer read
     if (threadIdx.x < kCam) s_cam[threadIdx.x] = __ldg(cams + (size_t)seg * kCam + threadIdx.x);
     if (FUSED)
         for (int i = threadIdx.x; i < 1024 + tiles; i += blockDim.x) s_fused[i] = 0;
     __syncthreads();
     const int frame = __ldg(seg_frame + seg);
-    const int gx = (width + kTile - 1) / kTile, gy = (height + kTile - 1) / kTile;
-    const int n_begin = blockIdx.x * per_block, n_end = min(N, n_begin + per_block);
-    const int lane = threadIdx.x & 31;
 
     for (int base = n_begin; base < n_end; base += blockDim.x) {
         const int n = base + threadIdx.x;
@@ -194,6 +209,7 @@ __global__ void __launch_bounds__(kBindThreads) bind_preprocess_kernel(
             if (v) atomicAdd(c + i, v);
         }
     }
+    }  // pieces
 }
 
 int bind_preprocess_launch(int S, int N, int F, int width, int height, const float* d_ff, const int32_t* d_seg_frame,
@@ -207,10 +223,8 @@ int bind_preprocess_launch(int S, int N, int F, int width, int height, const flo
         bind_preprocess_kernel<false><<<grid, kBindThreads, 0, stream>>>(
             N, F, width, height, (const float4*)d_ff, d_seg_frame, d_cams, (const float4*)d_xyzb, (const float4*)d_scale_lo,
             (const float4*)d_rot, (const float4*)d_sh, (float4*)d_P0, (float4*)d_P1, (float4*)d_P2, d_tiles_touched,
-            d_depth_keys, kBindThreads, nullptr, nullptr, tiles);
+            d_depth_keys, S, kBindThreads, nullptr, nullptr, tiles);
     } else {
-        // blocks walk ~4096 Gaussians each (32 rounds): long enough that the counter flush (1024 + tiles global atomics
-        // per block) is ~0.5 per Gaussian, short enough that the grid is many waves of 128-thread blocks
         const size_t smem = sizeof(uint32_t) * (1024 + (size_t)tiles);
         if (smem > 200 * 1024) {
             set_error("bind_preprocess: %d tiles per frame exceed the fused tile counters", tiles);
@@ -219,13 +233,21 @@ int bind_preprocess_launch(int S, int N, int F, int width, int height, const flo
         static DeviceOnce once;
         int rc = ensure_dyn_smem(once, bind_preprocess_kernel<true>, (int)smem);
         if (rc) return rc;
-        int per_block = 32 * kBindThreads;
-        if (tiles > 1024) per_block = 64 * kBindThreads;
-        dim3 grid(ceil_div(N, per_block), S);
+        // one resident wave: as many blocks as fit the SMs (registers: 8 per SM; shared memory: the counters), each
+        // walking an equal share of the S*N pairs, but never less than 8 rounds per block (the counter flush is
+        // 1024 + tiles global atomics per piece)
+        int per_sm = 8;
+        const int by_smem = (int)((200 * 1024) / (smem + 1024));
+        if (per_sm > by_smem) per_sm = by_smem;
+        const long long total = (long long)S * N;
+        long long per_block = (total + (long long)kNumSMs * per_sm - 1) / ((long long)kNumSMs * per_sm);
+        per_block = (per_block + kBindThreads - 1) / kBindThreads * kBindThreads;
+        if (per_block < 8 * kBindThreads) per_block = 8 * kBindThreads;
+        dim3 grid(ceil_div(total, per_block), 1);
         bind_preprocess_kernel<true><<<grid, kBindThreads, smem, stream>>>(
             N, F, width, height, (const float4*)d_ff, d_seg_frame, d_cams, (const float4*)d_xyzb, (const float4*)d_scale_lo,
             (const float4*)d_rot, (const float4*)d_sh, (float4*)d_P0, (float4*)d_P1, (float4*)d_P2, d_tiles_touched,
-            d_depth_keys, per_block, d_hist_depth, d_tile_cnt, tiles);
+            d_depth_keys, S, (int)per_block, d_hist_depth, d_tile_cnt, tiles);
     }
     count_launch();
     OMFS_LAUNCH_CHECK();

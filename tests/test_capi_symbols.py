@@ -131,3 +131,15 @@ def test_the_product_never_touches_the_oracle():
         allowed |= {n.lineno for n in ast.walk(fn) if isinstance(n, (ast.Import, ast.ImportFrom))}
     lines = {ln for ln, _ in oracle_imports(os.path.join(root, "bench.py"))}
     assert lines and lines <= allowed, (lines, allowed)
+
+
+def test_alias_imports_share_one_module_object():
+    """`omfs_b200.<module>` (dotted) and `from omfs_b200 import <module>` must be the same object: a second copy of
+    runtime would carry its own library handle and its own OmfsError class."""
+    import importlib
+    import sys
+    import omfs_b200  # noqa: F401
+    from omfs_b200.runtime import OmfsError
+    from omfs_b200 import runtime
+    real = importlib.import_module("omfs-4d-video-gen_b200.runtime")
+    assert runtime is real and OmfsError is real.OmfsError and sys.modules["omfs_b200.runtime"] is real

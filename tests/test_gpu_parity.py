@@ -88,7 +88,8 @@ def test_full_chain_small(rt, small_scene, gemm_impl):
 def test_level1_stages_and_unsorted_keys(rt, small_scene):
     """Every level-1 entry point on caller-owned device memory, including the unsorted key list."""
     import oracle
-    from omfs_b200.runtime import DeviceArray as DA
+    from omfs_b200 import runtime as _rt
+    DA = _rt.DeviceArray
     model, params, av, baked, cam = small_scene
     W, H = cam.width, cam.height
     T, V, F, N = params.n_frames, model.n_verts, model.n_faces, baked["n"]
@@ -286,7 +287,8 @@ def test_blend_gemm_tensor_core_vs_cuda_core(rt):
     """U1+U2: both tcgen05 kernels (concatenated-K operands, impl 2; panel re-use, impl 3; impl 0 picks by size)
     against the fp32 CUDA-core kernel on the same operands, ragged M (T = 1, 130, 257, 1100) and a ragged last N
     tile (npad = 1024 + 128) so that TMA's out-of-bounds fill is exercised on every side."""
-    from omfs_b200.runtime import DeviceArray as DA
+    from omfs_b200 import runtime as _rt
+    DA = _rt.DeviceArray
     L = rt.load_library()
     rng = np.random.default_rng(0)
     kpad, npad = 136, 1024 + 128
@@ -322,7 +324,8 @@ def test_displace_points_masks_and_moves_bit_exact(rt, golden_dir):
     bit-exact against the float64 restatement (which is pinned to the reference by the goldens)."""
     import os
     from oracle import reference_rows as rr
-    from omfs_b200.runtime import DeviceArray as DA
+    from omfs_b200 import runtime as _rt
+    DA = _rt.DeviceArray
     L = rt.load_library()
     g = np.load(os.path.join(golden_dir, "surgical_sim_golden.npz"))
     pts = np.concatenate([g["maxilla"], g["mandible"]]).astype(np.float32)
