@@ -1,5 +1,6 @@
 // common.cuh — shared by every translation unit of libomfs_b200.so (sm_100a only).
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -86,7 +87,7 @@ int binning_emit_scatter(int S, int N, int width, int height, size_t capacity, c
                          const uint32_t* d_tiles_touched, uint32_t* d_sorted_vals, void* d_workspace,
                          cudaStream_t stream);
 int binning_rebuild_keys(int S, int N, int width, int height, size_t capacity, const uint32_t* d_ranges,
-                         const uint32_t* d_vals, const float* d_P0, uint64_t* d_keys64, void* d_workspace,
+                         const uint32_t* d_vals, const uint32_t* d_depth_keys, uint64_t* d_keys64, void* d_workspace,
                          cudaStream_t stream);
 
 // compositing (composite.cu) with an explicit number of persistent warps per SM (0 = fill the SM).  The
@@ -99,5 +100,31 @@ int composite_launch(int S, int N, int width, int height, const float* d_P0, con
 // read through the read-only path; outputs that the next kernel re-reads stay default-cached so
 // they can live in the 126 MB L2 between the kernels of one batch.
 __device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
+
+// ---- the pair list entry.  d_sorted_vals[i] = Gaussian index (low kValIndexBits bits: the parity surface) | a 4-bit
+// hint (top bits): bit (kValIndexBits + 2*yhalf + xhalf) is set when the Gaussian's alpha >= 1/255 footprint box
+// (centre +- the extents of P0.z) contains a pixel of that 8x8 block of the 16x16 tile.  The binning (emit_scatter) sets
+// the hints, the compositing warps skip list entries whose bit for their block is clear without touching the
+// Gaussian's records.  Conservative by construction of the extents (exact_geom.cu: pack_cull_extents).
+constexpr int kValIndexBits = 28;
+constexpr uint32_t kValIndexMask = (1u << kValIndexBits) - 1u;
+
+// the two half-precision extents packed in P0.z
+__device__ __forceinline__ void unpack_extents(float w, float& bx, float& by) {
+    const uint32_t u = __float_as_uint(w);
+    const __half2 h = *reinterpret_cast<const __half2*>(&u);
+    bx = __low2float(h);
+    by = __high2float(h);
+}
+
+// 8x8-block index range [bmin, bmax] of the integer pixels p with c - e <= p <= c + e (empty: bmin > bmax).
+// The float sums round like the compositing cull's own (1 ulp of a pixel coordinate against extents inflated by
+// 0.02 px); the clamps keep the conversions in range for infinite extents.
+__device__ __forceinline__ void block_range(float c, float e, int& bmin, int& bmax) {
+    const float lo = fminf(fmaxf(ceilf(c - e), -8.0f), 1048576.0f);
+    const float hi = fminf(fmaxf(floorf(c + e), -16.0f), 1048576.0f);
+    bmin = (int)lo >> 3;
+    bmax = (lo <= hi) ? ((int)hi >> 3) : -1048576;   // NaN or inverted: nothing
+}
 
 }  // namespace omfs

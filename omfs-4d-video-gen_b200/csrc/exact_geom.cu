@@ -17,13 +17,15 @@
 namespace omfs {
 
 // Conservative half-extents (pixels) of the region where a Gaussian can pass the compositing test
-// `power2 + lo >= log2(1/255)`, packed as two round-UP halves into P2.w.  With
+// `power2 + lo >= log2(1/255)`, packed as two round-UP halves into P0.z (the slot beside the centre and the radius:
+// the binning reads ONE record per Gaussian for the tile rectangle and the block hints, compositing one for the
+// centre and the cull box; the depth, which only the parity taps read back, rides in P2.w).  With
 // q(d) = -(ca dx^2 + cb dx dy + cc dy^2) and Lq = lo - log2(1/255), minimising q over dy gives
 // dx^2 <= Lq * (-cc) / (ca*cc - cb^2/4) (symmetrically for dy).  The extents are inflated (x1.002 +
 // 0.02 px, then rounded up to half precision), far more than the 1e-6 relative rounding of the
 // compositing arithmetic: the per-warp cull that consumes them can only skip pixels that would have
-// been skipped anyway.  P2.w is an acceleration hint, NOT part of the parity surface (the oracle
-// leaves it 0); a value of +inf means "always test", -inf "never contributes".
+// been skipped anyway.  P0.z is an acceleration hint, NOT part of the parity surface (the oracle
+// has no such field); a value of +inf means "always test", -inf "never contributes".
 __device__ __forceinline__ float pack_cull_extents(float ca, float cb, float cc, float lo) {
     const float Lq = lo - kLog2Inv255;
     const float D = ca * cc - 0.25f * cb * cb;
@@ -164,9 +166,9 @@ __global__ void __launch_bounds__(kBindThreads) bind_preprocess_kernel(
                     acc = acc + 0.5f;
                     rgb[c] = fmaxf(acc, 0.0f);
                 }
-                P0[oi] = make_float4(o.px, o.py, o.depth, __int_as_float(o.radius));
+                P0[oi] = make_float4(o.px, o.py, pack_cull_extents(o.ca, o.cb, o.cc, s.w), __int_as_float(o.radius));
                 P1[oi] = make_float4(o.ca, o.cb, o.cc, s.w);
-                P2[oi] = make_float4(rgb[0], rgb[1], rgb[2], pack_cull_extents(o.ca, o.cb, o.cc, s.w));
+                P2[oi] = make_float4(rgb[0], rgb[1], rgb[2], o.depth);
                 tiles_touched[oi] = o.tiles;
                 if (depth_keys) depth_keys[oi] = __float_as_uint(o.depth);  // sort key of the depth sort (binning.cu)
             }
