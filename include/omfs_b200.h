@@ -94,7 +94,10 @@ int omfs_face_frames(int T, int V, int F, const float* d_verts, const int32_t* d
 /* U5+U6 fused: parent-triangle transform of every Gaussian, then cull / project / EWA / SH.
  * One segment = one (frame, camera) pair; d_seg_frame[S] gives the frame of each segment and
  * d_cams[S,40] its camera.  Outputs are [S,N,4] float4 streams plus d_tiles_touched[S,N]:
- *   P0 = (px, py, depth, radius as int32 bits)  P1 = (ca, cb, cc, lo)  P2 = (r, g, b, 0)
+ *   P0 = (px, py, cull extents, radius as int32 bits)  P1 = (ca, cb, cc, lo)  P2 = (r, g, b, depth)
+ * (the published fields; the cull extents — two half-precision half-widths of the alpha >= 1/255 footprint box —
+ * are an acceleration hint outside the parity surface, placed beside the centre so that binning and compositing
+ * read one record for both)
  * and (optional) d_depth_keys[S,N] = the depth's float bits, 0 for culled Gaussians: the key of the
  * depth sort in omfs_binning. */
 int omfs_bind_preprocess(int S, int N, int F, int width, int height,
@@ -105,12 +108,15 @@ int omfs_bind_preprocess(int S, int N, int F, int width, int height,
 
 /* U7+U8+U9.  Result: the pair list of the batch ordered by the published key
  * ((seg*tiles+tile)<<32 | depth bits, ties by Gaussian index): d_sorted_vals[capacity] (Gaussian index
- * inside its segment) and d_ranges[S*tiles,2] (untouched tiles stay (0,0)).  Internally (binning.cu):
+ * inside its segment in the low OMFS_VAL_INDEX_BITS bits; the top four bits are block hints for omfs_composite:
+ * bit 2*yhalf + xhalf is set when the Gaussian's footprint box reaches that 8x8 pixel block of the pair's tile)
+ * and d_ranges[S*tiles,2] (untouched tiles stay (0,0)).  N <= 2^28 - 1.  Internally (binning.cu):
  * segmented onesweep depth sort of the Gaussians, per-tile counts and their scan, then one fused
  * emit + counting-sort-by-tile kernel that writes every index straight to its final position.
  * d_sorted_keys[capacity] (optional) receives the 64-bit keys in final order, for parity / debugging.
  * d_num_pairs (uint32 on device) receives the pair count; if it exceeds capacity nothing is emitted
  * and d_status_flag (int on device) is set to 1.  All scratch comes from d_workspace. */
+#define OMFS_VAL_INDEX_BITS 28
 size_t omfs_binning_workspace_bytes(int S, int N, int width, int height, size_t capacity);
 int omfs_binning(int S, int N, int width, int height, size_t capacity,
                  const float* d_P0, const uint32_t* d_depth_keys, const uint32_t* d_tiles_touched,
@@ -118,7 +124,8 @@ int omfs_binning(int S, int N, int width, int height, size_t capacity,
                  uint32_t* d_num_pairs, int* d_status_flag, void* d_workspace, size_t workspace_bytes,
                  void* stream);
 
-/* U10: front-to-back alpha compositing, one warp per 8x8 pixel block.  d_image[S,3,H,W];
+/* U10: front-to-back alpha compositing, one warp per 8x8 pixel block; a warp only fetches the list entries whose
+ * block hint (see omfs_binning) names its block.  d_image[S,3,H,W];
  * d_image_u8 (optional) [S,H,W,3] gets the save_image quantisation in the same kernel.
  * d_tickets (optional): OMFS_COMPOSITE_TICKET_BYTES of device memory, zero before its first use and not
  * shared by launches that may run concurrently; the kernel leaves it zeroed.  With it the launch is one

@@ -220,7 +220,7 @@ constexpr int kEsChunk = kEsThreads * kEsGpt;        // 1024 depth-ordered Gauss
 constexpr int kEsWin = 1024;                         // pairs per warp per window (up to 1024 tiles)
 constexpr int kEsWarps = kEsThreads / 32;
 
-// dynamic shared memory: pair[8][kEsWin] u32 | gidx[kEsChunk] u32 | base[tiles] u32 | wcnt[8][tiles] u16
+// dynamic shared memory: pair[8][kEsWin] u32 | gidx, bx, by [kEsChunk] u32 | base[tiles] u32 | wcnt[8][tiles] u16
 constexpr int kEsWinShift = 10;
 static_assert((1 << kEsWinShift) == kEsWin, "window size must match its shift");
 // Above 1024 tiles the per-tile arrays dominate the footprint (4096 tiles: 16 KB of bases + 64 KB of counters):
@@ -230,7 +230,7 @@ static inline int emit_scatter_win_shift(int tiles) { return tiles > 1024 ? kEsW
 static inline size_t emit_scatter_smem(int tiles) {
     const int tp = (tiles + 1) & ~1;  // even row stride: the packed 16-bit counters are updated as 32-bit words
     const int win = 1 << emit_scatter_win_shift(tiles);
-    return sizeof(uint32_t) * (kEsWarps * win + kEsChunk + tiles) + sizeof(uint16_t) * kEsWarps * tp + 64;
+    return sizeof(uint32_t) * (kEsWarps * win + 3 * kEsChunk + tiles) + sizeof(uint16_t) * kEsWarps * tp + 64;
 }
 
 template <int TILE_BITS>
@@ -246,7 +246,9 @@ __global__ void __launch_bounds__(kEsThreads) emit_scatter_kernel(
     constexpr int kWin = 1 << kWinShift;
     uint32_t* s_pair = reinterpret_cast<uint32_t*>(es_raw);            // [8][kWin]: tile << 10 | local Gaussian
     uint32_t* s_gidx = s_pair + kEsWarps * kWin;                       // [kEsChunk]
-    uint32_t* s_base = s_gidx + kEsChunk;                              // [tiles]
+    uint32_t* s_bx = s_gidx + kEsChunk;                                // [kEsChunk] 8x8-block columns the footprint reaches: min | max << 16
+    uint32_t* s_by = s_bx + kEsChunk;                                  // [kEsChunk] ... rows
+    uint32_t* s_base = s_by + kEsChunk;                                // [tiles]
     uint16_t* s_wcnt = reinterpret_cast<uint16_t*>(s_base + tiles);    // [8][tp]
     const int tp = (tiles + 1) & ~1;
     __shared__ uint32_t s_scan[8];
@@ -260,6 +262,12 @@ __global__ void __launch_bounds__(kEsThreads) emit_scatter_kernel(
     const uint32_t n_chunks = (uint32_t)cps * (uint32_t)S;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t lanemask_lt = (1u << lane) - 1u;
+    // t / gx for tile ids t < 2^18 as one multiply-high (exact while gx < 2^14)
+    const uint32_t gx_magic = 0xffffffffu / (uint32_t)gx + 1u;
+    // two bits: do blocks b0, b0 + 1 lie in [bmin, bmax]?  (an empty range is stored as min 0xffff, max 0)
+    auto half_bits = [](uint32_t b0, uint32_t bmin, uint32_t bmax) -> uint32_t {
+        return (uint32_t)(b0 >= bmin && b0 <= bmax) | ((uint32_t)(b0 + 1 >= bmin && b0 + 1 <= bmax) << 1);
+    };
 
     while (true) {
         // chunks are handed out in increasing order: every predecessor a chunk looks back at is owned
@@ -302,6 +310,15 @@ __global__ void __launch_bounds__(kEsThreads) emit_scatter_kernel(
             rw[q] = 1;
             if (li < n_g) {
                 s_gidx[li] = gq[q];
+                {   // block hint ranges (common.cuh: kValIndexBits): 8x8 blocks with a pixel inside centre +- extents
+                    float ex, ey;
+                    unpack_extents(pq[q].z, ex, ey);
+                    int b0, b1;
+                    block_range(pq[q].x, ex, b0, b1);
+                    s_bx[li] = (b1 < 0 || b0 > b1) ? 0xffffu : ((uint32_t)max(b0, 0) | ((uint32_t)min(b1, 0xffff) << 16));
+                    block_range(pq[q].y, ey, b0, b1);
+                    s_by[li] = (b1 < 0 || b0 > b1) ? 0xffffu : ((uint32_t)max(b0, 0) | ((uint32_t)min(b1, 0xffff) << 16));
+                }
                 int minx, miny, maxx, maxy;
                 ex_tile_rect(pq[q].x, pq[q].y, __float_as_int(pq[q].w), gx, gy, minx, miny, maxx, maxy);
                 const uint32_t t = (uint32_t)((maxx - minx) * (maxy - miny));
@@ -482,7 +499,15 @@ __global__ void __launch_bounds__(kEsThreads) emit_scatter_kernel(
                     wc[t] = (uint16_t)(pre + __popc(peers));
                 }
                 pre = __shfl_sync(0xffffffffu, pre, leader & 31);
-                if (valid) vals_out[s_base[t] + pre + __popc(peers & lanemask_lt)] = s_gidx[pr & 1023u];
+                if (valid) {
+                    // block hint of the pair: which halves of tile (tx, ty) the footprint's block range reaches
+                    const uint32_t li = pr & 1023u;
+                    const uint32_t ty = __umulhi(t, gx_magic), tx = t - ty * (uint32_t)gx;
+                    const uint32_t rx = s_bx[li], ry = s_by[li];
+                    const uint32_t hx = half_bits(2u * tx, rx & 0xffffu, rx >> 16), hy = half_bits(2u * ty, ry & 0xffffu, ry >> 16);
+                    const uint32_t hint = ((hy & 1u) ? hx : 0u) | ((hy & 2u) ? (hx << 2) : 0u);
+                    vals_out[s_base[t] + pre + __popc(peers & lanemask_lt)] = s_gidx[li] | (hint << kValIndexBits);
+                }
                 __syncwarp();
             }
         }
@@ -716,14 +741,13 @@ __global__ void __launch_bounds__(kRsThreads, 4) rs_onesweep_kernel(
 __global__ void __launch_bounds__(256) rebuild_keys_kernel(int N, int tiles, long long n_tiles_total,
                                                            const uint32_t* __restrict__ ranges,
                                                            const uint32_t* __restrict__ vals,
-                                                           const float4* __restrict__ P0,
+                                                           const uint32_t* __restrict__ depth_keys,
                                                            uint64_t* __restrict__ keys64) {
     for (long long tg = blockIdx.x; tg < n_tiles_total; tg += gridDim.x) {
         const uint32_t lo = ranges[2 * tg], hi = ranges[2 * tg + 1];
         const long long seg = tg / tiles;
         for (uint32_t i = lo + threadIdx.x; i < hi; i += blockDim.x) {
-            const float4 p = ldg4(P0 + seg * N + vals[i]);
-            keys64[i] = ((uint64_t)tg << 32) | (uint64_t)__float_as_uint(p.z);
+            keys64[i] = ((uint64_t)tg << 32) | (uint64_t)__ldg(depth_keys + seg * N + (vals[i] & kValIndexMask));
         }
     }
 }
@@ -868,8 +892,8 @@ int binning_emit_scatter(int S, int N, int width, int height, size_t capacity, c
                          const uint32_t* d_tiles_touched, uint32_t* d_sorted_vals, void* d_workspace,
                          cudaStream_t stream) {
     BinningWs w = carve(d_workspace, S, N, width, height, capacity);
-    if (w.tiles > (1 << 22)) {
-        set_error("binning: too many tiles per frame (%d)", w.tiles);
+    if (w.tiles > (1 << (kValIndexBits - 10)) || N > (int)kValIndexMask) {   // pair word: hint | tile | local Gaussian
+        set_error("binning: too many tiles per frame (%d) or Gaussians (%d)", w.tiles, N);
         return OMFS_ERR_INVALID;
     }
     int rc = set_kernel_attrs(w.tiles);
@@ -892,11 +916,11 @@ int binning_emit_scatter(int S, int N, int width, int height, size_t capacity, c
 }
 
 int binning_rebuild_keys(int S, int N, int width, int height, size_t capacity, const uint32_t* d_ranges,
-                         const uint32_t* d_vals, const float* d_P0, uint64_t* d_keys64, void* d_workspace,
+                         const uint32_t* d_vals, const uint32_t* d_depth_keys, uint64_t* d_keys64, void* d_workspace,
                          cudaStream_t stream) {
     BinningWs w = carve(d_workspace, S, N, width, height, capacity);
     rebuild_keys_kernel<<<kNumSMs * 8, 256, 0, stream>>>(N, w.tiles, (long long)S * w.tiles, d_ranges, d_vals,
-                                                         (const float4*)d_P0, d_keys64);
+                                                         d_depth_keys, d_keys64);
     count_launch();
     OMFS_LAUNCH_CHECK();
     return OMFS_OK;
@@ -939,7 +963,7 @@ extern "C" int omfs_binning(int S, int N, int width, int height, size_t capacity
                               stream);
     if (rc) return rc;
     if (d_sorted_keys)
-        rc = binning_rebuild_keys(S, N, width, height, capacity, d_ranges, d_sorted_vals, d_P0, d_sorted_keys,
+        rc = binning_rebuild_keys(S, N, width, height, capacity, d_ranges, d_sorted_vals, d_depth_keys, d_sorted_keys,
                                   d_workspace, stream);
     return rc;
 }

@@ -720,8 +720,8 @@ static int render_core(omfs_session* s, int T, int n_views, const float* p_expr,
             if ((rc = binning_emit_scatter(S, N, W, H, s->capacity, P0, s->tt.as<uint32_t>(), vals, s->ws.p, st)))
                 return rc;
             if (s->cfg.debug_keys &&
-                (rc = binning_rebuild_keys(S, N, W, H, s->capacity, ranges, vals, P0, s->keys64.as<uint64_t>(),
-                                           s->ws.p, st)))
+                (rc = binning_rebuild_keys(S, N, W, H, s->capacity, ranges, vals, s->depth_keys.as<uint32_t>(),
+                                           s->keys64.as<uint64_t>(), s->ws.p, st)))
                 return rc;
             // ---- compositing: on its own stream unless stage timing is on (then everything stays in order
             // on the caller's stream so that the event intervals mean one stage each)

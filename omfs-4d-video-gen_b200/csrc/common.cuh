@@ -106,7 +106,7 @@ __device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
 // (centre +- the extents of P0.z) contains a pixel of that 8x8 block of the 16x16 tile.  The binning (emit_scatter) sets
 // the hints, the compositing warps skip list entries whose bit for their block is clear without touching the
 // Gaussian's records.  Conservative by construction of the extents (exact_geom.cu: pack_cull_extents).
-constexpr int kValIndexBits = 28;
+constexpr int kValIndexBits = OMFS_VAL_INDEX_BITS;
 constexpr uint32_t kValIndexMask = (1u << kValIndexBits) - 1u;
 
 // the two half-precision extents packed in P0.z

@@ -58,13 +58,6 @@ struct Ex2Dev {
 //   * a skipped Gaussian gets alpha = 0 (then T*(1-0) == T and fma(c,0,C) == C bit for bit), so there is
 //     no per-entry divergence (no BSSY/BSYNC); a saturated pixel parks its transmittance in Tbg and goes
 //     on with T = -0; saturation is detected by one compare + vote per pair (see blend_pair).
-__device__ __forceinline__ void unpack_extents(float w, float& bx, float& by) {
-    const uint32_t u = __float_as_uint(w);
-    const __half2 h = *reinterpret_cast<const __half2*>(&u);
-    bx = __low2float(h);
-    by = __high2float(h);
-}
-
 #ifndef OMFS_COMP_WARPS
 #define OMFS_COMP_WARPS 1
 #endif
@@ -159,10 +152,25 @@ __device__ __forceinline__ void blend_pair(const float2 a0, const float2 a1, con
 }
 
 // A warp owns an 8x8 pixel block of its tile: lane l holds the two pixels (x, y) and (x, y + 4).  Two pixels
-// per lane halve the number of warps that walk a tile's list (per-entry gathers and cull) and the
-// shared-memory broadcasts per pixel evaluated — the L1/shared data pipe is the unit the one-pixel-per-lane
-// version saturated first (ncu l1tex__data_pipe_lsu_wavefronts 90 %) — and let the blend run packed.
+// per lane halve the number of warps that walk a tile's list and the shared-memory broadcasts per pixel evaluated
+// — the L1/shared data pipe is the unit the one-pixel-per-lane version saturated first (ncu
+// l1tex__data_pipe_lsu_wavefronts 90 %) — and let the blend run packed.
 constexpr int kBlocksPerTile = 4;  // 8x8 pixel blocks (warps) per 16x16 tile
+
+// The walk over the tile's list is in two levels, because most of it is not for this block: of the (entry, 8x8
+// block) combinations of the bench frame only 22 % pass the footprint test, so a walk that gathers every entry's
+// records to find that out spends more issue slots and L1 wavefronts on the 78 % than on evaluating the rest
+// (round-1 kernel: 43 % of its warp instructions outside the evaluation loop, 2 of 3 gathers for nothing).
+//   level 1  SCAN: the list word itself says whether the entry can reach this block (block hints set by the
+//            binning, common.cuh kValIndexBits).  128 entries per step: 4 coalesced loads, 4 ballots; the indices
+//            that pass go, in order, into a per-warp queue in shared memory.  No record is touched.
+//   level 2  ROUND: up to 32 queued indices, one per lane — every lane busy — gather centre/extents, conic, colour,
+//            are tested against the box of the block's LIVE pixels, and the survivors are compacted (still in depth
+//            order) into the pair slots the evaluation reads.
+// The loop is software-pipelined: the list words of the next scan step and the records of the next round are
+// requested before the current round is evaluated.
+constexpr int kQueueCap = 256;   // queued indices per warp (power of two)
+constexpr int kScanGroups = 4;   // 32-entry groups per scan step
 
 __global__ void OMFS_COMP_BOUNDS composite_kernel(int n_seg, int N, int width, int height, const float4* __restrict__ P0,
                                                        const float4* __restrict__ P1,
@@ -174,8 +182,10 @@ __global__ void OMFS_COMP_BOUNDS composite_kernel(int n_seg, int N, int width, i
                                                        unsigned long long* __restrict__ tickets) {
     // survivors of the current round, COMPACTED in depth order and stored as pairs (see kPairFloats)
     __shared__ float4 s_rec_all[kCompWarps][kPairSlots * 5];
+    __shared__ uint32_t s_queue_all[kCompWarps][kQueueCap];
     float4* s_rec = s_rec_all[threadIdx.x >> 5];
     float* s_f = reinterpret_cast<float*>(s_rec);
+    uint32_t* s_queue = s_queue_all[threadIdx.x >> 5];
 
     const int gxt = (width + kTile - 1) / kTile, gyt = (height + kTile - 1) / kTile;
     const int lane = threadIdx.x & 31;
@@ -190,23 +200,25 @@ __global__ void OMFS_COMP_BOUNDS composite_kernel(int n_seg, int N, int width, i
     // processed, so the atomic's latency is hidden); without one the grid has a CTA per unit and the
     // loop below runs once.  One CTA per unit leaves the SMs at ~72 % of their resident-warp limit (CTA
     // launch latency against ~20 us of work per unit) and pays the prologue once per unit.
-    const int units_per_seg = gxt * gyt * kBlocksPerTile;
-    const long long units_total = (long long)n_seg * units_per_seg;
-    const long long unit_stride = (long long)gridDim.x * kCompWarps;
-    auto draw = [&]() -> long long {
-        unsigned long long t = 0;
-        if (lane == 0) t = atomicAdd(tickets, 1ull);
-        return (long long)__shfl_sync(0xffffffffu, t, 0);
+    const uint32_t tiles_per_seg = (uint32_t)(gxt * gyt);
+    const uint32_t units_per_seg = tiles_per_seg * kBlocksPerTile;
+    // unit numbers are 32-bit: the launcher checks units_total + the grid's overshoot < 2^32
+    const uint32_t units_total = (uint32_t)n_seg * units_per_seg;
+    const uint32_t unit_stride = gridDim.x * kCompWarps;
+    auto draw = [&]() -> uint32_t {
+        uint32_t t = 0;
+        if (lane == 0) t = (uint32_t)atomicAdd(tickets, 1ull);
+        return __shfl_sync(0xffffffffu, t, 0);
     };
-    long long unit = (long long)blockIdx.x * kCompWarps + (threadIdx.x >> 5), unit_next = 0;
+    uint32_t unit = blockIdx.x * kCompWarps + (threadIdx.x >> 5), unit_next = 0;
     if (tickets) unit = draw();
     for (; unit < units_total; unit = unit_next) {
     unit_next = tickets ? draw() : unit + unit_stride;
-    const int seg = (int)(unit / units_per_seg), rem = (int)(unit % units_per_seg);
-    const int tile = rem / kBlocksPerTile, sub = rem % kBlocksPerTile;
-    const int bx0 = (tile % gxt) * kTile + (sub & 1) * 8;
-    const int by0 = (tile / gxt) * kTile + (sub >> 1) * 8;
-    if (bx0 >= width || by0 >= height) continue;  // pixel block entirely outside the image (cannot happen: tiles start inside)
+    const uint32_t seg = unit / units_per_seg, rem = unit - seg * units_per_seg;
+    const uint32_t tile = rem / kBlocksPerTile, sub = rem % kBlocksPerTile;
+    const uint32_t tyq = tile / (uint32_t)gxt;
+    const int bx0 = (int)(tile - tyq * (uint32_t)gxt) * kTile + (int)(sub & 1u) * 8;
+    const int by0 = (int)tyq * kTile + (int)(sub >> 1) * 8;
     const int pxi = bx0 + (lane & 7);
     const int pyi = by0 + (lane >> 3);
     const float2 npx = make_float2(-(float)pxi, -(float)pxi);
@@ -215,76 +227,76 @@ __global__ void OMFS_COMP_BOUNDS composite_kernel(int n_seg, int N, int width, i
     Pixels px;
     px.T = make_float2((pxi < width && pyi < height) ? 1.0f : -0.0f, (pxi < width && pyi + 4 < height) ? 1.0f : -0.0f);
     px.Tbg = px.C0 = px.C1 = px.C2 = make_float2(0.0f, 0.0f);
-#if OMFS_COMP_LIVE_BOX
+    // cull box = bounding box of the block's live pixels (OMFS_COMP_LIVE_BOX), else the whole block
     float wx0 = (float)bx0, wx1 = (float)(bx0 + 7), wy0 = (float)by0, wy1 = (float)(by0 + 7);
-#else
-    const float wx0 = (float)bx0, wx1 = (float)(bx0 + 7), wy0 = (float)by0, wy1 = (float)(by0 + 7);
-#endif
-    const uint2 range = ranges[(size_t)seg * (gxt * gyt) + tile];
-    const float4* p0 = P0 + (size_t)seg * N;
-    const float4* p1 = P1 + (size_t)seg * N;
-    const float4* p2 = P2 + (size_t)seg * N;
+    const uint2 range = ranges[(size_t)seg * tiles_per_seg + tile];
+    const uint32_t rec0 = seg * (uint32_t)N;   // first record of the segment (S*N < 2^31)
 
-    // Software pipeline, three rounds deep, so that no load is consumed in the iteration that issued it
-    // (index -> record -> conic are DEPENDENT gathers, each an L2 round trip):
-    //   iteration r:  publish round r (its conic was requested one iteration ago)
-    //                 cull round r+1 (its records were requested one iteration ago), request the survivors' conics
-    //                 request the records of round r+2 (its indices were requested one iteration ago)
-    //                 request the indices of round r+3
-    //                 evaluate round r from shared memory
-    // Entries past the end of the list read Gaussian 0 of the segment (harmless) and never hit.
     const int len = (int)(range.y - range.x);
-    const uint32_t* vp = vals + range.x + lane;
-    auto fetch_index = [&](int round) -> uint32_t { return (round * 32 + lane < len) ? __ldg(vp + round * 32) : 0u; };
-    auto cull = [&](const float4& a, const float4& c, int round) -> bool {
-        float ex, ey;
-        unpack_extents(c.w, ex, ey);
-        return (round * 32 + lane < len) & (a.x + ex >= wx0) & (a.x - ex <= wx1) & (a.y + ey >= wy0) & (a.y - ey <= wy1);
-    };
-    const int rounds = (len + 31) >> 5;
-    if (rounds > 0) {
-        // prologue
-        uint32_t g1 = fetch_index(0);
-        uint32_t g2 = fetch_index(1);
-        uint32_t g3 = fetch_index(2);
-        float4 a1 = ldg4(p0 + g1), c1 = ldg4(p2 + g1);
-        float4 a2 = ldg4(p0 + g2), c2 = ldg4(p2 + g2);
-        bool hit = cull(a1, c1, 0);
-        float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (hit) b = ldg4(p1 + g1);
-        uint32_t mask = __ballot_sync(0xffffffffu, hit);
-        float ax = a1.x, ay = a1.y, cr = c1.x, cg = c1.y, cb_ = c1.z;
-        // now: round 0 = (ax, ay, b, cr..), hit/mask;  (a2, c2) = records of round 1 (indices g2);  g3 = indices of round 2
-        for (int r = 0; r < rounds; r++) {
+    const int n_groups = (len + 31) >> 5;
+    const uint32_t vp = range.x + (uint32_t)lane;
+    const int hint_bit = kValIndexBits + (int)sub;
+    // list words of group g (entries past the end read as 0: no hint bit, never queued)
+    auto fetch_group = [&](int g) -> uint32_t { return (g * 32 + lane < len) ? __ldg(vals + (vp + (uint32_t)(g * 32))) : 0u; };
+
+    if (n_groups > 0) {
+        uint32_t w[kScanGroups];
+#pragma unroll
+        for (int k = 0; k < kScanGroups; k++) w[k] = fetch_group(k);
+        int scan_g = 0;                    // first group of the next scan step (its words are in w[])
+        uint32_t q_head = 0, q_tail = 0;   // queue positions popped / pushed so far (warp-uniform)
+        bool have = false, cand = false;   // a popped round's records are in (a, b, c); this lane holds a candidate
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a, c = a;
+        while (true) {
             bool parked = false;
-            // 1. publish round r
-            const int cnt = __popc(mask);
-            if (hit) {
-                const int s = __popc(mask & lanemask_lt);
-                const int h = s & 1;
-                float* d = s_f + (s >> 1) * kPairFloats + h;
-                d[0] = ax;
-                d[2] = ay;
-                d[4] = b.x;
-                d[6] = b.y;
-                d[8] = b.z;
-                d[10] = b.w;
-                *reinterpret_cast<float4*>(s_f + (s >> 1) * kPairFloats + 12 + 4 * h) = make_float4(cr, cg, cb_, 0.f);
-                if (s == cnt - 1 && h == 0) d[11] = __int_as_float(0xff800000);  // odd count: mute the partner
+            // 1. publish the popped round: live-box test, ballot, compaction into the pair slots
+            int cnt = 0;
+            if (have) {
+                float ex, ey;
+                unpack_extents(a.z, ex, ey);
+                const bool hit = cand & (a.x + ex >= wx0) & (a.x - ex <= wx1) & (a.y + ey >= wy0) & (a.y - ey <= wy1);
+                const uint32_t mask = __ballot_sync(0xffffffffu, hit);
+                cnt = __popc(mask);
+                if (hit) {
+                    const int s = __popc(mask & lanemask_lt);
+                    const int h = s & 1;
+                    float* d = s_f + (s >> 1) * kPairFloats + h;
+                    d[0] = a.x;
+                    d[2] = a.y;
+                    d[4] = b.x;
+                    d[6] = b.y;
+                    d[8] = b.z;
+                    d[10] = b.w;
+                    *reinterpret_cast<float4*>(s_f + (s >> 1) * kPairFloats + 12 + 4 * h) = make_float4(c.x, c.y, c.z, 0.f);
+                    if (s == cnt - 1 && h == 0) d[11] = __int_as_float(0xff800000);  // odd count: mute the partner
+                }
             }
-            // 2. cull round r+1 and request its survivors' conics
-            const bool hitn = cull(a2, c2, r + 1);
-            float4 bn = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (hitn) bn = ldg4(p1 + g2);
-            const uint32_t maskn = __ballot_sync(0xffffffffu, hitn);
-            const float axn = a2.x, ayn = a2.y, crn = c2.x, cgn = c2.y, cbn = c2.z;
-            // 3. request the records of round r+2 and the indices of round r+3
-            g2 = g3;
-            a2 = ldg4(p0 + g3);
-            c2 = ldg4(p2 + g3);
-            g3 = fetch_index(r + 3);
+            // 2. scan step: push the hinted entries of kScanGroups groups, request the next groups' words
+            if (scan_g < n_groups && q_tail - q_head <= (uint32_t)(kQueueCap - 32 * kScanGroups)) {
+#pragma unroll
+                for (int k = 0; k < kScanGroups; k++) {
+                    const bool in = (w[k] >> hint_bit) & 1u;
+                    const uint32_t m = __ballot_sync(0xffffffffu, in);
+                    if (in) s_queue[(q_tail + __popc(m & lanemask_lt)) & (kQueueCap - 1)] = w[k] & kValIndexMask;
+                    q_tail += __popc(m);
+                }
+                scan_g += kScanGroups;
+#pragma unroll
+                for (int k = 0; k < kScanGroups; k++) w[k] = fetch_group(scan_g + k);
+            }
             __syncwarp();
-            // 4. evaluate round r
+            // 3. pop the next round and request its records
+            const uint32_t take = min(q_tail - q_head, 32u);
+            have = take != 0u;
+            if (have) {
+                cand = (uint32_t)lane < take;
+                const uint32_t g = rec0 + (cand ? s_queue[(q_head + lane) & (kQueueCap - 1)] : 0u);
+                q_head += take;
+                a = ldg4(P0 + g);
+                b = ldg4(P1 + g);
+                c = ldg4(P2 + g);
+            }
+            // 4. evaluate the published round
             const int npairs = (cnt + 1) >> 1;
             const float4* rec = s_rec;
 #pragma unroll kCompUnroll
@@ -308,14 +320,14 @@ __global__ void OMFS_COMP_BOUNDS composite_kernel(int n_seg, int N, int width, i
                 blend_pair(a0, a1, rec[3], rec[4], px, parked);
             }
             __syncwarp();
-#if OMFS_COMP_LIVE_BOX
             if (parked) {  // only a round in which a pixel stopped can finish the block or shrink its live box
                 // bit l of m0 / m1: lane l's pixel (x, y) / (x, y + 4) is still live (sign bit of T clear)
                 const uint32_t m0 = __ballot_sync(0xffffffffu, (__float_as_uint(px.T.x) >> 31) == 0u);
                 const uint32_t m1 = __ballot_sync(0xffffffffu, (__float_as_uint(px.T.y) >> 31) == 0u);
                 if ((m0 | m1) == 0u) break;  // every pixel parked: the block is finished
-                // shrink the cull box to the live pixels (the cull of round r+1 above already ran with the previous,
-                // larger box: stale boxes stay conservative because pixels never come back)
+#if OMFS_COMP_LIVE_BOX
+                // shrink the cull box to the live pixels (a round popped before this point is tested against it at
+                // its publish; a stale, larger box would be just as correct: pixels never come back)
                 uint32_t cols = m0 | m1;
                 cols |= cols >> 16;
                 cols |= cols >> 8;
@@ -327,22 +339,9 @@ __global__ void OMFS_COMP_BOUNDS composite_kernel(int n_seg, int N, int width, i
                 wx1 = (float)(bx0 + xmax);
                 wy0 = (float)(by0 + ymin);
                 wy1 = (float)(by0 + ymax);
-            }
-#else
-            // both pixels parked (sign bits set) in every lane: the block is finished
-            const bool done = (__float_as_uint(px.T.x) & __float_as_uint(px.T.y)) >> 31;
-            if (cnt && __all_sync(0xffffffffu, done)) break;
-            (void)parked;
 #endif
-            // 5. rotate
-            hit = hitn;
-            mask = maskn;
-            b = bn;
-            ax = axn;
-            ay = ayn;
-            cr = crn;
-            cg = cgn;
-            cb_ = cbn;
+            }
+            if (!have && scan_g >= n_groups) break;  // list scanned, queue drained, last round evaluated
         }
     }
     const size_t hw = (size_t)width * height;
@@ -412,6 +411,7 @@ int composite_launch(int S, int N, int width, int height, const float* d_P0, con
     const long long ctas_all = (units + kCompWarps - 1) / kCompWarps;
     if (warps_per_sm <= 0 || warps_per_sm > OMFS_COMP_RESIDENT_WARPS) warps_per_sm = OMFS_COMP_RESIDENT_WARPS;
     const long long wave = (long long)kNumSMs * std::max(1, warps_per_sm / kCompWarps);  // persistent CTAs
+    OMFS_REQUIRE(units < (1ll << 32) - (1ll << 20), "too many work units for one launch");
     OMFS_REQUIRE(d_tickets || ctas_all < (1ll << 31), "too many work units for one launch without a ticket counter");
     const int grid = (int)((d_tickets && ctas_all > wave) ? wave : ctas_all);
     composite_kernel<<<grid, 32 * kCompWarps, 0, stream>>>(

@@ -339,6 +339,33 @@ class Session:
 
 
 # ---------------------------------------------------------------------------------------------
+# Layout of the per-Gaussian records and of the pair list as the kernels keep them (include/omfs_b200.h), against
+# the published fields the oracle restates:
+#   P0 = (px, py, cull extents [two halves, a hint], radius bits)   P2 = (r, g, b, depth)
+#   pair word = Gaussian index (low 28 bits) | block hints (top 4 bits)
+VAL_INDEX_BITS = 28
+VAL_INDEX_MASK = (1 << VAL_INDEX_BITS) - 1
+
+
+def published_records(P0: np.ndarray, P2: np.ndarray):
+    """(P0, P2) in the published field order — P0 = (px, py, depth, radius), P2 = (r, g, b, 0) — from the device
+    layout, plus the cull extents [..., 2] in pixels (the hint that sits in the device P0.z)."""
+    p0, p2 = P0.copy(), P2.copy()
+    p0[..., 2] = P2[..., 3]
+    p2[..., 3] = 0.0
+    ext = np.ascontiguousarray(P0[..., 2]).view(np.float16).reshape(P0.shape[:-1] + (2,)).astype(np.float32)
+    return p0, p2, ext
+
+
+def pair_indices(vals: np.ndarray) -> np.ndarray:
+    return vals & np.uint32(VAL_INDEX_MASK)
+
+
+def pair_hints(vals: np.ndarray) -> np.ndarray:
+    return vals >> np.uint32(VAL_INDEX_BITS)
+
+
+# ---------------------------------------------------------------------------------------------
 # device memory helpers through the library's own CUDA runtime (so numpy-only callers work)
 def memcpy_d2h(dst: np.ndarray, src_ptr: int):
     check(load_library().omfs_memcpy_d2h(dst.ctypes.data_as(c_void_p), c_void_p(src_ptr), dst.nbytes))

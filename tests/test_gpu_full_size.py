@@ -78,9 +78,9 @@ def test_sort_properties_full_size(full_scene):
     R = sess.dims()["pairs_last_batch"]
     N = baked["n"]
     keys = sess.tap_array("keys", (R,), np.uint64)
-    vals = sess.tap_array("vals", (R,), np.uint32)
+    vals = rt.pair_indices(sess.tap_array("vals", (R,), np.uint32))
     tt = sess.tap_array("tiles_touched", (S, N), np.uint32)
-    P0 = sess.tap_array("P0", (S, N, 4), np.float32)
+    P0 = rt.published_records(sess.tap_array("P0", (S, N, 4), np.float32), sess.tap_array("P2", (S, N, 4), np.float32))[0]
     assert int(tt.sum()) == R
     assert np.all(keys[1:] >= keys[:-1])
     assert vals.max() < N
@@ -166,7 +166,8 @@ def test_config4_multiview_1024_500k():
                   independent_chain_psnr_db=rr.psnr(img[segs] * 255.0, full.image * 255.0),
                   verts_max_abs_m=np.abs(verts - full.verts).max(), tile_pairs_per_image=pairs / S)
     # last batch = frame 1, all 16 views: preprocess outputs bit-exact for the sampled views of that frame
-    P0 = sess.tap_array("P0", (n_views, N, 4), np.float32)
+    P0 = rt.published_records(sess.tap_array("P0", (n_views, N, 4), np.float32),
+                              sess.tap_array("P2", (n_views, N, 4), np.float32))[0]
     tt = sess.tap_array("tiles_touched", (n_views, N), np.uint32)
     for k, (f, v) in enumerate(sample):
         if f != 1:
@@ -177,7 +178,7 @@ def test_config4_multiview_1024_500k():
     R = sess.dims()["pairs_last_batch"]
     assert int(tt.sum()) == R
     keys = sess.tap_array("keys", (R,), np.uint64)
-    vals = sess.tap_array("vals", (R,), np.uint32)
+    vals = rt.pair_indices(sess.tap_array("vals", (R,), np.uint32))
     tiles = (W // 16) * (H // 16)
     ranges = sess.tap_array("ranges", (n_views * tiles, 2), np.uint32).astype(np.int64)
     assert np.all(keys[1:] >= keys[:-1])

@@ -47,6 +47,47 @@ def assert_independent_image_parity(img, full_image):
     assert float(diff.max()) < 1.0 / 255.0 * 2.0 + TOL, float(diff.max())
 
 
+def check_block_hints(hints, ref, ext, W, H):
+    """The 4-bit block hints of the pair list (top bits of every pair word; bit 2*yhalf + xhalf = that 8x8 block of
+    the pair's tile): (1) CONSERVATIVE — a block with a pixel whose exponent reaches log2(1/255), evaluated in
+    float64 from the oracle's records, always has its bit set; (2) they ARE the footprint box, recomputed here from
+    the centre and the extents tap in integer pixel ranges; (3) they do cull (well under all-ones)."""
+    gx = (W + 15) // 16
+    tiles = gx * ((H + 15) // 16)
+    keys = ref.binned.sorted_keys
+    tg = (keys >> np.uint64(32)).astype(np.int64)
+    seg, tile = tg // tiles, tg % tiles
+    g = ref.binned.sorted_values.astype(np.int64)
+    P0 = ref.pre.P0[seg, g].astype(np.float64)
+    P1 = ref.pre.P1[seg, g].astype(np.float64)
+    e = ext[seg, g].astype(np.float32)
+    cx, cy = ref.pre.P0[seg, g, 0], ref.pre.P0[seg, g, 1]
+    bx0, by0 = (tile % gx) * 16, (tile // gx) * 16
+    want_box = np.zeros(len(g), np.uint32)
+    need = np.zeros(len(g), np.uint32)
+    xs = np.arange(8)
+    for sub in range(4):
+        x0, y0 = bx0 + 8 * (sub & 1), by0 + 8 * (sub >> 1)
+        # (2) integer pixels p with c - e <= p <= c + e (float32 sums, as on the device), intersected with the block
+        lo_x, hi_x = np.ceil((cx - e[:, 0]).astype(np.float32)), np.floor((cx + e[:, 0]).astype(np.float32))
+        lo_y, hi_y = np.ceil((cy - e[:, 1]).astype(np.float32)), np.floor((cy + e[:, 1]).astype(np.float32))
+        box = (np.maximum(lo_x, x0) <= np.minimum(hi_x, x0 + 7)) & (np.maximum(lo_y, y0) <= np.minimum(hi_y, y0 + 7))
+        want_box |= box.astype(np.uint32) << np.uint32(sub)
+        # (1) exact footprint on the block's pixels inside the image
+        px = (x0[:, None] + xs[None, :]).astype(np.float64)
+        py = (y0[:, None] + xs[None, :]).astype(np.float64)
+        dx = P0[:, 0, None] - px
+        dy = P0[:, 1, None] - py
+        ee = (P1[:, 3, None, None] + P1[:, 0, None, None] * dx[:, None, :] ** 2 + P1[:, 1, None, None] * dx[:, None, :] * dy[:, :, None]
+              + P1[:, 2, None, None] * dy[:, :, None] ** 2)
+        inside = (px[:, None, :] < W) & (py[:, :, None] < H)
+        reach = ((ee >= np.log2(1.0 / 255.0)) & inside).any(axis=(1, 2))
+        need |= reach.astype(np.uint32) << np.uint32(sub)
+    assert np.array_equal(hints, want_box)
+    assert not (need & ~hints).any()
+    assert np.unpackbits(hints.astype(np.uint8)).sum() < 0.8 * 4 * len(hints)
+
+
 def run_session(rt, model, params, baked, cams, W, H, max_batch, gemm_impl=0, plan_offset=None, **kw):
     sess = rt.Session(model, baked, W, H, max_batch=max_batch, gemm_impl=gemm_impl, debug_keys=True, **kw)
     sess.set_subject(params.shape, params.static_offset, plan_offset)
@@ -67,17 +108,20 @@ def test_full_chain_small(rt, small_scene, gemm_impl):
     ref = oracle.render(model, params, baked, [cam.pack()] * T, W, H, verts=verts)
     # exact domain, bit for bit
     assert np.array_equal(bits(sess.tap_array("ff", (T, F, 20), np.float32)), bits(ref.ff))
-    assert np.array_equal(bits(sess.tap_array("P0", (T, N, 4), np.float32)), bits(ref.pre.P0))
+    P0, P2, ext = rt.published_records(sess.tap_array("P0", (T, N, 4), np.float32), sess.tap_array("P2", (T, N, 4), np.float32))
+    assert np.array_equal(bits(P0), bits(ref.pre.P0))
     assert np.array_equal(bits(sess.tap_array("P1", (T, N, 4), np.float32)), bits(ref.pre.P1))
-    assert np.array_equal(bits(sess.tap_array("P2", (T, N, 4), np.float32)[..., :3]), bits(ref.pre.P2[..., :3]))  # .w = cull hint
+    assert np.array_equal(bits(P2), bits(ref.pre.P2))
     assert np.array_equal(sess.tap_array("tiles_touched", (T, N), np.uint32), ref.pre.tiles_touched)
     R = ref.binned.n_pairs
     assert sess.dims()["pairs_last_batch"] == R == sess.stats()["pairs"]
     assert np.array_equal(sess.tap_array("depth_keys", (T, N), np.uint32), ref.pre.P0[..., 2].view(np.uint32))
     assert np.array_equal(sess.tap_array("keys", (R,), np.uint64), ref.binned.sorted_keys)
-    assert np.array_equal(sess.tap_array("vals", (R,), np.uint32), ref.binned.sorted_values)
+    vals = sess.tap_array("vals", (R,), np.uint32)
+    assert np.array_equal(rt.pair_indices(vals), ref.binned.sorted_values)
     tiles = ((W + 15) // 16) * ((H + 15) // 16)
     assert np.array_equal(sess.tap_array("ranges", (T * tiles, 2), np.uint32), ref.binned.ranges)
+    check_block_hints(rt.pair_hints(vals), ref, ext, W, H)
     # images
     assert np.abs(img - ref.image).max() <= 2e-4
     assert_independent_image_parity(img, full.image)
@@ -110,7 +154,7 @@ def test_level1_stages_and_unsorted_keys(rt, small_scene):
     rt.check(L.omfs_bind_preprocess(S, N, F, W, H, d_ff.ptr, d_seg.ptr, d_cams.ptr, d_b["xyzb"].ptr,
                                     d_b["scale_lo"].ptr, d_b["rot"].ptr, d_b["sh"].ptr, d_P[0].ptr, d_P[1].ptr,
                                     d_P[2].ptr, d_tt.ptr, None, None))
-    assert np.array_equal(bits(d_P[0].numpy()), bits(ref.pre.P0))
+    assert np.array_equal(bits(rt.published_records(d_P[0].numpy(), d_P[2].numpy())[0]), bits(ref.pre.P0))
     assert np.array_equal(d_tt.numpy(), ref.pre.tiles_touched)
     # Gaussian -> triangle indices ride through the baked stream untouched
     from omfs_b200 import avatar as avatar_mod
@@ -138,7 +182,7 @@ def test_level1_stages_and_unsorted_keys(rt, small_scene):
     # the sorted list: bit-exact keys, values and ranges.  (The multiset of emitted pairs is implied:
     # the oracle's sorted list IS its emitted list, stably sorted.)
     assert np.array_equal(d_keys.numpy()[:R], ref.binned.sorted_keys)
-    assert np.array_equal(d_vals.numpy()[:R], ref.binned.sorted_values)
+    assert np.array_equal(rt.pair_indices(d_vals.numpy()[:R]), ref.binned.sorted_values)
     assert np.array_equal(d_ranges.numpy(), ref.binned.ranges)
     assert np.array_equal(np.sort(ref.binned.keys), ref.binned.sorted_keys)
 
@@ -198,7 +242,7 @@ def test_ragged_batches_views_and_odd_image_size(rt):
     assert np.abs(img - ref.image).max() <= 2e-4
     assert_independent_image_parity(img, full.image)
     # last batch = frame 4, two views
-    P0 = sess.tap_array("P0", (2, 3001, 4), np.float32)
+    P0 = rt.published_records(sess.tap_array("P0", (2, 3001, 4), np.float32), sess.tap_array("P2", (2, 3001, 4), np.float32))[0]
     assert np.array_equal(bits(P0), bits(ref.pre.P0[8:]))
     sess.close()
 
@@ -256,10 +300,11 @@ def test_degenerate_gaussians_on_device(rt, small_scene):
         ref = oracle.render(model, one, baked, [cam.pack()], W, H, verts=verts)
     N = baked["n"]
     assert np.array_equal(sess.tap_array("tiles_touched", (1, N), np.uint32), ref.pre.tiles_touched)
-    assert np.array_equal(bits(sess.tap_array("P0", (1, N, 4), np.float32)), bits(ref.pre.P0))
+    P0 = rt.published_records(sess.tap_array("P0", (1, N, 4), np.float32), sess.tap_array("P2", (1, N, 4), np.float32))[0]
+    assert np.array_equal(bits(P0), bits(ref.pre.P0))
     R = ref.binned.n_pairs
     assert np.array_equal(sess.tap_array("keys", (R,), np.uint64), ref.binned.sorted_keys)
-    assert np.array_equal(sess.tap_array("vals", (R,), np.uint32), ref.binned.sorted_values)
+    assert np.array_equal(rt.pair_indices(sess.tap_array("vals", (R,), np.uint32)), ref.binned.sorted_values)
     assert np.isfinite(img).all() and np.abs(img - ref.image).max() <= 2e-4
     sess.close()
 
