@@ -151,6 +151,28 @@ __device__ __forceinline__ void blend_pair(const float2 a0, const float2 a1, con
     p.T = Tn;
 }
 
+// Can the Gaussian (centre gx, gy; conic + log2 opacity in cn = (ca, cb, cc, lo), pre-scaled as in ex_blend) reach
+// alpha >= 1/255 anywhere in the pixel box [x0, x1] x [y0, y1]?  The exponent e = lo + q(dx, dy) is a concave
+// quadratic with its maximum at the centre, so over a box that does not contain the centre the maximum lies on one of
+// the (at most two) edges facing the centre: along the segment from the centre to any point of the box q only
+// decreases, and the segment enters the box through such an edge.  On an edge q is a parabola in one variable: its
+// vertex, clamped to the edge, is the exact maximum.  Both candidates are points of the box, so the larger of the two
+// values is the maximum (and never more).  The test is an acceleration hint outside the parity surface: the division
+// is approximate and the threshold is relaxed by 0.02 (the exponent is in log2 units: 1.4 % in alpha, against
+// arithmetic that is good to ~1e-5), so it can only keep an entry too many; a form that is not negative definite
+// (never produced by the preprocess for finite inputs) is always kept.
+__device__ __forceinline__ bool reaches_box(float gx, float gy, const float4& cn, float x0, float x1, float y0, float y1) {
+    const float dx0 = gx - x1, dx1 = gx - x0, dy0 = gy - y1, dy1 = gy - y0;   // dx = gx - px over the box
+    const float xs = fminf(fmaxf(0.0f, dx0), dx1), ys = fminf(fmaxf(0.0f, dy0), dy1);   // box point nearest the centre
+    const float hb = -0.5f * cn.y;
+    const float dyb = fminf(fmaxf(__fdividef(hb, cn.z) * xs, dy0), dy1);   // vertex of q(xs, .) on the edge dx = xs
+    const float dxb = fminf(fmaxf(__fdividef(hb, cn.x) * ys, dx0), dx1);   // vertex of q(., ys) on the edge dy = ys
+    const float q1 = fmaf(fmaf(cn.z, dyb, cn.y * xs), dyb, (cn.x * xs) * xs);
+    const float q2 = fmaf(fmaf(cn.x, dxb, cn.y * ys), dxb, (cn.z * ys) * ys);
+    const bool concave = cn.x * cn.z - 0.25f * (cn.y * cn.y) > 0.0f;
+    return !concave | (cn.w + fmaxf(q1, q2) >= kLog2Inv255 - 0.02f);
+}
+
 // A warp owns an 8x8 pixel block of its tile: lane l holds the two pixels (x, y) and (x, y + 4).  Two pixels
 // per lane halve the number of warps that walk a tile's list and the shared-memory broadcasts per pixel evaluated
 // — the L1/shared data pipe is the unit the one-pixel-per-lane version saturated first (ncu
@@ -212,11 +234,23 @@ __global__ void OMFS_COMP_BOUNDS composite_kernel(int n_seg, int N, int width, i
     };
     uint32_t unit = blockIdx.x * kCompWarps + (threadIdx.x >> 5), unit_next = 0;
     if (tickets) unit = draw();
+    // a warp's units only increase, by about one wave per draw: the segment is tracked by stepping (a 32-bit
+    // division costs ~25 issue slots per unit), the tile row by a float reciprocal that is exact for tiles < 2^18
+    uint32_t seg = 0, seg_unit0 = 0;   // current segment and its first unit
+    const float inv_gxt = 1.0f / (float)gxt;
     for (; unit < units_total; unit = unit_next) {
     unit_next = tickets ? draw() : unit + unit_stride;
-    const uint32_t seg = unit / units_per_seg, rem = unit - seg * units_per_seg;
+    if (unit - seg_unit0 >= 8u * units_per_seg) {
+        seg = unit / units_per_seg;
+        seg_unit0 = seg * units_per_seg;
+    }
+    while (unit - seg_unit0 >= units_per_seg) {
+        seg_unit0 += units_per_seg;
+        seg++;
+    }
+    const uint32_t rem = unit - seg_unit0;
     const uint32_t tile = rem / kBlocksPerTile, sub = rem % kBlocksPerTile;
-    const uint32_t tyq = tile / (uint32_t)gxt;
+    const uint32_t tyq = (uint32_t)(((float)tile + 0.5f) * inv_gxt);
     const int bx0 = (int)(tile - tyq * (uint32_t)gxt) * kTile + (int)(sub & 1u) * 8;
     const int by0 = (int)tyq * kTile + (int)(sub >> 1) * 8;
     const int pxi = bx0 + (lane & 7);
@@ -252,9 +286,7 @@ __global__ void OMFS_COMP_BOUNDS composite_kernel(int n_seg, int N, int width, i
             // 1. publish the popped round: live-box test, ballot, compaction into the pair slots
             int cnt = 0;
             if (have) {
-                float ex, ey;
-                unpack_extents(a.z, ex, ey);
-                const bool hit = cand & (a.x + ex >= wx0) & (a.x - ex <= wx1) & (a.y + ey >= wy0) & (a.y - ey <= wy1);
+                const bool hit = cand & reaches_box(a.x, a.y, b, wx0, wx1, wy0, wy1);
                 const uint32_t mask = __ballot_sync(0xffffffffu, hit);
                 cnt = __popc(mask);
                 if (hit) {
@@ -412,6 +444,7 @@ int composite_launch(int S, int N, int width, int height, const float* d_P0, con
     if (warps_per_sm <= 0 || warps_per_sm > OMFS_COMP_RESIDENT_WARPS) warps_per_sm = OMFS_COMP_RESIDENT_WARPS;
     const long long wave = (long long)kNumSMs * std::max(1, warps_per_sm / kCompWarps);  // persistent CTAs
     OMFS_REQUIRE(units < (1ll << 32) - (1ll << 20), "too many work units for one launch");
+    OMFS_REQUIRE(tiles <= (1 << (kValIndexBits - 10)), "too many tiles per frame");
     OMFS_REQUIRE(d_tickets || ctas_all < (1ll << 31), "too many work units for one launch without a ticket counter");
     const int grid = (int)((d_tickets && ctas_all > wave) ? wave : ctas_all);
     composite_kernel<<<grid, 32 * kCompWarps, 0, stream>>>(
