@@ -196,6 +196,7 @@ struct omfs_session {
     cudaEvent_t ev_pre = nullptr, ev_scan = nullptr;
     bool fuse_front = true;   // OMFS_FUSE_FRONT=0: the separate histogram / tile-count kernels (A/B, debugging)
     bool last_batch_full = true;   // OMFS_COMP_LAST_FULL=0: the last batch keeps the pipelined warp count (A/B)
+    int comp_pipelined_warps = kCompPipelinedWarps;   // OMFS_COMP_PIPE_WARPS=n: compositing warps per SM beside a front end (A/B)
     cudaEvent_t ev_done[2]{}, ev_copied[2]{}, ev_front[2]{}, ev_comp[2]{};
     bool ev_comp_pending[2]{};
     bool subject_set = false;
@@ -383,6 +384,8 @@ extern "C" int omfs_session_create(const omfs_model_desc* m, const omfs_session_
         s->fuse_front = !(e && e[0] == '0');
         e = getenv("OMFS_COMP_LAST_FULL");
         s->last_batch_full = !(e && e[0] == '0');
+        e = getenv("OMFS_COMP_PIPE_WARPS");
+        if (e && atoi(e) > 0 && atoi(e) <= 32) s->comp_pipelined_warps = atoi(e);
     }
     for (int i = 0; i < 2; i++) {
         TRY_CUDA(cudaEventCreateWithFlags(&s->ev_done[i], cudaEventDisableTiming));
@@ -754,7 +757,7 @@ static int render_core(omfs_session* s, int T, int n_views, const float* p_expr,
             // whole SM.
             const bool last_batch = (g0 + gT >= T) && (bi + 1 == sizes.size());
             if ((rc = composite_launch(S, N, W, H, P0, P1, P2, vals, ranges, s->cfg.bg, dst_f, dst_8, s->tickets.p,
-                                       (pipelined && !(last_batch && s->last_batch_full)) ? kCompPipelinedWarps : 0, cst)))
+                                       (pipelined && !(last_batch && s->last_batch_full)) ? s->comp_pipelined_warps : 0, cst)))
                 return rc;
             if ((rc = mark(-1))) return rc;
             if (pipelined) {
