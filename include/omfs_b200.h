@@ -248,6 +248,15 @@ int omfs_session_render_host_png(omfs_session* s, const omfs_frames_desc* frames
 int omfs_session_render_device(omfs_session* s, const omfs_frames_desc* d_frames,
                                uint8_t* d_out_u8, float* d_out_f32, void* stream);
 
+/* Streaming callers (one clip after another, or one frame block per step): with the deferred join on,
+ * omfs_session_render_device returns without making `stream` wait for the call's last compositing launch, so the
+ * next call's front end overlaps it exactly as the batches inside one call overlap.  The caller orders its own
+ * consumers with omfs_session_join(s, consumer_stream): that stream then waits for every compositing launch
+ * enqueued so far (it may be the rendering stream itself, or e.g. the stream that pushes the frames to a peer).
+ * Host-output calls always join.  Off by default: then every call is complete in stream order, as documented. */
+int omfs_session_set_deferred_join(omfs_session* s, int on);
+int omfs_session_join(omfs_session* s, void* stream);
+
 /* Counters of the last render call: [0] tile pairs (whole call), [1] kernel launches, [2] batches,
  * [3] overflow flag.  Valid after omfs_session_render_host / omfs_session_sync. */
 int omfs_session_stats(omfs_session* s, uint64_t* out4);

@@ -196,6 +196,8 @@ struct omfs_session {
     cudaEvent_t ev_pre = nullptr, ev_scan = nullptr;
     bool fuse_front = true;   // OMFS_FUSE_FRONT=0: the separate histogram / tile-count kernels (A/B, debugging)
     bool last_batch_full = true;   // OMFS_COMP_LAST_FULL=0: the last batch keeps the pipelined warp count (A/B)
+    bool defer_join = false;       // omfs_session_set_deferred_join: device-output calls leave their compositing un-joined
+    int set_parity = 0;            // deferred join: buffer set the next call starts with (the other one may still composite)
     int comp_pipelined_warps = kCompPipelinedWarps;   // OMFS_COMP_PIPE_WARPS=n: compositing warps per SM beside a front end (A/B)
     cudaEvent_t ev_done[2]{}, ev_copied[2]{}, ev_front[2]{}, ev_comp[2]{};
     bool ev_comp_pending[2]{};
@@ -621,6 +623,11 @@ static int render_core(omfs_session* s, int T, int n_views, const float* p_expr,
     };
 
     int batch_index = 0;
+    // Deferred join (device output only): this call's last compositing launch may still run when the next call's
+    // front end starts, so the next call begins with the OTHER buffer set, and the last batch keeps the pipelined
+    // occupancy (a front end will run beside it).
+    const bool deferred = s->defer_join && !out_on_host;
+    const int parity0 = deferred ? s->set_parity : 0;
     for (int g0 = 0; g0 < T; g0 += geo) {
         const int gT = std::min(geo, T - g0);
         // ---- FLAME: operand prep, blendshape GEMM (tensor cores), skinning
@@ -671,7 +678,7 @@ static int render_core(omfs_session* s, int T, int n_views, const float* p_expr,
         for (size_t bi = 0; bi < sizes.size(); b0 += sizes[bi], bi++) {
             const int bT = sizes[bi];
             const int S = bT * n_views;
-            const int ib = batch_index & 1;
+            const int ib = (batch_index + parity0) & 1;
             // the buffer set `ib` is free once the compositing of two batches ago has read it
             if (s->ev_comp_pending[ib]) {
                 OMFS_CUDA(cudaStreamWaitEvent(st, s->ev_comp[ib], 0));
@@ -757,7 +764,7 @@ static int render_core(omfs_session* s, int T, int n_views, const float* p_expr,
             // whole SM.
             const bool last_batch = (g0 + gT >= T) && (bi + 1 == sizes.size());
             if ((rc = composite_launch(S, N, W, H, P0, P1, P2, vals, ranges, s->cfg.bg, dst_f, dst_8, s->tickets.p,
-                                       (pipelined && !(last_batch && s->last_batch_full)) ? s->comp_pipelined_warps : 0, cst)))
+                                       (pipelined && !(last_batch && s->last_batch_full && !deferred)) ? s->comp_pipelined_warps : 0, cst)))
                 return rc;
             if ((rc = mark(-1))) return rc;
             if (pipelined) {
@@ -810,12 +817,18 @@ static int render_core(omfs_session* s, int T, int n_views, const float* p_expr,
     if (png)
         for (int k = 0; k < omfs_session::kPngRing; k++)
             if ((rc = png_drain(s, (batch_index + k) % omfs_session::kPngRing, png))) return rc;
-    // everything this call launched is complete when the caller's stream is: join the compositing stream
-    for (int ib = 0; ib < 2; ib++)
-        if (s->ev_comp_pending[ib]) {
-            OMFS_CUDA(cudaStreamWaitEvent(st, s->ev_comp[ib], 0));
-            s->ev_comp_pending[ib] = false;
-        }
+    // everything this call launched is complete when the caller's stream is: join the compositing stream — unless
+    // the caller asked to join by itself (omfs_session_join), so that consecutive calls overlap like the batches
+    // of one call do
+    if (deferred) {
+        s->set_parity = (parity0 + batch_index) & 1;
+    } else {
+        for (int ib = 0; ib < 2; ib++)
+            if (s->ev_comp_pending[ib]) {
+                OMFS_CUDA(cudaStreamWaitEvent(st, s->ev_comp[ib], 0));
+                s->ev_comp_pending[ib] = false;
+            }
+    }
     s->stats[1] = g_launches - launches0;
     s->stats[2] = (uint64_t)batch_index;
     return OMFS_OK;
@@ -1022,6 +1035,30 @@ extern "C" int omfs_session_sync(omfs_session* s) {
 }
 
 extern "C" void* omfs_session_stream(omfs_session* s) { return s ? (void*)s->stream : nullptr; }
+
+extern "C" int omfs_session_set_deferred_join(omfs_session* s, int on) {
+    OMFS_REQUIRE(s, "null argument");
+    OMFS_CUDA(cudaSetDevice(s->cfg.device));
+    if (!on && s->defer_join) {   // leaving the mode: whatever is still compositing is joined on the last caller stream
+        for (int ib = 0; ib < 2; ib++)
+            if (s->ev_comp_pending[ib]) {
+                OMFS_CUDA(cudaStreamWaitEvent(s->user_stream, s->ev_comp[ib], 0));
+                s->ev_comp_pending[ib] = false;
+            }
+        s->set_parity = 0;
+    }
+    s->defer_join = on != 0;
+    return OMFS_OK;
+}
+
+extern "C" int omfs_session_join(omfs_session* s, void* stream) {
+    OMFS_REQUIRE(s, "null argument");
+    OMFS_CUDA(cudaSetDevice(s->cfg.device));
+    // the flags stay set: the rendering stream itself has not waited, and the next call must before it reuses a set
+    for (int ib = 0; ib < 2; ib++)
+        if (s->ev_comp_pending[ib]) OMFS_CUDA(cudaStreamWaitEvent((cudaStream_t)stream, s->ev_comp[ib], 0));
+    return OMFS_OK;
+}
 
 extern "C" int omfs_session_stats(omfs_session* s, uint64_t* out4) {
     OMFS_REQUIRE(s && out4, "null argument");

@@ -84,17 +84,43 @@ constexpr int kPairSlots = 16;  // 32 survivors per round = 16 pairs
 constexpr int kPairFloats = 20;
 
 // alpha of one Gaussian at one pixel: min(0.99, 2^e), or 0 when ex_blend would skip it.
-// keep = (e >= log2(1/255)) && (e <= lo) is the complement of ex_blend's skip test (no NaNs reach this
-// point); spelled in PTX so the two compares chain into ONE predicate and one select.
+// keep = (e >= log2(1/255)) && (e <= lo) is the complement of ex_blend's skip test (a NaN exponent fails the first
+// compare); spelled in PTX so the two compares chain into ONE predicate and one select.
+// GUARD = false drops the `e <= lo` half (the published `power > 0` rejection).  That is only allowed for Gaussians
+// for which it can never fire — see well_conditioned() below — and saves one of the five issue slots.
+template <bool GUARD>
 __device__ __forceinline__ float alpha_of(float e, float lo) {
     float alpha = fminf(0.99f, ex2_approx(e));
-    asm("{\n\t.reg .pred p, q;\n\t"
-        "setp.le.f32 q, %1, %2;\n\t"
-        "setp.ge.and.f32 p, %1, %3, q;\n\t"
-        "selp.f32 %0, %0, 0f00000000, p;\n\t}"
-        : "+f"(alpha)
-        : "f"(e), "f"(lo), "f"(kLog2Inv255));
+    if (GUARD) {
+        asm("{\n\t.reg .pred p, q;\n\t"
+            "setp.le.f32 q, %1, %2;\n\t"
+            "setp.ge.and.f32 p, %1, %3, q;\n\t"
+            "selp.f32 %0, %0, 0f00000000, p;\n\t}"
+            : "+f"(alpha)
+            : "f"(e), "f"(lo), "f"(kLog2Inv255));
+    } else {
+        asm("{\n\t.reg .pred p;\n\t"
+            "setp.ge.f32 p, %1, %2;\n\t"
+            "selp.f32 %0, %0, 0f00000000, p;\n\t}"
+            : "+f"(alpha)
+            : "f"(e), "f"(kLog2Inv255));
+    }
     return alpha;
+}
+
+// When can `e > lo` (ex_blend's rejection of a positive power) never happen?  With A = ca dx^2, B = cb dx dy,
+// C = cc dy^2 and q = A + B + C <= -lmin r^2 (lmin, lmax: the eigenvalues of the scaled conic, r^2 = dx^2 + dy^2),
+// ex_blend computes c0 = RN(lo + A(1 + d1)) <= lo and e = RN(s dy + c0) with s dy = B + C + eta, |eta| <= 2 eps M,
+// M = (|ca| + |cc|) r^2 <= 2 lmax r^2.  Since lo - c0 >= |A|(1 - eps) - ulp(lo)/2, the exact sum before the last
+// rounding satisfies  s dy + c0 - lo <= q + ulp(lo)/2 + 3 eps M;  e > lo needs that sum to reach lo + ulp(lo)/2,
+// i.e. q + 3 eps M >= 0, i.e. lmin / lmax <= 6 eps = 3.6e-7.  lmin / lmax >= D / tr^2 (D = ca cc - cb^2/4 = lmin lmax,
+// tr = ca + cc, |tr| >= lmax); the kernel asks for D > 1e-4 tr^2 in float arithmetic (whose error in D is below
+// 1e-7 tr^2): two and a half orders of magnitude of margin.  Every Gaussian of a trained avatar qualifies (the EWA
+// dilation of 0.3 px^2 bounds the conic's condition by radius^2 / 2.7); a round that holds one that does not is
+// evaluated by the guarded loop.
+__device__ __forceinline__ bool well_conditioned(const float4& cn) {
+    const float tr = cn.x + cn.z;
+    return cn.x * cn.z - 0.25f * (cn.y * cn.y) > 1.0e-4f * (tr * tr);
 }
 
 // State of the lane's two pixels (x, y) and (x, y + 4), packed so that the blend runs as f32x2 instructions
@@ -171,6 +197,32 @@ __device__ __forceinline__ bool reaches_box(float gx, float gy, const float4& cn
     const float q2 = fmaf(fmaf(cn.x, dxb, cn.y * ys), dxb, (cn.z * ys) * ys);
     const bool concave = cn.x * cn.z - 0.25f * (cn.y * cn.y) > 0.0f;
     return !concave | (cn.w + fmaxf(q1, q2) >= kLog2Inv255 - 0.02f);
+}
+
+// The published round: npairs pair slots in shared memory onto the lane's two pixels.
+template <bool GUARD>
+__device__ __forceinline__ void evaluate_round(const float4* rec, int npairs, const float2 npx, const float2 npy0,
+                                               const float2 npy1, Pixels& px, bool& parked) {
+#pragma unroll kCompUnroll
+    for (int j = 0; j < npairs; j++, rec += 5) {
+        const float4 q0 = rec[0], q1 = rec[1], q2 = rec[2];
+        // exact_math.cuh::ex_blend's sequence, both Gaussians of the pair per instruction.  The column
+        // terms (dx, c0 = lo + ca dx dx, v = cb dx) are shared by the lane's two pixels (same x).
+        const float2 lo = make_float2(q2.z, q2.w);
+        const float2 dx = __fadd2_rn(make_float2(q0.x, q0.y), npx);
+        const float2 u = __fmul2_rn(make_float2(q1.x, q1.y), dx);
+        const float2 c0 = __ffma2_rn(u, dx, lo);
+        const float2 v = __fmul2_rn(make_float2(q1.z, q1.w), dx);
+        auto exponent = [&](const float2 npy) -> float2 {
+            const float2 dy = __fadd2_rn(make_float2(q0.z, q0.w), npy);
+            const float2 sd = __ffma2_rn(make_float2(q2.x, q2.y), dy, v);
+            return __ffma2_rn(sd, dy, c0);
+        };
+        const float2 ea = exponent(npy0), eb = exponent(npy1);
+        const float2 a0 = make_float2(alpha_of<GUARD>(ea.x, lo.x), alpha_of<GUARD>(eb.x, lo.x));  // Gaussian 0 at both pixels
+        const float2 a1 = make_float2(alpha_of<GUARD>(ea.y, lo.y), alpha_of<GUARD>(eb.y, lo.y));  // Gaussian 1
+        blend_pair(a0, a1, rec[3], rec[4], px, parked);
+    }
 }
 
 // A warp owns an 8x8 pixel block of its tile: lane l holds the two pixels (x, y) and (x, y + 4).  Two pixels
@@ -285,9 +337,11 @@ __global__ void OMFS_COMP_BOUNDS composite_kernel(int n_seg, int N, int width, i
             bool parked = false;
             // 1. publish the popped round: live-box test, ballot, compaction into the pair slots
             int cnt = 0;
+            bool guard = false;   // (warp-uniform) the round holds a Gaussian that needs ex_blend's `e <= lo` test
             if (have) {
                 const bool hit = cand & reaches_box(a.x, a.y, b, wx0, wx1, wy0, wy1);
                 const uint32_t mask = __ballot_sync(0xffffffffu, hit);
+                guard = __any_sync(0xffffffffu, hit && !well_conditioned(b));
                 cnt = __popc(mask);
                 if (hit) {
                     const int s = __popc(mask & lanemask_lt);
@@ -329,28 +383,10 @@ __global__ void OMFS_COMP_BOUNDS composite_kernel(int n_seg, int N, int width, i
                 c = ldg4(P2 + g);
             }
             // 4. evaluate the published round
-            const int npairs = (cnt + 1) >> 1;
-            const float4* rec = s_rec;
-#pragma unroll kCompUnroll
-            for (int j = 0; j < npairs; j++, rec += 5) {
-                const float4 q0 = rec[0], q1 = rec[1], q2 = rec[2];
-                // exact_math.cuh::ex_blend's sequence, both Gaussians of the pair per instruction.  The column
-                // terms (dx, c0 = lo + ca dx dx, v = cb dx) are shared by the lane's two pixels (same x).
-                const float2 lo = make_float2(q2.z, q2.w);
-                const float2 dx = __fadd2_rn(make_float2(q0.x, q0.y), npx);
-                const float2 u = __fmul2_rn(make_float2(q1.x, q1.y), dx);
-                const float2 c0 = __ffma2_rn(u, dx, lo);
-                const float2 v = __fmul2_rn(make_float2(q1.z, q1.w), dx);
-                auto exponent = [&](const float2 npy) -> float2 {
-                    const float2 dy = __fadd2_rn(make_float2(q0.z, q0.w), npy);
-                    const float2 sd = __ffma2_rn(make_float2(q2.x, q2.y), dy, v);
-                    return __ffma2_rn(sd, dy, c0);
-                };
-                const float2 ea = exponent(npy0), eb = exponent(npy1);
-                const float2 a0 = make_float2(alpha_of(ea.x, lo.x), alpha_of(eb.x, lo.x));  // Gaussian 0 at both pixels
-                const float2 a1 = make_float2(alpha_of(ea.y, lo.y), alpha_of(eb.y, lo.y));  // Gaussian 1
-                blend_pair(a0, a1, rec[3], rec[4], px, parked);
-            }
+            if (guard)
+                evaluate_round<true>(s_rec, (cnt + 1) >> 1, npx, npy0, npy1, px, parked);
+            else
+                evaluate_round<false>(s_rec, (cnt + 1) >> 1, npx, npy0, npy1, px, parked);
             __syncwarp();
             if (parked) {  // only a round in which a pixel stopped can finish the block or shrink its live box
                 // bit l of m0 / m1: lane l's pixel (x, y) / (x, y + 4) is still live (sign bit of T clear)

@@ -83,6 +83,8 @@ def load_library():
     L.omfs_png_encode.argtypes = [c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_size_t,
                                   c_void_p]
     L.omfs_session_sync.argtypes = [c_void_p]
+    L.omfs_session_set_deferred_join.argtypes = [c_void_p, c_int]
+    L.omfs_session_join.argtypes = [c_void_p, c_void_p]
     L.omfs_session_reserve_pairs.argtypes = [c_void_p, c_uint64]
     L.omfs_session_stats.argtypes = [c_void_p, POINTER(c_uint64)]
     L.omfs_session_tap.argtypes = [c_void_p, c_char_p, POINTER(c_void_p), POINTER(c_size_t)]
@@ -297,6 +299,15 @@ class Session:
 
     def sync(self):
         check(self._L.omfs_session_sync(self._h))
+
+    def set_deferred_join(self, on: bool = True):
+        """render_device calls stop joining their last compositing launch into the caller's stream, so consecutive
+        calls overlap; order consumers with join(stream)."""
+        check(self._L.omfs_session_set_deferred_join(self._h, 1 if on else 0))
+
+    def join(self, stream=0):
+        """`stream` waits for every compositing launch enqueued so far."""
+        check(self._L.omfs_session_join(self._h, stream or None))
 
     @property
     def stream(self) -> int:

@@ -284,6 +284,39 @@ def test_tapered_multi_batch_call_and_dense_opaque_splats(rt):
     sess.close()
 
 
+def test_needle_splats_take_the_guarded_loop(rt):
+    """Long thin splats (one axis x150, the others /8): their conics are badly conditioned (D <= 1e-4 tr^2), which is
+    when the compositing kernel may NOT drop ex_blend's `e <= lo` rejection — rounds that hold one run the guarded
+    loop (composite.cu: well_conditioned).  A third of the avatar is needles, so guarded and unguarded rounds both
+    decide pixels; the frame must match the oracle on the same vertices like any other."""
+    import omfs_b200  # noqa: F401
+    import oracle
+    from omfs_b200 import avatar, synthetic
+    W, H, T = 160, 112, 3
+    model = synthetic.make_flame_model(seed=31, n_verts=642)
+    params = synthetic.make_frame_params(T, seed=32, n_verts=642)
+    av = synthetic.make_avatar(4000, model.n_faces, seed=33)
+    needles = np.arange(av.scaling.shape[0]) % 3 == 0
+    av.scaling[needles, 0] += np.float32(np.log(150.0))
+    av.scaling[needles, 1:] -= np.float32(np.log(8.0))
+    baked = avatar.bake(av)
+    cam = synthetic.make_camera(W, H)
+    sess, u8, img = run_session(rt, model, params, baked, [cam], W, H, max_batch=T)
+    verts = sess.tap_array("verts", (T, 642, 3), np.float32)
+    ref = oracle.render(model, params, baked, [cam.pack()] * T, W, H, verts=verts)
+    P1 = ref.pre.P1.astype(np.float64)
+    vis = ref.pre.tiles_touched > 0
+    D = P1[..., 0] * P1[..., 2] - 0.25 * P1[..., 1] ** 2
+    tr = P1[..., 0] + P1[..., 2]
+    ill = vis & (D <= 1e-4 * tr * tr)
+    assert ill.sum() > 100 and (vis & ~ill).sum() > 100, (int(ill.sum()), int(vis.sum()))
+    assert np.abs(img - ref.image).max() <= 2e-4
+    assert (oracle.to_uint8(ref.image) != u8).mean() < 1e-4
+    R = ref.binned.n_pairs
+    assert np.array_equal(rt.pair_indices(sess.tap_array("vals", (R,), np.uint32)), ref.binned.sorted_values)
+    sess.close()
+
+
 def test_degenerate_gaussians_on_device(rt, small_scene):
     """NaN / infinite / absurd Gaussians (tests/test_exact_math_host.py::_degenerate_avatar): the device culls exactly
     the ones the oracle culls (tiles touched, P0 bit for bit), never blends the NaN-opacity one, and the frame is
