@@ -317,6 +317,53 @@ def test_needle_splats_take_the_guarded_loop(rt):
     sess.close()
 
 
+def test_deferred_join_overlaps_calls_without_changing_a_bit(rt):
+    """Streaming use (bench.py's step loop): with the deferred join on, render_device returns without joining its
+    last compositing launch, so calls overlap on the device; join(stream) orders a consumer.  Seven back-to-back
+    calls of an odd number of batches each (the buffer sets alternate ACROSS calls) into different outputs must
+    give, frame for frame, what synchronous calls give."""
+    import omfs_b200  # noqa: F401
+    from omfs_b200 import avatar, synthetic
+    T, W, H = 10, 128, 96
+    model, params, av, cam = synthetic.make_scene(n_gauss=5000, n_frames=T, width=W, height=H, n_verts=642)
+    baked = avatar.bake(av)
+    DA = rt.DeviceArray
+    d_cam = DA.from_numpy(cam.pack()[None])
+
+    def ptrs_of(p):
+        d = {k: DA.from_numpy(np.ascontiguousarray(getattr(p, k), dtype=np.float32))
+             for k in ("expr", "rotation", "neck_pose", "jaw_pose", "eyes_pose", "translation")}
+        out = {k: v.ptr for k, v in d.items()}
+        out["cams"] = d_cam.ptr
+        return d, out
+
+    clips = [params.slice(i % 2, T) for i in range(7)]   # two different clips, alternating
+    held = [ptrs_of(c) for c in clips]
+    sess = rt.Session(model, baked, W, H, max_batch=3)   # 9 or 10 frames in batches of 3: several batches per call
+    sess.set_subject(params.shape, params.static_offset)
+    want = []
+    for c, (_, ptrs) in zip(clips, held):
+        out = DA((c.n_frames, H, W, 3), np.uint8)
+        sess.render_device(ptrs, c.n_frames, 1, d_out_u8=out.ptr)
+        sess.sync()
+        want.append(out.numpy())
+    assert len(want[0]) == 10 and len(want[1]) == 9 and np.array_equal(want[0][1:], want[1])
+    sess.set_deferred_join(True)
+    outs = [DA((c.n_frames, H, W, 3), np.uint8) for c in clips]
+    for c, (_, ptrs), out in zip(clips, held, outs):
+        sess.render_device(ptrs, c.n_frames, 1, d_out_u8=out.ptr)
+    sess.join()
+    sess.sync()
+    for got, ref in zip(outs, want):
+        assert np.array_equal(got.numpy(), ref)
+    sess.set_deferred_join(False)                        # back to joined calls
+    out = DA((clips[0].n_frames, H, W, 3), np.uint8)
+    sess.render_device(held[0][1], clips[0].n_frames, 1, d_out_u8=out.ptr)
+    sess.sync()
+    assert np.array_equal(out.numpy(), want[0])
+    sess.close()
+
+
 def test_degenerate_gaussians_on_device(rt, small_scene):
     """NaN / infinite / absurd Gaussians (tests/test_exact_math_host.py::_degenerate_avatar): the device culls exactly
     the ones the oracle culls (tiles touched, P0 bit for bit), never blends the NaN-opacity one, and the frame is
