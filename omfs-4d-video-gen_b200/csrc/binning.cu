@@ -227,6 +227,9 @@ static_assert((1 << kEsWinShift) == kEsWin, "window size must match its shift");
 // with 1024-pair windows a CTA needs 119 KB and only ONE fits an SM (ncu: 12.5 % occupancy, issue slots 36 %
 // busy).  Halving the windows brings it to 103 KB, two CTAs per SM, at the price of a second expansion pass.
 static inline int emit_scatter_win_shift(int tiles) { return tiles > 1024 ? kEsWinShift - 1 : kEsWinShift; }
+// Up to 1024 tiles a CTA needs 65.6 KB: three CTAs take 195.3 KB, just inside the 196 KB shared-memory carve-out, which
+// leaves 60 KB of L1 for the record gathers.  ONE more KB per CTA selects the 228 KB carve-out (28 KB of L1) and costs
+// the kernel 25 % (measured: 0.336 -> 0.417 ms per 60 frames).  Anything added here must be paid for elsewhere.
 static inline size_t emit_scatter_smem(int tiles) {
     const int tp = (tiles + 1) & ~1;  // even row stride: the packed 16-bit counters are updated as 32-bit words
     const int win = 1 << emit_scatter_win_shift(tiles);

@@ -1031,6 +1031,10 @@ extern "C" int omfs_session_sync(omfs_session* s) {
     OMFS_CUDA(cudaStreamSynchronize(s->user_stream));
     OMFS_CUDA(cudaStreamSynchronize(s->stream));
     OMFS_CUDA(cudaStreamSynchronize(s->copy_stream));
+    // with the deferred join the compositing stream is not joined into the caller's: wait for it here
+    if (s->comp_stream) OMFS_CUDA(cudaStreamSynchronize(s->comp_stream));
+    if (s->defer_join)
+        for (int ib = 0; ib < 2; ib++) s->ev_comp_pending[ib] = false;
     return finish_stats(s);
 }
 
