@@ -220,47 +220,49 @@ constexpr int kEsChunk = kEsThreads * kEsGpt;        // 1024 depth-ordered Gauss
 constexpr int kEsWin = 1024;                         // pairs per warp per window (up to 1024 tiles)
 constexpr int kEsWarps = kEsThreads / 32;
 
-// dynamic shared memory: pair[8][kEsWin] u32 | gidx, bx, by [kEsChunk] u32 | base[tiles] u32 | wcnt[8][tiles] u16
+// dynamic shared memory: pair[8][kEsWin] u32 | gidx, bx, by [kEsChunk] u32 | base[band tiles] u32 | wcnt[8][band tiles] u16
 constexpr int kEsWinShift = 10;
 static_assert((1 << kEsWinShift) == kEsWin, "window size must match its shift");
-// Above 1024 tiles the per-tile arrays dominate the footprint (4096 tiles: 16 KB of bases + 64 KB of counters):
-// with 1024-pair windows a CTA needs 119 KB and only ONE fits an SM (ncu: 12.5 % occupancy, issue slots 36 %
-// busy).  Halving the windows brings it to 103 KB, two CTAs per SM, at the price of a second expansion pass.
-static inline int emit_scatter_win_shift(int tiles) { return tiles > 1024 ? kEsWinShift - 1 : kEsWinShift; }
-// Up to 1024 tiles a CTA needs 65.6 KB: three CTAs take 195.3 KB, just inside the 196 KB shared-memory carve-out, which
-// leaves 60 KB of L1 for the record gathers.  ONE more KB per CTA selects the 228 KB carve-out (28 KB of L1) and costs
-// the kernel 25 % (measured: 0.336 -> 0.417 ms per 60 frames).  Anything added here must be paid for elsewhere.
-static inline size_t emit_scatter_smem(int tiles) {
-    const int tp = (tiles + 1) & ~1;  // even row stride: the packed 16-bit counters are updated as 32-bit words
-    const int win = 1 << emit_scatter_win_shift(tiles);
-    return sizeof(uint32_t) * (kEsWarps * win + 3 * kEsChunk + tiles) + sizeof(uint16_t) * kEsWarps * tp + 64;
+// The per-tile arrays (bases, per-warp counters: 20 B per tile) never cover more than kEsBandTiles tiles: a frame with
+// more tiles is processed in BANDS of whole tile rows (1024^2: 4 bands of 16 rows x 64 tiles).  A CTA loads its
+// chunk's Gaussians once and runs count / publish / look-back / rank / scatter once per band on the rectangles clipped
+// to the band.  Round 1 sized the arrays for the whole frame instead: at 4096 tiles 115 KB per CTA (two CTAs per SM,
+// 28 KB of L1), 512-pair windows, rectangles walked three times — 15 issue slots per pair against 10 at 1024 tiles.
+constexpr int kEsBandTiles = 1024;
+static inline int emit_scatter_band_rows(int gx, int gy) { return std::min(gy, std::max(1, kEsBandTiles / gx)); }
+// Up to 1024 tiles per band a CTA needs 65.6 KB: three CTAs take 195.3 KB, just inside the 196 KB shared-memory carve-out,
+// which leaves 60 KB of L1 for the record gathers.  ONE more KB per CTA selects the 228 KB carve-out (28 KB of L1) and
+// costs the kernel 25 % (measured: 0.336 -> 0.417 ms per 60 frames).  Anything added here must be paid for elsewhere.
+static inline size_t emit_scatter_smem(int band_tiles) {
+    const int tp = (band_tiles + 1) & ~1;  // even row stride: the packed 16-bit counters are updated as 32-bit words
+    return sizeof(uint32_t) * (kEsWarps * kEsWin + 3 * kEsChunk + band_tiles) + sizeof(uint16_t) * kEsWarps * tp + 64;
 }
 
-template <int TILE_BITS>
 __global__ void __launch_bounds__(kEsThreads) emit_scatter_kernel(
-    int S, int N, int width, int height, int tiles, const uint32_t* __restrict__ perm_a,
+    int S, int N, int width, int height, int tiles, int band_rows, const uint32_t* __restrict__ perm_a,
     const uint32_t* __restrict__ perm_b, const uint32_t* __restrict__ perm_select,
     const uint32_t* __restrict__ tt, const float4* __restrict__ P0, const uint32_t* __restrict__ tile_start,
     const uint32_t* __restrict__ sort_count, uint32_t* __restrict__ chunk_counter,
     volatile uint32_t* __restrict__ status /*[chunks][tiles]*/, uint32_t* __restrict__ vals_out) {
     extern __shared__ __align__(16) unsigned char es_raw[];
-    // window size of this instantiation (see emit_scatter_win_shift)
-    constexpr int kWinShift = TILE_BITS > 10 ? kEsWinShift - 1 : kEsWinShift;
-    constexpr int kWin = 1 << kWinShift;
-    uint32_t* s_pair = reinterpret_cast<uint32_t*>(es_raw);            // [8][kWin]: tile << 10 | local Gaussian
+    constexpr int kWinShift = kEsWinShift;
+    constexpr int kWin = kEsWin;
+    constexpr int TILE_BITS = 10;   // band-local tile ids < kEsBandTiles: one ballot per bit in the ranking
+    uint32_t* s_pair = reinterpret_cast<uint32_t*>(es_raw);            // [8][kWin]: band-local tile << 10 | local Gaussian
     uint32_t* s_gidx = s_pair + kEsWarps * kWin;                       // [kEsChunk]
     uint32_t* s_bx = s_gidx + kEsChunk;                                // [kEsChunk] 8x8-block columns the footprint reaches: min | max << 16
     uint32_t* s_by = s_bx + kEsChunk;                                  // [kEsChunk] ... rows
-    uint32_t* s_base = s_by + kEsChunk;                                // [tiles]
-    uint16_t* s_wcnt = reinterpret_cast<uint16_t*>(s_base + tiles);    // [8][tp]
-    const int tp = (tiles + 1) & ~1;
+    const int gx = (width + kTile - 1) / kTile, gy = (height + kTile - 1) / kTile;
+    const int band_tiles = band_rows * gx;                             // <= kEsBandTiles (checked by the launcher)
+    uint32_t* s_base = s_by + kEsChunk;                                // [band_tiles]
+    uint16_t* s_wcnt = reinterpret_cast<uint16_t*>(s_base + band_tiles);  // [8][tp]
+    const int tp = (band_tiles + 1) & ~1;
     __shared__ uint32_t s_scan[8];
     __shared__ uint32_t s_chunk;
 
     if (*sort_count == 0) return;  // empty batch, or overflow (flagged by tile_scan_kernel)
     // the depth sort ends in perm_a, or in perm_b when its last pass was skipped as trivial
     const uint32_t* __restrict__ perm = (*perm_select) ? perm_b : perm_a;
-    const int gx = (width + kTile - 1) / kTile, gy = (height + kTile - 1) / kTile;
     const int cps = (N + kEsChunk - 1) / kEsChunk;  // chunks per segment
     const uint32_t n_chunks = (uint32_t)cps * (uint32_t)S;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -294,10 +296,9 @@ __global__ void __launch_bounds__(kEsThreads) emit_scatter_kernel(
         // then the record gathers, are issued as independent batches (two dependent round trips per chunk
         // instead of one chain per Gaussian); the pair count is the area of the rectangle, which is what
         // the preprocess stored in tiles_touched (a culled Gaussian has radius 0 at (0,0): area 0).
-        int rminx[kEsGpt], rminy[kEsGpt], rw[kEsGpt];
-        uint32_t cnt[kEsGpt], gq[kEsGpt];
+        int rminx[kEsGpt], rw[kEsGpt], fminy[kEsGpt], fmaxy[kEsGpt];   // the whole rectangle: columns, width, rows
+        uint32_t gq[kEsGpt];
         float4 pq[kEsGpt];
-        uint32_t acc = 0;
 #pragma unroll
         for (int q = 0; q < kEsGpt; q++) {
             const int li = threadIdx.x * kEsGpt + q;
@@ -308,8 +309,7 @@ __global__ void __launch_bounds__(kEsThreads) emit_scatter_kernel(
 #pragma unroll
         for (int q = 0; q < kEsGpt; q++) {
             const int li = threadIdx.x * kEsGpt + q;
-            cnt[q] = 0;
-            rminx[q] = rminy[q] = 0;
+            rminx[q] = fminy[q] = fmaxy[q] = 0;
             rw[q] = 1;
             if (li < n_g) {
                 s_gidx[li] = gq[q];
@@ -324,14 +324,27 @@ __global__ void __launch_bounds__(kEsThreads) emit_scatter_kernel(
                 }
                 int minx, miny, maxx, maxy;
                 ex_tile_rect(pq[q].x, pq[q].y, __float_as_int(pq[q].w), gx, gy, minx, miny, maxx, maxy);
-                const uint32_t t = (uint32_t)((maxx - minx) * (maxy - miny));
-                if (t) {
+                if ((maxx - minx) * (maxy - miny) > 0) {
                     rminx[q] = minx;
-                    rminy[q] = miny;
                     rw[q] = maxx - minx;
-                    cnt[q] = t;
+                    fminy[q] = miny;
+                    fmaxy[q] = maxy;
                 }
             }
+        }
+        // ---- one band of tile rows at a time (a frame of up to kEsBandTiles tiles is one band)
+        for (int y0 = 0; y0 < gy; y0 += band_rows) {
+        const int y1 = min(gy, y0 + band_rows);
+        const int nt = (y1 - y0) * gx;             // tiles of this band
+        const int tile_lo = y0 * gx;               // its first tile in the frame's numbering
+        int rminy[kEsGpt];                         // first row of the clipped rectangle, band-local
+        uint32_t cnt[kEsGpt];                      // pairs of the clipped rectangle
+        uint32_t acc = 0;
+#pragma unroll
+        for (int q = 0; q < kEsGpt; q++) {
+            const int cy0 = max(fminy[q], y0), cy1 = min(fmaxy[q], y1);
+            rminy[q] = cy0 - y0;
+            cnt[q] = cy1 > cy0 ? (uint32_t)((cy1 - cy0) * rw[q]) : 0u;
             acc += cnt[q];
         }
         uint32_t total_pairs;
@@ -416,8 +429,8 @@ __global__ void __launch_bounds__(kEsThreads) emit_scatter_kernel(
         // ---- per tile: offsets of the warps inside the chunk and the chunk aggregate.  EVERY aggregate of the
         // chunk is published before any look-back starts, so a successor never waits for a tile whose owner
         // thread is still busy looking back for an earlier one.
-        volatile uint32_t* my_status = status + (size_t)chunk * tiles;
-        for (int t = threadIdx.x; t < tiles; t += kEsThreads) {
+        volatile uint32_t* my_status = status + (size_t)chunk * tiles + tile_lo;
+        for (int t = threadIdx.x; t < nt; t += kEsThreads) {
             uint32_t off = 0;
 #pragma unroll
             for (int w = 0; w < kEsWarps; w++) {
@@ -431,7 +444,7 @@ __global__ void __launch_bounds__(kEsThreads) emit_scatter_kernel(
         // ---- look-back, kEsLook tiles per thread at a time: the probes of a batch are independent loads, so a
         // thread pays one round trip per batch and step, not one per tile (at 4096 tiles a thread owns 16)
         constexpr int kEsLook = 4;
-        for (int t0 = threadIdx.x; t0 < tiles; t0 += kEsThreads * kEsLook) {
+        for (int t0 = threadIdx.x; t0 < nt; t0 += kEsThreads * kEsLook) {
             uint32_t excl[kEsLook], look[kEsLook];
             bool pend[kEsLook];
             bool any = false;
@@ -439,7 +452,7 @@ __global__ void __launch_bounds__(kEsThreads) emit_scatter_kernel(
             for (int g = 0; g < kEsLook; g++) {
                 excl[g] = 0;
                 look[g] = chunk - 1;
-                pend[g] = lc > 0 && t0 + g * kEsThreads < tiles;
+                pend[g] = lc > 0 && t0 + g * kEsThreads < nt;
                 any = any || pend[g];
             }
             uint32_t spins = 0;
@@ -448,7 +461,7 @@ __global__ void __launch_bounds__(kEsThreads) emit_scatter_kernel(
                 uint32_t sv[kEsLook];
 #pragma unroll
                 for (int g = 0; g < kEsLook; g++)
-                    sv[g] = pend[g] ? status[(size_t)look[g] * tiles + t0 + g * kEsThreads] : 0u;
+                    sv[g] = pend[g] ? status[(size_t)look[g] * tiles + tile_lo + t0 + g * kEsThreads] : 0u;
                 any = false;
 #pragma unroll
                 for (int g = 0; g < kEsLook; g++) {
@@ -467,9 +480,9 @@ __global__ void __launch_bounds__(kEsThreads) emit_scatter_kernel(
 #pragma unroll
             for (int g = 0; g < kEsLook; g++) {
                 const int t = t0 + g * kEsThreads;
-                if (t >= tiles) continue;
+                if (t >= nt) continue;
                 if (lc > 0) my_status[t] = kFlagPrefix | ((excl[g] + s_base[t]) & kValMask);
-                s_base[t] = __ldg(tile_start + (size_t)seg * tiles + t) + excl[g];
+                s_base[t] = __ldg(tile_start + (size_t)seg * tiles + tile_lo + t) + excl[g];
             }
         }
         // ---- pass B: (expand the pairs IN ORDER into the owning warp's window,) rank, scatter
@@ -505,7 +518,7 @@ __global__ void __launch_bounds__(kEsThreads) emit_scatter_kernel(
                 if (valid) {
                     // block hint of the pair: which halves of tile (tx, ty) the footprint's block range reaches
                     const uint32_t li = pr & 1023u;
-                    const uint32_t ty = __umulhi(t, gx_magic), tx = t - ty * (uint32_t)gx;
+                    const uint32_t tyl = __umulhi(t, gx_magic), tx = t - tyl * (uint32_t)gx, ty = tyl + (uint32_t)y0;
                     const uint32_t rx = s_bx[li], ry = s_by[li];
                     const uint32_t hx = half_bits(2u * tx, rx & 0xffffu, rx >> 16), hy = half_bits(2u * ty, ry & 0xffffu, ry >> 16);
                     const uint32_t hint = ((hy & 1u) ? hx : 0u) | ((hy & 2u) ? (hx << 2) : 0u);
@@ -515,6 +528,12 @@ __global__ void __launch_bounds__(kEsThreads) emit_scatter_kernel(
             }
         }
         __syncthreads();
+        if (y1 < gy) {   // the next band starts from clean counters
+            uint32_t* z = reinterpret_cast<uint32_t*>(s_wcnt);
+            for (int i = threadIdx.x; i < kEsWarps * tp / 2; i += kEsThreads) z[i] = 0;
+            __syncthreads();
+        }
+        }  // bands
     }
 }
 
@@ -812,13 +831,11 @@ static BinningWs carve(void* base, int S, int N, int width, int height, size_t c
 }
 
 static int set_kernel_attrs(int tiles) {
-    static DeviceOnce rs_once, es10_once, es12_once, es22_once;
+    static DeviceOnce rs_once, es_once;
     int rc;
     if ((rc = ensure_dyn_smem(rs_once, rs_onesweep_kernel, (int)sizeof(RsSmem)))) return rc;
-    const int need = (int)emit_scatter_smem(tiles);
-    if ((rc = ensure_dyn_smem(es10_once, emit_scatter_kernel<10>, need))) return rc;
-    if ((rc = ensure_dyn_smem(es12_once, emit_scatter_kernel<12>, need))) return rc;
-    if ((rc = ensure_dyn_smem(es22_once, emit_scatter_kernel<22>, need))) return rc;
+    (void)tiles;
+    if ((rc = ensure_dyn_smem(es_once, emit_scatter_kernel, (int)emit_scatter_smem(kEsBandTiles)))) return rc;
     return OMFS_OK;
 }
 
@@ -901,18 +918,15 @@ int binning_emit_scatter(int S, int N, int width, int height, size_t capacity, c
     }
     int rc = set_kernel_attrs(w.tiles);
     if (rc) return rc;
-    const size_t smem = emit_scatter_smem(w.tiles);
-    if (smem > 227 * 1024) {
-        set_error("binning: %d tiles per frame need %zu bytes of shared memory", w.tiles, smem);
+    const int gx = (width + kTile - 1) / kTile, gy = (height + kTile - 1) / kTile;
+    if (gx > kEsBandTiles) {
+        set_error("binning: %d tile columns per frame exceed one band (%d tiles)", gx, kEsBandTiles);
         return OMFS_ERR_INVALID;
     }
-    // ballots per pair = bits of the tile id inside a frame: 10 at 512^2, 12 at 1024^2
-    auto kern = w.tile_bits <= 10 ? emit_scatter_kernel<10> : (w.tile_bits <= 12 ? emit_scatter_kernel<12>
-                                                                                 : emit_scatter_kernel<22>);
-    kern<<<kNumSMs * 4, kEsThreads, smem, stream>>>(S, N, width, height, w.tiles, w.perm[0], w.perm[1],
-                                                    w.counters + 6, d_tiles_touched, (const float4*)d_P0,
-                                                    w.tile_start, w.sort_count, w.counters + 4, w.status_emit,
-                                                    d_sorted_vals);
+    const int band_rows = emit_scatter_band_rows(gx, gy);
+    emit_scatter_kernel<<<kNumSMs * 4, kEsThreads, emit_scatter_smem(band_rows * gx), stream>>>(
+        S, N, width, height, w.tiles, band_rows, w.perm[0], w.perm[1], w.counters + 6, d_tiles_touched,
+        (const float4*)d_P0, w.tile_start, w.sort_count, w.counters + 4, w.status_emit, d_sorted_vals);
     count_launch();
     OMFS_LAUNCH_CHECK();
     return OMFS_OK;
