@@ -626,7 +626,10 @@ __device__ __forceinline__ uint32_t digit_peers(uint32_t d, uint32_t valid_mask)
 // segment whose length is read from the device).  vals_in == NULL: values are the identity
 // permutation inside each segment (first pass of the depth sort).  digit_start is [n_seg][stride]
 // with this pass's 256 offsets at the front of each row.
-__global__ void __launch_bounds__(kRsThreads, 4) rs_onesweep_kernel(
+#ifndef OMFS_RS_CTAS
+#define OMFS_RS_CTAS 4   // resident CTAs per SM (42 KB of shared memory each)
+#endif
+__global__ void __launch_bounds__(kRsThreads, OMFS_RS_CTAS) rs_onesweep_kernel(
     const uint32_t* __restrict__ keys_in, const uint32_t* __restrict__ vals_in, uint32_t* __restrict__ keys_out,
     uint32_t* __restrict__ vals_out, const uint32_t* __restrict__ count_ptr, uint32_t seg_len, uint32_t n_seg,
     int shift, const uint32_t* __restrict__ digit_start, uint32_t digit_stride,
@@ -871,7 +874,7 @@ int binning_depth_sort(int S, int N, int width, int height, size_t capacity, con
     for (int p = 0; p < 4; p++) {
         uint32_t* kout = w.dkeys[(p + 1) & 1];
         uint32_t* vout = w.perm[(p + 1) & 1];
-        rs_onesweep_kernel<<<kNumSMs * 4, kRsThreads, sizeof(RsSmem), stream>>>(
+        rs_onesweep_kernel<<<kNumSMs * OMFS_RS_CTAS, kRsThreads, sizeof(RsSmem), stream>>>(
             kin, vin, kout, vout, nullptr, (uint32_t)N, (uint32_t)S, 8 * p, w.hist_depth + p * kRadix, 4 * kRadix,
             w.counters + p, w.status_depth + (size_t)p * w.status_depth_stride, p == 3 ? w.counters + 5 : nullptr,
             w.counters + 6);

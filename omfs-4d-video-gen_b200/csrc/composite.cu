@@ -243,8 +243,14 @@ constexpr int kBlocksPerTile = 4;  // 8x8 pixel blocks (warps) per 16x16 tile
 //            order) into the pair slots the evaluation reads.
 // The loop is software-pipelined: the list words of the next scan step and the records of the next round are
 // requested before the current round is evaluated.
-constexpr int kQueueCap = 256;   // queued indices per warp (power of two)
-constexpr int kScanGroups = 4;   // 32-entry groups per scan step
+#ifndef OMFS_COMP_QUEUE
+#define OMFS_COMP_QUEUE 256
+#endif
+#ifndef OMFS_COMP_SCAN_GROUPS
+#define OMFS_COMP_SCAN_GROUPS 4
+#endif
+constexpr int kQueueCap = OMFS_COMP_QUEUE;          // queued indices per warp (power of two)
+constexpr int kScanGroups = OMFS_COMP_SCAN_GROUPS;  // 32-entry groups per scan step
 
 __global__ void OMFS_COMP_BOUNDS composite_kernel(int n_seg, int N, int width, int height, const float4* __restrict__ P0,
                                                        const float4* __restrict__ P1,
