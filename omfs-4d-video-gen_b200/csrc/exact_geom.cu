@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(kBindThreads) bind_preprocess_kernel(
     uint32_t* __restrict__ depth_keys, int S, int per_block, uint32_t* __restrict__ hist_depth /*[S][4][256]*/,
     uint32_t* __restrict__ tile_cnt /*[S][tiles]*/, int tiles) {
     __shared__ float s_cam[kCam];
-    extern __shared__ uint32_t s_fused[];   // FUSED: [4][256] depth-digit counters, then [tiles] tile counters
+    extern __shared__ uint32_t s_fused[];   // FUSED: [4][256] depth-digit counters, then the [(gy+1)][(gx+1)] corner grid of the tile counts
     const int gx = (width + kTile - 1) / kTile, gy = (height + kTile - 1) / kTile;
     const int lane = threadIdx.x & 31;
     long long flat_lo, flat_hi;
@@ -108,7 +108,7 @@ __global__ void __launch_bounds__(kBindThreads) bind_preprocess_kernel(
     __syncthreads();   // the previous piece's counters are flushed, its camera no longer read
     if (threadIdx.x < kCam) s_cam[threadIdx.x] = __ldg(cams + (size_t)seg * kCam + threadIdx.x);
     if (FUSED)
-        for (int i = threadIdx.x; i < 1024 + tiles; i += blockDim.x) s_fused[i] = 0;
+        for (int i = threadIdx.x; i < 1024 + (gx + 1) * (gy + 1); i += blockDim.x) s_fused[i] = 0;
     __syncthreads();
     const int frame = __ldg(seg_frame + seg);
 
@@ -191,10 +191,16 @@ __global__ void __launch_bounds__(kBindThreads) bind_preprocess_kernel(
                 atomicAdd(&s_fused[768 + top], 1u);
             }
             if (ok) {
-                int minx, miny, maxx, maxy;
-                ex_tile_rect(o.px, o.py, o.radius, gx, gy, minx, miny, maxx, maxy);
-                for (int y = miny; y < maxy; y++)
-                    for (int x = minx; x < maxx; x++) atomicAdd(&s_fused[1024 + y * gx + x], 1u);
+                // the rectangle ex_bind_project counted the tiles of, as the four corners of a 2-D difference array
+                // on the (gx + 1) x (gy + 1) corner grid (counters wrap modulo 2^32; the prefix sums at the flush
+                // bring them back).  Four atomics per Gaussian whatever the rectangle: the per-tile loop it replaces
+                // ran as long as the largest rectangle of the warp (13 % of the kernel's issue slots).
+                uint32_t* d2 = s_fused + 1024;
+                const int gw = gx + 1;
+                atomicAdd(d2 + o.miny * gw + o.minx, 1u);
+                atomicAdd(d2 + o.miny * gw + o.maxx, 0xffffffffu);
+                atomicAdd(d2 + o.maxy * gw + o.minx, 0xffffffffu);
+                atomicAdd(d2 + o.maxy * gw + o.maxx, 1u);
             }
         }
     }
@@ -205,9 +211,30 @@ __global__ void __launch_bounds__(kBindThreads) bind_preprocess_kernel(
             const uint32_t v = s_fused[i];
             if (v) atomicAdd(h + i, v);
         }
+        // difference array -> counts: inclusive prefix sums along every row, then along every column (a thread per
+        // row / column; the row stride gx + 1 is odd for the usual sizes, so the row pass is free of bank conflicts)
+        uint32_t* d2 = s_fused + 1024;
+        const int gw = gx + 1, gh = gy + 1;
+        for (int y = threadIdx.x; y < gh; y += blockDim.x) {
+            uint32_t run = 0;
+            for (int x = 0; x < gw; x++) {
+                run += d2[y * gw + x];
+                d2[y * gw + x] = run;
+            }
+        }
+        __syncthreads();
+        for (int x = threadIdx.x; x < gw; x += blockDim.x) {
+            uint32_t run = 0;
+            for (int y = 0; y < gh; y++) {
+                run += d2[y * gw + x];
+                d2[y * gw + x] = run;
+            }
+        }
+        __syncthreads();
         uint32_t* c = tile_cnt + (size_t)seg * tiles;
         for (int i = threadIdx.x; i < tiles; i += blockDim.x) {
-            const uint32_t v = s_fused[1024 + i];
+            const int ty = i / gx, tx = i - ty * gx;
+            const uint32_t v = d2[ty * gw + tx];
             if (v) atomicAdd(c + i, v);
         }
     }
@@ -227,7 +254,8 @@ int bind_preprocess_launch(int S, int N, int F, int width, int height, const flo
             (const float4*)d_rot, (const float4*)d_sh, (float4*)d_P0, (float4*)d_P1, (float4*)d_P2, d_tiles_touched,
             d_depth_keys, S, kBindThreads, nullptr, nullptr, tiles);
     } else {
-        const size_t smem = sizeof(uint32_t) * (1024 + (size_t)tiles);
+        const size_t corners = (size_t)((width + kTile - 1) / kTile + 1) * ((height + kTile - 1) / kTile + 1);
+        const size_t smem = sizeof(uint32_t) * (1024 + corners);
         if (smem > 200 * 1024) {
             set_error("bind_preprocess: %d tiles per frame exceed the fused tile counters", tiles);
             return OMFS_ERR_INVALID;

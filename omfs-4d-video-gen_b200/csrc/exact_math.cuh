@@ -183,6 +183,7 @@ struct BindPre {
     int radius;
     float ca, cb, cc;
     uint32_t tiles;
+    int minx, miny, maxx, maxy;  // the tile rectangle `tiles` is the area of
     // bind result (for SH direction and debugging)
     float mx, my, mz;
 };
@@ -281,6 +282,10 @@ OMFS_HD bool ex_bind_project(const float ff[20], float lx, float ly, float lz, f
     o.cb = kConB * cony;
     o.cc = kConA * conz;
     o.tiles = tt;
+    o.minx = minx;
+    o.miny = miny;
+    o.maxx = maxx;
+    o.maxy = maxy;
     return true;
 }
 
