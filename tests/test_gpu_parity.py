@@ -284,6 +284,35 @@ def test_tapered_multi_batch_call_and_dense_opaque_splats(rt):
     sess.close()
 
 
+def test_wide_frame_in_ragged_tile_bands(rt):
+    """More than 1024 tiles: emit_scatter walks the frame in bands of whole tile rows.  1040 x 560 gives 65 x 35
+    tiles = bands of 15, 15 and 5 rows (none a power of two, the last one short, rectangles straddling the band
+    edges): sorted lists, ranges, hints and the image against the oracle, bit for bit where the surface is exact."""
+    import omfs_b200  # noqa: F401
+    import oracle
+    from omfs_b200 import avatar, synthetic
+    W, H, T = 1040, 560, 2
+    model, params, av, cam = synthetic.make_scene(n_gauss=9000, n_frames=T, width=W, height=H, n_verts=642)
+    av.scaling[:] = av.scaling + np.float32(0.7)          # larger splats: rectangles of several tile rows
+    baked = avatar.bake(av)
+    sess, u8, img = run_session(rt, model, params, baked, [cam], W, H, max_batch=T)
+    verts = sess.tap_array("verts", (T, 642, 3), np.float32)
+    ref = oracle.render(model, params, baked, [cam.pack()] * T, W, H, verts=verts)
+    tiles = 65 * 35
+    R = ref.binned.n_pairs
+    assert R == sess.dims()["pairs_last_batch"] and R / (T * baked["n"]) > 3.0
+    assert np.array_equal(sess.tap_array("keys", (R,), np.uint64), ref.binned.sorted_keys)
+    vals = sess.tap_array("vals", (R,), np.uint32)
+    assert np.array_equal(rt.pair_indices(vals), ref.binned.sorted_values)
+    assert np.array_equal(sess.tap_array("ranges", (T * tiles, 2), np.uint32), ref.binned.ranges)
+    ext = rt.published_records(sess.tap_array("P0", (T, baked["n"], 4), np.float32),
+                               sess.tap_array("P2", (T, baked["n"], 4), np.float32))[2]
+    check_block_hints(rt.pair_hints(vals), ref, ext, W, H)
+    assert np.abs(img - ref.image).max() <= 2e-4
+    assert (oracle.to_uint8(ref.image) != u8).mean() < 1e-4
+    sess.close()
+
+
 def test_needle_splats_take_the_guarded_loop(rt):
     """Long thin splats (one axis x150, the others /8): their conics are badly conditioned (D <= 1e-4 tr^2), which is
     when the compositing kernel may NOT drop ex_blend's `e <= lo` rejection — rounds that hold one run the guarded
