@@ -137,7 +137,9 @@ def _f32(a) -> np.ndarray:
 
 
 def _ptr(a: np.ndarray | None):
-    return None if a is None else a.ctypes.data_as(c_void_p)
+    # the raw address from the array interface: `a.ctypes.data_as` costs ~7 us per array, eight arrays per call — 3 % of a
+    # 38-frame host call
+    return None if a is None else c_void_p(a.__array_interface__["data"][0])
 
 
 class PinnedArray:
