@@ -5,17 +5,19 @@
 // only approximate operation is ex2.approx (the oracle uses exp2f), which moves the image by ~1e-7.
 //
 // Structure
-//   * one warp = one 8x8 pixel block, two pixels per lane; the tile's depth-sorted list is consumed 32 entries
-//     at a time with a lane-parallel footprint cull (extents precomputed by the preprocess kernel and
-//     carried in P2.w) and a ballot, so only the ~1/3 of the tile's Gaussians that can touch the
-//     block are evaluated — the kernel is FP32-issue bound, skipped (Gaussian, warp) pairs are the win;
+//   * one warp = one 8x8 pixel block, two pixels per lane.  The tile's depth-sorted list is walked in two levels:
+//     the pair WORDS are scanned 128 at a time and only the entries whose block hint names this block (set by the
+//     binning from the footprint box) are queued; queued entries are then fetched 32 at a time with every lane
+//     busy, tested exactly against the box of the block's live pixels, and evaluated from shared memory — the
+//     kernel is FP32-issue bound, so work that is never started is the win (22 % of the (entry, block)
+//     combinations pass the hint, ~19 % are evaluated);
 //   * persistent one-warp CTAs that draw (segment, tile, block) work units from a ticket counter; no block
 //     barriers anywhere: a finished pixel block goes straight on to the next unit;
 //   * early termination per pixel (T < 1e-4) and per warp (all 64 pixels saturated);
 //   * the optional uint8 HWC image (the save_image quantisation) is produced by the same kernel,
 //     so the frame sink costs no extra pass over HBM.
 // Roofline: 40 B per tile pair against ~256 pixel evaluations of ~7 issue slots each: the
-// issue rate and the L1/shared data pipe bind (both ~71 % busy, profiles/r1_ncu_summary.md), not HBM (4 %);
+// issue rate binds (67-76 % of the issue slots busy, DRAM 6 % of peak: profiles/r2d_ncu_summary.md), not HBM;
 // bench.py reports the HBM fraction BASELINE.json asks for and says so.
 #include <cuda_fp16.h>
 
