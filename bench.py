@@ -48,7 +48,7 @@ KEYS = ("expr", "rotation", "neck_pose", "jaw_pose", "eyes_pose", "translation")
 # `segs_per_unit` images.
 WORKLOADS = {
     2: dict(metric="surgery-render frames/s (512^2, 100k Gaussians)", width=512, height=512, n_gauss=100_000,
-            units=300, unit_name="frames", views=1, frames_per_unit=1, batch=60, pairs_per_seg=0,
+            units=300, unit_name="frames", views=1, frames_per_unit=1, batch=75, pairs_per_seg=0,
             name="configs[2]: 512x512 x {units}-frame surgery video, 100k FLAME-bound Gaussians"),
     3: dict(metric="multi-view render images/s (1024^2, 16 views, 500k Gaussians)", width=1024, height=1024,
             n_gauss=500_000, units=300, unit_name="frames", views=16, frames_per_unit=1, batch=32,
