@@ -243,6 +243,18 @@ int omfs_session_render_host(omfs_session* s, const omfs_frames_desc* frames,
 int omfs_session_render_host_png(omfs_session* s, const omfs_frames_desc* frames, uint8_t* h_png,
                                  size_t h_png_capacity, uint64_t* h_offsets, uint8_t* h_out_u8);
 
+/* The same call for a STREAM of clips (one after another, or one frame block per step): submit enqueues a clip and
+ * returns without waiting; collect completes the OLDEST submitted clip — its PNG files and offsets are then in the
+ * buffers given to its submit.  Up to two clips may be outstanding, so clip i+1 is uploaded and rendered while the last
+ * batches of clip i are still being encoded and copied: the overlap a blocking call cannot have (the session's
+ * buffers and ring slots simply continue from one call to the next).  Everything a clip reads or writes on the host
+ * (parameter arrays, h_png, h_offsets) must stay valid and untouched until its collect; a tile-pair overflow or a
+ * too small h_png is reported by the collect (OMFS_ERR_CAPACITY: every outstanding clip is dropped, reserve and
+ * submit again).  The blocking calls refuse to run while clips are outstanding. */
+int omfs_session_submit_host_png(omfs_session* s, const omfs_frames_desc* frames, uint8_t* h_png,
+                                 size_t h_png_capacity, uint64_t* h_offsets);
+int omfs_session_collect_host_png(omfs_session* s);
+
 /* Device in, device out (inputs already resident; same field meaning, device pointers).
  * d_out_u8 / d_out_f32 may be NULL.  Asynchronous on `stream`. */
 int omfs_session_render_device(omfs_session* s, const omfs_frames_desc* d_frames,

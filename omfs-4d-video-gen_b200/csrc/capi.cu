@@ -181,6 +181,16 @@ struct DevBuf {
 #endif
 constexpr int kCompPipelinedWarps = OMFS_COMP_PIPELINED_WARPS;
 
+// Host destination of the device frame sink for one call: packed PNG streams and their offsets.
+struct PngSink {
+    uint8_t* h_png = nullptr;
+    size_t capacity = 0;
+    uint64_t* h_offsets = nullptr;   // [segments + 1]
+    size_t written = 0;              // bytes handed to the copy engine so far
+    bool streaming = false;          // a submit / collect call: failures are kept for the collect
+    int error = OMFS_OK;             // first failure while draining
+};
+
 struct omfs_session {
     omfs_session_config cfg{};
     int V = 0, F = 0, n_expr = 0, N = 0, kpad = 0, npad = 0, tiles = 0;
@@ -238,7 +248,16 @@ struct omfs_session {
         bool active = false;
         size_t seg0 = 0;
         int S = 0;
+        PngSink* sink = nullptr;   // the call the slot's batch belongs to
     } png_slot[kPngRing];
+    // streaming host calls (omfs_session_submit_host_png / omfs_session_collect_host_png): up to kMaxPending calls
+    // whose frames are still on their way to host memory
+    static constexpr int kMaxPending = 2;
+    PngSink* pending[kMaxPending]{};
+    int n_pending = 0;
+    long long stream_base = 0;        // batches of all streaming calls so far: ring slot and buffer set continue across calls
+    bool copied_pending[2]{};         // ev_copied[ib] has been recorded and not yet waited for by a compositing launch
+    cudaEvent_t ev_collect = nullptr;
     size_t png_frame_cap = 0, png_ws_bytes = 0;
     std::vector<int32_t> seg_frame_host;
     int seg_table_fpb = -1, seg_table_views = -1;
@@ -279,6 +298,9 @@ extern "C" void omfs_session_destroy(omfs_session* s) {
     }
     if (s->ev_pre) cudaEventDestroy(s->ev_pre);
     if (s->ev_scan) cudaEventDestroy(s->ev_scan);
+    if (s->png_stream) cudaStreamSynchronize(s->png_stream);
+    if (s->ev_collect) cudaEventDestroy(s->ev_collect);
+    while (s->n_pending > 0) delete s->pending[--s->n_pending];   // clips submitted and never collected
     DevBuf* all[] = {&s->template_, &s->shapedirs, &s->bt, &s->jreg, &s->weights, &s->faces, &s->xyzb,
                      &s->scale_lo, &s->rot, &s->sh, &s->base, &s->shape, &s->static_off, &s->plan_off,
                      &s->expr, &s->rotation, &s->neck, &s->jaw, &s->eyes, &s->transl, &s->dyn, &s->jdyn,
@@ -499,13 +521,6 @@ extern "C" int omfs_session_set_subject(omfs_session* s, const float* h_shape300
     return OMFS_OK;
 }
 
-// Host destination of the device frame sink for one call: packed PNG streams and their offsets.
-struct PngSink {
-    uint8_t* h_png = nullptr;
-    size_t capacity = 0;
-    uint64_t* h_offsets = nullptr;   // [segments + 1]
-    size_t written = 0;              // bytes handed to the copy engine so far
-};
 
 // Lazily created state of the device frame sink (streams, ring buffers) for batches of up to max_batch frames.
 static int png_prepare(omfs_session* s) {
@@ -532,17 +547,20 @@ static int png_prepare(omfs_session* s) {
 
 // The batch in ring slot r has been encoded (or will be shortly): wait for its frame offsets, hand exactly the bytes
 // it produced to the copy engine, publish the offsets to the caller.
-static int png_drain(omfs_session* s, int r, PngSink* sink) {
+static int png_drain(omfs_session* s, int r) {
     omfs_session::PngSlot& slot = s->png_slot[r];
     if (!slot.active) return OMFS_OK;
     slot.active = false;
+    PngSink* sink = slot.sink;
     OMFS_CUDA(cudaEventSynchronize(s->ev_png_off[r]));
+    if (sink->error != OMFS_OK) return OMFS_OK;   // the call already failed: nothing more is copied for it
     const unsigned long long* off = s->png_off_host[r];
     const size_t total = (size_t)off[slot.S];
     if (sink->written + total > sink->capacity) {
         set_error("png sink: the caller's buffer (%zu bytes) is too small: %zu bytes needed so far (size it with "
                   "omfs_png_max_bytes per frame)", sink->capacity, sink->written + total);
-        return OMFS_ERR_CAPACITY;
+        sink->error = OMFS_ERR_CAPACITY;
+        return sink->streaming ? OMFS_OK : OMFS_ERR_CAPACITY;   // a streaming call hears of it at its collect
     }
     OMFS_CUDA(cudaMemcpyAsync(sink->h_png + sink->written, s->png_buf[r].p, total, cudaMemcpyDeviceToHost, s->copy_stream));
     OMFS_CUDA(cudaEventRecord(s->ev_png_copied[r], s->copy_stream));
@@ -555,14 +573,16 @@ static int png_drain(omfs_session* s, int r, PngSink* sink) {
 static int render_core(omfs_session* s, int T, int n_views, const float* p_expr, const float* p_rot,
                        const float* p_neck, const float* p_jaw, const float* p_eyes, const float* p_transl,
                        const float* p_dyn, const float* p_cams, uint8_t* out_u8, float* out_f32, bool out_on_host,
-                       cudaStream_t st, PngSink* png = nullptr) {
+                       cudaStream_t st, PngSink* png = nullptr, bool streaming = false) {
     const int V = s->V, F = s->F, N = s->N, W = s->cfg.width, H = s->cfg.height;
     const size_t hw = (size_t)W * H;
     if (png) {
         int prc = png_prepare(s);
         if (prc) return prc;
-        for (auto& slot : s->png_slot) slot.active = false;
+        if (!streaming)
+            for (auto& slot : s->png_slot) slot.active = false;
     }
+    if (!streaming) s->copied_pending[0] = s->copied_pending[1] = false;   // a blocking call left nothing in flight
     const unsigned long long launches0 = g_launches;
     s->stats[0] = s->stats[2] = s->stats[3] = 0;
     int rc;
@@ -599,7 +619,9 @@ static int render_core(omfs_session* s, int T, int n_views, const float* p_expr,
     }
     uint32_t* d_num_pairs = s->counters.as<uint32_t>();
     int* d_flag = s->counters.as<int>() + 1;
-    OMFS_CUDA(cudaMemsetAsync(s->counters.p, 0, 256, st));
+    // (streaming calls keep the counters of the calls before them: the overflow flag of clip i must survive until its
+    // collect, which may come after clip i+1 was submitted)
+    if (!(streaming && s->stream_base > 0)) OMFS_CUDA(cudaMemsetAsync(s->counters.p, 0, 256, st));
 
     unsigned long long* d_pair_accum = reinterpret_cast<unsigned long long*>(s->counters.as<unsigned char>() + 16);
     uint32_t* d_pair_max = s->counters.as<uint32_t>() + 2;
@@ -627,7 +649,9 @@ static int render_core(omfs_session* s, int T, int n_views, const float* p_expr,
     // front end starts, so the next call begins with the OTHER buffer set, and the last batch keeps the pipelined
     // occupancy (a front end will run beside it).
     const bool deferred = s->defer_join && !out_on_host;
-    const int parity0 = deferred ? s->set_parity : 0;
+    // Streaming host calls go one step further: ring slot, image buffer and record set all continue from the
+    // previous call, whose last batches may still be encoding or copying.
+    const long long idx0 = streaming ? s->stream_base : (deferred ? s->set_parity : 0);
     for (int g0 = 0; g0 < T; g0 += geo) {
         const int gT = std::min(geo, T - g0);
         // ---- FLAME: operand prep, blendshape GEMM (tensor cores), skinning
@@ -657,7 +681,7 @@ static int render_core(omfs_session* s, int T, int n_views, const float* p_expr,
         // keeps its batches whole (the debug taps then describe the whole call).
         std::vector<int> sizes;
         for (int b0 = 0; b0 < gT; b0 += fpb) sizes.push_back(std::min(fpb, gT - b0));
-        if (out_on_host && pipelined && T >= 3 * fpb) {
+        if (out_on_host && pipelined && !streaming && T >= 3 * fpb) {
             const int floor_frames = std::max(2, fpb / 8);
             auto taper = [&](int frames) {  // descending pieces
                 std::vector<int> out;
@@ -678,7 +702,8 @@ static int render_core(omfs_session* s, int T, int n_views, const float* p_expr,
         for (size_t bi = 0; bi < sizes.size(); b0 += sizes[bi], bi++) {
             const int bT = sizes[bi];
             const int S = bT * n_views;
-            const int ib = (batch_index + parity0) & 1;
+            const long long gi = idx0 + batch_index;   // position in the stream of batches this numbering continues
+            const int ib = (int)(gi & 1);
             // the buffer set `ib` is free once the compositing of two batches ago has read it
             if (s->ev_comp_pending[ib]) {
                 OMFS_CUDA(cudaStreamWaitEvent(st, s->ev_comp[ib], 0));
@@ -741,7 +766,10 @@ static int render_core(omfs_session* s, int T, int n_views, const float* p_expr,
                 OMFS_CUDA(cudaStreamWaitEvent(cst, s->ev_front[ib], 0));
             }
             // the image buffer may still be draining to the host from two batches ago
-            if (batch_index >= 2 && out_on_host) OMFS_CUDA(cudaStreamWaitEvent(cst, s->ev_copied[ib], 0));
+            if (out_on_host && s->copied_pending[ib]) {
+                OMFS_CUDA(cudaStreamWaitEvent(cst, s->ev_copied[ib], 0));
+                s->copied_pending[ib] = false;
+            }
             float* img = s->image[ib].as<float>();
             uint8_t* img8 = s->image_u8[ib].as<uint8_t>();
             const size_t seg0 = (size_t)(g0 + b0) * n_views;
@@ -752,10 +780,8 @@ static int render_core(omfs_session* s, int T, int n_views, const float* p_expr,
             // of batch b-2 and hands its streams to the copy engine (the GPU still has batch b-1 queued meanwhile),
             // so the copies overlap the rendering of the following batches and a ring slot is always drained long
             // before it comes round again.
-            const int pr = batch_index % omfs_session::kPngRing;
-            if (png && batch_index >= 2 &&
-                (rc = png_drain(s, (batch_index - 2) % omfs_session::kPngRing, png)))
-                return rc;
+            const int pr = (int)(gi % omfs_session::kPngRing);
+            if (png && gi >= 2 && (rc = png_drain(s, (int)((gi - 2) % omfs_session::kPngRing)))) return rc;
             if (!dst_f && !dst_8) dst_f = img;  // nothing requested: still render (debug taps)
             if ((rc = mark(kStComposite))) return rc;
             // Pipelined: the persistent compositing warps leave 12 of the 32 warp slots per SM to the front end of
@@ -764,7 +790,7 @@ static int render_core(omfs_session* s, int T, int n_views, const float* p_expr,
             // whole SM.
             const bool last_batch = (g0 + gT >= T) && (bi + 1 == sizes.size());
             if ((rc = composite_launch(S, N, W, H, P0, P1, P2, vals, ranges, s->cfg.bg, dst_f, dst_8, s->tickets.p,
-                                       (pipelined && !(last_batch && s->last_batch_full && !deferred)) ? s->comp_pipelined_warps : 0, cst)))
+                                       (pipelined && !(last_batch && s->last_batch_full && !deferred && !streaming)) ? s->comp_pipelined_warps : 0, cst)))
                 return rc;
             if ((rc = mark(-1))) return rc;
             if (pipelined) {
@@ -793,6 +819,7 @@ static int render_core(omfs_session* s, int T, int n_views, const float* p_expr,
                     s->png_slot[pr].active = true;
                     s->png_slot[pr].seg0 = seg0;
                     s->png_slot[pr].S = S;
+                    s->png_slot[pr].sink = png;
                 }
                 if (out_u8)
                     OMFS_CUDA(cudaMemcpyAsync(out_u8 + seg0 * 3 * hw, img8, (size_t)S * 3 * hw,
@@ -805,23 +832,27 @@ static int render_core(omfs_session* s, int T, int n_views, const float* p_expr,
                 // that the copy stream never queues a later batch's stream copy behind this batch's encode.
                 if (png && !out_u8 && !out_f32) {
                     OMFS_CUDA(cudaEventRecord(s->ev_copied[ib], s->png_stream));
+                    s->copied_pending[ib] = true;
                 } else {
                     if (png) OMFS_CUDA(cudaStreamWaitEvent(s->copy_stream, s->ev_png_off[pr], 0));
                     OMFS_CUDA(cudaEventRecord(s->ev_copied[ib], s->copy_stream));
+                    s->copied_pending[ib] = true;
                 }
             }
             batch_index++;
         }
     }
     // the sink's remaining batches, oldest first
-    if (png)
+    if (png && !streaming)
         for (int k = 0; k < omfs_session::kPngRing; k++)
-            if ((rc = png_drain(s, (batch_index + k) % omfs_session::kPngRing, png))) return rc;
+            if ((rc = png_drain(s, (batch_index + k) % omfs_session::kPngRing))) return rc;
     // everything this call launched is complete when the caller's stream is: join the compositing stream — unless
     // the caller asked to join by itself (omfs_session_join), so that consecutive calls overlap like the batches
     // of one call do
-    if (deferred) {
-        s->set_parity = (parity0 + batch_index) & 1;
+    if (streaming) {
+        s->stream_base = idx0 + batch_index;
+    } else if (deferred) {
+        s->set_parity = (int)((idx0 + batch_index) & 1);
     } else {
         for (int ib = 0; ib < 2; ib++)
             if (s->ev_comp_pending[ib]) {
@@ -954,6 +985,7 @@ extern "C" int omfs_session_render_host_png(omfs_session* s, const omfs_frames_d
     OMFS_REQUIRE(fr->expr && fr->rotation && fr->neck_pose && fr->jaw_pose && fr->eyes_pose && fr->translation &&
                      fr->cams,
                  "null frame array");
+    OMFS_REQUIRE(s->n_pending == 0, "streaming calls are outstanding: collect them first (omfs_session_collect_host_png)");
     OMFS_CUDA(cudaSetDevice(s->cfg.device));
     const int T = fr->n_frames;
     h_offsets[0] = 0;
@@ -1008,6 +1040,93 @@ extern "C" int omfs_session_render_host_png(omfs_session* s, const omfs_frames_d
     return rc;
 }
 
+// ---- streaming form of the call above.  submit enqueues a clip and returns; collect completes the OLDEST submitted
+// clip: its PNG streams and offsets are then in the caller's buffers.  Up to kMaxPending clips may be outstanding, so
+// clip i+1 renders while clip i's last batches are still being encoded and copied — the overlap a blocking call
+// cannot have.  Everything the call reads and writes on the host (parameter arrays, h_png, h_offsets) must stay
+// valid until its collect.
+extern "C" int omfs_session_submit_host_png(omfs_session* s, const omfs_frames_desc* fr, uint8_t* h_png,
+                                            size_t h_png_capacity, uint64_t* h_offsets) {
+    OMFS_REQUIRE(s && fr && h_png && h_offsets, "null argument");
+    OMFS_REQUIRE(s->subject_set, "omfs_session_set_subject must be called first");
+    OMFS_REQUIRE(fr->n_frames > 0 && fr->n_views > 0 && fr->n_views <= s->cfg.max_batch, "bad frame/view counts");
+    OMFS_REQUIRE(fr->expr && fr->rotation && fr->neck_pose && fr->jaw_pose && fr->eyes_pose && fr->translation &&
+                     fr->cams,
+                 "null frame array");
+    OMFS_REQUIRE(s->n_pending < omfs_session::kMaxPending, "too many clips outstanding: collect one first");
+    OMFS_REQUIRE(!s->profiling, "stage profiling needs the blocking calls");
+    OMFS_CUDA(cudaSetDevice(s->cfg.device));
+    const int T = fr->n_frames;
+    cudaStream_t st = s->stream;
+    int rc;
+    if ((rc = upload(s->expr, fr->expr, sizeof(float) * (size_t)T * s->n_expr, st))) return rc;
+    if ((rc = upload(s->rotation, fr->rotation, sizeof(float) * 3 * T, st))) return rc;
+    if ((rc = upload(s->neck, fr->neck_pose, sizeof(float) * 3 * T, st))) return rc;
+    if ((rc = upload(s->jaw, fr->jaw_pose, sizeof(float) * 3 * T, st))) return rc;
+    if ((rc = upload(s->eyes, fr->eyes_pose, sizeof(float) * 6 * T, st))) return rc;
+    if ((rc = upload(s->transl, fr->translation, sizeof(float) * 3 * T, st))) return rc;
+    if (fr->dynamic_offset &&
+        (rc = upload(s->dyn, fr->dynamic_offset, sizeof(float) * 3 * (size_t)s->V * T, st)))
+        return rc;
+    if ((rc = upload(s->cams_in, fr->cams, sizeof(float) * kCam * fr->n_views, st))) return rc;
+    PngSink* sink = new PngSink();
+    sink->h_png = h_png;
+    sink->capacity = h_png_capacity;
+    sink->h_offsets = h_offsets;
+    sink->streaming = true;
+    h_offsets[0] = 0;
+    s->pending[s->n_pending++] = sink;
+    rc = render_core(s, T, fr->n_views, s->expr.as<float>(), s->rotation.as<float>(), s->neck.as<float>(),
+                     s->jaw.as<float>(), s->eyes.as<float>(), s->transl.as<float>(),
+                     fr->dynamic_offset ? s->dyn.as<float>() : nullptr, s->cams_in.as<float>(), nullptr, nullptr, true, st,
+                     sink, true);
+    if (rc != OMFS_OK) sink->error = rc;   // reported again by the collect, which also cleans up
+    return rc;
+}
+
+extern "C" int omfs_session_collect_host_png(omfs_session* s) {
+    OMFS_REQUIRE(s, "null argument");
+    OMFS_REQUIRE(s->n_pending > 0, "no clip outstanding");
+    OMFS_CUDA(cudaSetDevice(s->cfg.device));
+    PngSink* sink = s->pending[0];
+    // drain what is left of this clip, oldest batch first (batches of a later clip are not touched: their slots
+    // carry their own sink), then wait for its last copy
+    int rc = OMFS_OK;
+    for (int k = 0; k < omfs_session::kPngRing && rc == OMFS_OK; k++) {
+        const int r = (int)((s->stream_base + k) % omfs_session::kPngRing);   // oldest slot first
+        if (s->png_slot[r].active && s->png_slot[r].sink == sink) rc = png_drain(s, r);
+    }
+    if (!s->ev_collect) OMFS_CUDA(cudaEventCreateWithFlags(&s->ev_collect, cudaEventDisableTiming));
+    cudaError_t e = cudaEventRecord(s->ev_collect, s->copy_stream);
+    if (e == cudaSuccess) e = cudaEventSynchronize(s->ev_collect);
+    if (rc == OMFS_OK && e != cudaSuccess) rc = cuda_fail(e, "collect", __FILE__, __LINE__);
+    if (rc == OMFS_OK) rc = sink->error;
+    if (rc == OMFS_OK) {   // tile-pair overflow of any batch so far (sticky until the stream of calls is reset)
+        uint32_t h[2] = {0, 0};
+        e = cudaMemcpyAsync(h, s->counters.p, sizeof(h), cudaMemcpyDeviceToHost, s->copy_stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s->copy_stream);
+        if (e != cudaSuccess) rc = cuda_fail(e, "collect (flags)", __FILE__, __LINE__);
+        else if (h[1]) {
+            set_error("tile-pair list overflowed the session capacity (%zu): raise pair_capacity or call "
+                      "omfs_session_reserve_pairs, then submit the clip again", s->capacity);
+            rc = OMFS_ERR_CAPACITY;
+        }
+    }
+    delete sink;
+    for (int i = 1; i < s->n_pending; i++) s->pending[i - 1] = s->pending[i];
+    s->pending[--s->n_pending] = nullptr;
+    if (rc != OMFS_OK) {   // a failed stream of calls is wound up: nothing half-run stays pending
+        cudaDeviceSynchronize();
+        for (auto& slot : s->png_slot) slot.active = false;
+        while (s->n_pending > 0) delete s->pending[--s->n_pending];
+        for (int i = 0; i < omfs_session::kMaxPending; i++) s->pending[i] = nullptr;
+        cudaMemset(s->counters.p, 0, 256);
+        s->stream_base = 0;
+        s->copied_pending[0] = s->copied_pending[1] = false;
+    }
+    return rc;
+}
+
 extern "C" int omfs_session_render_device(omfs_session* s, const omfs_frames_desc* fr, uint8_t* d_out_u8,
                                           float* d_out_f32, void* stream) {
     OMFS_REQUIRE(s && fr, "null argument");
@@ -1033,6 +1152,7 @@ extern "C" int omfs_session_sync(omfs_session* s) {
     OMFS_CUDA(cudaStreamSynchronize(s->copy_stream));
     // with the deferred join the compositing stream is not joined into the caller's: wait for it here
     if (s->comp_stream) OMFS_CUDA(cudaStreamSynchronize(s->comp_stream));
+    if (s->png_stream) OMFS_CUDA(cudaStreamSynchronize(s->png_stream));
     if (s->defer_join)
         for (int ib = 0; ib < 2; ib++) s->ev_comp_pending[ib] = false;
     return finish_stats(s);

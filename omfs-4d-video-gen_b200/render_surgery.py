@@ -343,15 +343,17 @@ def _render_dataset(model_path: str, data_dir: str, iteration: int = -1,
         print(f"[render_surgery] Rendering {len(frames)} frames, {av.n} Gaussians, iteration {it} "
               f"(in-process, B200){where}")
         cams = [f.camera for f in frames]
+        renders_dir = os.path.join(train_dir, f"ours_{it}", "renders")
         try:
             if hi > lo:
-                images, pngs = _render_frames(model, params.slice(lo, hi), av, cams[lo:hi], want_png=True,
-                                              want_u8=need_frames)
+                # without raw frames the clip is streamed: the files of one chunk are written while the next renders
+                images, pngs = _render_frames(
+                    model, params.slice(lo, hi), av, cams[lo:hi], want_png=True, want_u8=need_frames,
+                    on_pngs=None if need_frames else (lambda first, got: write_png_files(renders_dir, got, first=lo + first)))
             else:
                 images, pngs = np.empty((0, cams[0].height, cams[0].width, 3), np.uint8), []
         except Exception as e:  # the reference surfaces renderer failures as RuntimeError (:317-322)
             raise RuntimeError(f"Rendering failed:\n{str(e)[-2000:]}") from e
-        renders_dir = os.path.join(train_dir, f"ours_{it}", "renders")
         write_png_files(renders_dir, pngs, first=lo)
         write_gt_frames(os.path.join(train_dir, f"ours_{it}", "gt"), data_dir, frames[lo:hi], first=lo)
     except Exception as e:
@@ -373,10 +375,18 @@ def render_with_gaussians(model_path: str, data_dir: str, iteration: int = -1,
     return _render_dataset(model_path, data_dir, iteration, clear_old_renders, need_frames=False)[0]
 
 
+STREAM_CHUNK = 64   # frames per clip of the streamed path below
+
+
 def _render_frames(model, params: FrameParams, av, cams, plan_offset=None, device: int | None = None,
-                   want_png: bool = False, want_u8: bool = True):
+                   want_png: bool = False, want_u8: bool = True, on_pngs=None):
     """uint8 [T,H,W,3]; with `want_png`, the pair (frames or None, list of PNG files as bytes) — the PNGs are
-    encoded on the device.  Frames may have different cameras (one per frame) but one image size."""
+    encoded on the device.  Frames may have different cameras (one per frame) but one image size.
+
+    With `want_png` and no raw frames wanted the clip is STREAMED (`Session.submit_host_png` / `collect_host_png`):
+    clips of STREAM_CHUNK frames, two in flight, so the GPU renders the next clip while this thread handles the
+    previous one's files.  `on_pngs(first_frame, [bytes, ...])`, if given, is called for every clip as it arrives
+    (the caller writes files while rendering goes on) and the returned list stays empty."""
     from . import runtime
     sizes = {(c.width, c.height) for c in cams}
     if len(sizes) != 1:
@@ -394,6 +404,41 @@ def _render_frames(model, params: FrameParams, av, cams, plan_offset=None, devic
         sess.set_subject(params.shape, params.static_offset, plan_offset)
         # runs of consecutive frames with the same camera are one call
         keys = [c.pack().tobytes() for c in cams]
+        if want_png and out is None:
+            # streamed: cut the runs into clips, keep two in flight
+            clips = []
+            t0 = 0
+            while t0 < T:
+                t1 = t0 + 1
+                while t1 < T and t1 - t0 < STREAM_CHUNK and keys[t1] == keys[t0]:
+                    t1 += 1
+                clips.append((t0, t1))
+                t0 = t1
+            cap = int(runtime.load_library().omfs_png_max_bytes(W, H))
+            n_max = max(b - a for a, b in clips)
+            bufs = [(runtime.PinnedArray((n_max * cap,), np.uint8), runtime.PinnedArray((n_max + 1,), np.uint64))
+                    for _ in range(min(2, len(clips)))]
+            flying: list = []
+
+            def collect():
+                a, b = flying.pop(0)
+                data, off = sess.collect_host_png()
+                view = memoryview(data)
+                got = [bytes(view[int(off[i]):int(off[i + 1])]) for i in range(b - a)]
+                if on_pngs is not None:
+                    on_pngs(a, got)
+                else:
+                    pngs.extend(got)
+
+            for k, (a, b) in enumerate(clips):
+                if len(flying) == 2:
+                    collect()
+                png_buf, off_buf = bufs[k % 2]
+                sess.submit_host_png(params.slice(a, b), [cams[a]], png_buf.array, off_buf.array)
+                flying.append((a, b))
+            while flying:
+                collect()
+            return out, pngs
         t0 = 0
         while t0 < T:
             t1 = t0 + 1

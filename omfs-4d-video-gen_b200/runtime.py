@@ -83,6 +83,8 @@ def load_library():
     L.omfs_png_encode.argtypes = [c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_size_t,
                                   c_void_p]
     L.omfs_session_sync.argtypes = [c_void_p]
+    L.omfs_session_submit_host_png.argtypes = [c_void_p, POINTER(FramesDesc), c_void_p, c_size_t, c_void_p]
+    L.omfs_session_collect_host_png.argtypes = [c_void_p]
     L.omfs_session_set_deferred_join.argtypes = [c_void_p, c_int]
     L.omfs_session_join.argtypes = [c_void_p, c_void_p]
     L.omfs_session_reserve_pairs.argtypes = [c_void_p, c_uint64]
@@ -203,6 +205,7 @@ class Session:
                                                  "lbs_weights", "faces", "xyzb", "scale_lo", "rot", "sh")])
         cfg = SessionConfig(self.width, self.height, self.max_batch, self.device, int(gemm_impl), int(bool(debug_keys)),
                             int(pair_capacity), (c_float * 3)(*[float(x) for x in bg]))
+        self._submitted: list = []   # clips between submit_host_png and collect_host_png (buffers kept alive)
         self._h = c_void_p()
         check(L.omfs_session_create(ctypes.byref(md), ctypes.byref(cfg), ctypes.byref(self._h)))
         del keep  # the library copied everything to the device
@@ -286,6 +289,30 @@ class Session:
         check(self._L.omfs_session_render_host_png(self._h, ctypes.byref(fd), _ptr(out_png), out_png.nbytes,
                                                    _ptr(out_offsets), _ptr(out_u8) if want_u8 else None))
         return (out_png, out_offsets[:S + 1], out_u8) if want_u8 else (out_png, out_offsets[:S + 1])
+
+    def submit_host_png(self, params, cams, out_png: np.ndarray, out_offsets: np.ndarray):
+        """Streaming form of render_host_png: enqueue the clip and return; collect_host_png() completes the oldest
+        submitted clip (at most two outstanding).  `out_png` / `out_offsets` (uint8 / uint64, S + 1 offsets) and the
+        parameter arrays must stay alive and untouched until that collect; they are held here until then."""
+        keep: list = [out_png, out_offsets]
+        fd, S = self._frames_desc(params, cams, keep)
+        if out_offsets.size < S + 1:
+            raise OmfsError(f"submit_host_png: offsets array has {out_offsets.size} entries, {S + 1} needed")
+        check(self._L.omfs_session_submit_host_png(self._h, ctypes.byref(fd), _ptr(out_png), out_png.nbytes,
+                                                   _ptr(out_offsets)))
+        self._submitted.append((keep, out_png, out_offsets, S))
+
+    def collect_host_png(self):
+        """Wait for the oldest submitted clip; returns its (png, offsets[:S + 1])."""
+        if not self._submitted:
+            raise OmfsError("collect_host_png: no clip outstanding")
+        _, out_png, out_offsets, S = self._submitted.pop(0)
+        try:
+            check(self._L.omfs_session_collect_host_png(self._h))
+        except OmfsError:
+            self._submitted.clear()   # the library dropped every outstanding clip
+            raise
+        return out_png, out_offsets[:S + 1]
 
     def render_device(self, d_params: dict, n_frames: int, n_views: int, d_out_u8=0, d_out_f32=0, stream=0):
         """Device pointers in (ints), device pointers out.  Asynchronous; call sync()."""

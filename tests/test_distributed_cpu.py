@@ -68,7 +68,7 @@ def _dropin_worker(rank, world, port, data, mdl, fail_rank):
                       LOCAL_RANK=str(rank))
     from omfs_b200 import render_surgery as rs
 
-    def fake_render(model, params, av, cams, plan_offset=None, device=None, want_png=False, want_u8=True):
+    def fake_render(model, params, av, cams, plan_offset=None, device=None, want_png=False, want_u8=True, on_pngs=None):
         if rank == fail_rank:
             raise ValueError("injected renderer failure")
         assert len(cams) == params.n_frames
@@ -76,7 +76,13 @@ def _dropin_worker(rank, world, port, data, mdl, fail_rank):
         out[..., 0] = np.round(params.translation[:, 0] * 1000).astype(np.uint8)[:, None, None]   # frame id
         out[..., 1] = 10 + rank
         # the stand-in for the device sink: the host encoder of the same package
-        return (out if want_u8 else None, [rs.encode_png(f) for f in out]) if want_png else out
+        pngs = [rs.encode_png(f) for f in out]
+        if want_png and on_pngs is not None:   # the streamed form: clips arrive one by one, nothing is returned
+            half = len(pngs) // 2
+            on_pngs(0, pngs[:half])
+            on_pngs(half, pngs[half:])
+            pngs = []
+        return (out if want_u8 else None, pngs) if want_png else out
 
     rs._render_frames = fake_render
     try:

@@ -106,3 +106,46 @@ def test_session_png_equals_raw_frames_across_batches():
             sess.render_host_png(params, [cam], out_png=np.empty(1000, np.uint8))
         png3, off3 = sess.render_host_png(params.slice(0, 3), [cam])      # the session is usable afterwards
         assert np.array_equal(_decode_both(png3[int(off3[2]):int(off3[3])].tobytes()), raw[2])
+
+
+def test_streamed_clips_equal_blocking_calls():
+    """omfs_session_submit_host_png / collect: clips of different lengths (one, several and an odd number of launch
+    groups) pushed two deep give, byte for byte, the PNG streams and offsets of the blocking call; a buffer that is
+    too small is reported by the collect and leaves the session usable."""
+    import omfs_b200  # noqa: F401
+    from omfs_b200 import avatar, runtime as rt, synthetic
+    T, W, H = 11, 128, 96
+    model, params, av, cam = synthetic.make_scene(n_gauss=5000, n_frames=T, width=W, height=H, n_verts=642)
+    baked = avatar.bake(av)
+    clips = [params.slice(0, 11), params.slice(3, 5), params.slice(1, 10), params.slice(0, 3), params.slice(2, 11)]
+    with rt.Session(model, baked, W, H, max_batch=3) as sess:
+        sess.set_subject(params.shape, params.static_offset)
+        cap = int(rt.load_library().omfs_png_max_bytes(W, H))
+        want = []
+        for c in clips:
+            png, off = sess.render_host_png(c, [cam])
+            want.append((png[:int(off[-1])].copy(), off.copy()))
+        bufs = [(rt.PinnedArray((T * cap,), np.uint8), rt.PinnedArray((T + 1,), np.uint64)) for _ in range(2)]
+        got = []
+        for i, c in enumerate(clips):
+            if i >= 2:
+                png, off = sess.collect_host_png()
+                got.append((png[:int(off[-1])].copy(), off.copy()))
+            sess.submit_host_png(c, [cam], bufs[i % 2][0].array, bufs[i % 2][1].array)
+        with pytest.raises(rt.OmfsError, match="outstanding"):
+            sess.render_host_png(clips[0], [cam])             # blocking calls wait their turn
+        while len(got) < len(clips):
+            png, off = sess.collect_host_png()
+            got.append((png[:int(off[-1])].copy(), off.copy()))
+        for (gp, go), (wp, wo) in zip(got, want):
+            assert np.array_equal(go, wo) and np.array_equal(gp, wp)
+        # too small a buffer: the collect says so, the session goes on
+        small = rt.PinnedArray((1000,), np.uint8)
+        sess.submit_host_png(clips[1], [cam], small.array, bufs[0][1].array)
+        with pytest.raises(rt.OmfsError, match="too small"):
+            sess.collect_host_png()
+        png, off = sess.render_host_png(clips[1], [cam])
+        assert np.array_equal(png[:int(off[-1])], want[1][0])
+        sess.submit_host_png(clips[3], [cam], bufs[1][0].array, bufs[1][1].array)
+        png, off = sess.collect_host_png()
+        assert np.array_equal(png[:int(off[-1])], want[3][0]) and np.array_equal(off, want[3][1])

@@ -316,13 +316,19 @@ def test_main_flow_with_a_stand_in_renderer(tmp_path, monkeypatch):
     n_train = len(flame_io.load_transforms(data, "train"))
     seen = {}
 
-    def fake_render(model_, params_, av_, cams, plan_offset=None, device=None, want_png=False, want_u8=True):
+    def fake_render(model_, params_, av_, cams, plan_offset=None, device=None, want_png=False, want_u8=True, on_pngs=None):
         seen["translation"] = params_.translation.copy()
         seen["jaw"] = params_.jaw_pose.copy()
         out = np.zeros((params_.n_frames, H, W, 3), np.uint8)
         out[..., 0] = np.arange(params_.n_frames, dtype=np.uint8)[:, None, None]
         # the stand-in for the device sink: the host encoder of the same package
-        return (out if want_u8 else None, [rs.encode_png(f) for f in out]) if want_png else out
+        pngs = [rs.encode_png(f) for f in out]
+        if want_png and on_pngs is not None:   # the streamed form: clips arrive one by one, nothing is returned
+            half = len(pngs) // 2
+            on_pngs(0, pngs[:half])
+            on_pngs(half, pngs[half:])
+            pngs = []
+        return (out if want_u8 else None, pngs) if want_png else out
 
     fake = tmp_path / "ffmpeg"
     fake.write_text("#!/bin/sh\nfor a in \"$@\"; do echo \"$a\" >> %s; done\ncat > %s\n" %

@@ -15,5 +15,5 @@ for N in (1,2,4,8):
     except Exception as e:
         print(N,"failed",e); continue
     if N==1: base=d["value"]; be=d["e2e"]["value"]
-    print(N, "value", round(d["value"]), "x%.2f"%(d["value"]/base), "e2e", round(d["e2e"]["value"]), "x%.2f"%(d["e2e"]["value"]/be), "ms/step", round(d["ms_per_step"],3), d["config"].get("gather"), [round(x,2) for x in d["ms_per_step_by_rank"]])
+    print(N, "value", round(d["value"]), "x%.2f"%(d["value"]/base), "e2e", round(d["e2e"]["value"]), "x%.2f"%(d["e2e"]["value"]/be), "blocking", round(d["e2e_blocking"]["value"]), "ms/step", round(d["ms_per_step"],3), d["config"].get("gather"), [round(x,2) for x in d["ms_per_step_by_rank"]])
 PY
