@@ -232,6 +232,7 @@ def main():
     ap.add_argument("--cpu-frames", type=int, default=300, help="time steps of the cpu_baseline sample")
     ap.add_argument("--ref-frames", type=int, default=60, help="time steps per step of --impl reference")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--stream-depth", type=int, default=3, choices=(2, 3), help="clips in flight of the streamed e2e path")
     ap.add_argument("--sync-steps", action="store_true",
                     help="A/B: every step joins its compositing into the rendering stream before the next one starts")
     ap.add_argument("--no-weak", action="store_true", help="N > 1: skip the weak-scaling companion measurement")
@@ -542,8 +543,9 @@ def main():
     # pinned output buffers).  Every step still uploads its own parameters from pinned host memory and delivers its own
     # PNG streams to host memory inside the timed region; what changes is that step i+1 renders while the tail of
     # step i (encode of the last group, offsets, stream copy) is in flight — the overlap a blocking call cannot have.
-    lanes = [(host_png, host_off), (runtime.PinnedArray((max(1, n_chunk_seg) * png_cap,), np.uint8),
-                                    runtime.PinnedArray((n_chunk_seg + 1,), np.uint64))]
+    n_lanes = 3 if args.stream_depth >= 3 else 2
+    lanes = [(host_png, host_off)] + [(runtime.PinnedArray((max(1, n_chunk_seg) * png_cap,), np.uint8),
+                                       runtime.PinnedArray((n_chunk_seg + 1,), np.uint64)) for _ in range(n_lanes - 1)]
     lane_no = [0]
     in_flight = [0]
     streamed_bytes = [0]
@@ -556,9 +558,9 @@ def main():
     def step_host_streamed():
         for lo in range(0, T_local, e2e_chunk):
             hi = min(T_local, lo + e2e_chunk)
-            if in_flight[0] == 2:
+            if in_flight[0] == n_lanes:
                 collect_one()
-            png_, off_ = lanes[lane_no[0] & 1]
+            png_, off_ = lanes[lane_no[0] % n_lanes]
             lane_no[0] += 1
             sess.submit_host_png(hp_slice(lo, hi), cams, png_.array, off_.array)
             in_flight[0] += 1
@@ -709,7 +711,7 @@ def main():
             **({"diagnosis": "--no-gather: NOT a valid multi-GPU number"} if args.no_gather and world > 1 else {}),
             "e2e": {"value": e2e_streamed, "unit": UNIT, "h2d_bytes_per_step": int(h2d_total),
                     "d2h_bytes_per_step": int(png_total.item()), "steps": e2e_steps,
-                    "note": "omfs_session_submit_host_png / omfs_session_collect_host_png on every rank, two clips in "
+                    "note": "omfs_session_submit_host_png / omfs_session_collect_host_png on every rank, up to three clips in "
                             "flight: every step uploads its own parameters from pinned host memory and delivers its own "
                             "frames to host memory as PNG files encoded on the device (filter + deflate + CRC in "
                             "csrc/png.cu) inside the timed region; step i+1 renders while the tail of step i is encoded "

@@ -245,7 +245,7 @@ int omfs_session_render_host_png(omfs_session* s, const omfs_frames_desc* frames
 
 /* The same call for a STREAM of clips (one after another, or one frame block per step): submit enqueues a clip and
  * returns without waiting; collect completes the OLDEST submitted clip — its PNG files and offsets are then in the
- * buffers given to its submit.  Up to two clips may be outstanding, so clip i+1 is uploaded and rendered while the last
+ * buffers given to its submit.  Up to three clips may be outstanding, so clip i+1 is uploaded and rendered while the last
  * batches of clip i are still being encoded and copied: the overlap a blocking call cannot have (the session's
  * buffers and ring slots simply continue from one call to the next).  Everything a clip reads or writes on the host
  * (parameter arrays, h_png, h_offsets) must stay valid and untouched until its collect; a tile-pair overflow or a

@@ -252,7 +252,7 @@ struct omfs_session {
     } png_slot[kPngRing];
     // streaming host calls (omfs_session_submit_host_png / omfs_session_collect_host_png): up to kMaxPending calls
     // whose frames are still on their way to host memory
-    static constexpr int kMaxPending = 2;
+    static constexpr int kMaxPending = 3;
     PngSink* pending[kMaxPending]{};
     int n_pending = 0;
     long long stream_base = 0;        // batches of all streaming calls so far: ring slot and buffer set continue across calls

@@ -292,7 +292,7 @@ class Session:
 
     def submit_host_png(self, params, cams, out_png: np.ndarray, out_offsets: np.ndarray):
         """Streaming form of render_host_png: enqueue the clip and return; collect_host_png() completes the oldest
-        submitted clip (at most two outstanding).  `out_png` / `out_offsets` (uint8 / uint64, S + 1 offsets) and the
+        submitted clip (at most three outstanding).  `out_png` / `out_offsets` (uint8 / uint64, S + 1 offsets) and the
         parameter arrays must stay alive and untouched until that collect; they are held here until then."""
         keep: list = [out_png, out_offsets]
         fd, S = self._frames_desc(params, cams, keep)
