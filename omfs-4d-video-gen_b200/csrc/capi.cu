@@ -928,6 +928,7 @@ extern "C" int omfs_session_render_host(omfs_session* s, const omfs_frames_desc*
     OMFS_REQUIRE(fr->expr && fr->rotation && fr->neck_pose && fr->jaw_pose && fr->eyes_pose && fr->translation &&
                      fr->cams,
                  "null frame array");
+    OMFS_REQUIRE(s->n_pending == 0, "streaming calls are outstanding: collect them first (omfs_session_collect_host_png)");
     OMFS_CUDA(cudaSetDevice(s->cfg.device));
     const int T = fr->n_frames;
     if (T == 0) return OMFS_OK;
@@ -1135,6 +1136,7 @@ extern "C" int omfs_session_render_device(omfs_session* s, const omfs_frames_des
     OMFS_REQUIRE(fr->expr && fr->rotation && fr->neck_pose && fr->jaw_pose && fr->eyes_pose && fr->translation &&
                      fr->cams,
                  "null frame array");
+    OMFS_REQUIRE(s->n_pending == 0, "streaming calls are outstanding: collect them first (omfs_session_collect_host_png)");
     OMFS_CUDA(cudaSetDevice(s->cfg.device));
     if (fr->n_frames == 0) return OMFS_OK;
     cudaStream_t st = (cudaStream_t)stream;  // NULL = the legacy default stream, as everywhere in this ABI
