@@ -53,6 +53,17 @@ def test_render_with_gaussians_from_disk_matches_oracle(tmp_path):
     # the in-memory path renders the same frames without the temporary dataset
     mem = rs.render_surgery_frames(model, params.slice(0, n_train), av, [cam] * n_train, 5.0, -4.0 * 1.5, 1.0)
     assert np.array_equal(mem, got)
+    # the streamed path in several clips (two frames each, two in flight): the files do not change by a byte
+    files = [open(os.path.join(out_dir, n), "rb").read() for n in names]
+    old_chunk, rs.STREAM_CHUNK = rs.STREAM_CHUNK, 2
+    tmp = rs.create_modified_dataset(data, lefort, bsso)
+    try:
+        out_dir = rs.render_with_gaussians(mdl, tmp)
+    finally:
+        rs.STREAM_CHUNK = old_chunk
+        shutil.rmtree(tmp, ignore_errors=True)
+    assert sorted(os.listdir(out_dir)) == names
+    assert [open(os.path.join(out_dir, n), "rb").read() for n in names] == files
     # pinned iteration + deterministic export flow
     out2 = rs.render_with_gaussians(mdl, data, iteration=3000)
     exp = rs.export_deterministic_frames(out2, str(tmp_path / "ab"), None, max_frames=2)

@@ -4,7 +4,7 @@
 # 3. ncu --set full of the top kernels.  Everything lands in gpurun_out/<tag>_*.
 tag=$1
 set -o pipefail
-CMD="python bench.py --steps 1 --warmup 1 --frames 60 --no-cpu"
+CMD="python bench.py --steps 1 --warmup 1 --frames 75 --no-cpu"
 python bench.py > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err || { echo "bench failed"; tail -5 gpurun_out/${tag}_bench.err; exit 1; }
 $CMD > gpurun_out/${tag}_plain.log 2>&1 || { echo "plain run failed"; exit 1; }
 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,smsp__inst_executed.sum --clock-control none -c 400 --csv \
