@@ -217,45 +217,76 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(int n_tiles_total, cons
 constexpr int kEsThreads = 256;
 constexpr int kEsGpt = 4;                            // Gaussians per thread
 constexpr int kEsChunk = kEsThreads * kEsGpt;        // 1024 depth-ordered Gaussians per work item
-constexpr int kEsWin = 1024;                         // pairs per warp per window (up to 1024 tiles)
 constexpr int kEsWarps = kEsThreads / 32;
+constexpr int kEsRecPad = 40;                        // sentinel records behind the compacted list (a step probes 32 past its cursor)
+constexpr uint32_t kEsOffBits = 21;                  // pair offset inside a (chunk, band): < 1024 Gaussians x 1024 tiles
+constexpr uint32_t kEsOffMask = (1u << kEsOffBits) - 1u;
+#ifndef OMFS_ES_MATCH
+#define OMFS_ES_MATCH 1   // 1: rank a step's pairs with one MATCH.ANY instead of one ballot per tile-id bit; 2: alternate
+#endif
+#ifndef OMFS_ES_CTAS
+#define OMFS_ES_CTAS 4    // resident CTAs per SM (41.3 KB of shared memory each at 1024 tiles, 64 registers)
+#endif
 
-// dynamic shared memory: pair[8][kEsWin] u32 | gidx, bx, by [kEsChunk] u32 | base[band tiles] u32 | wcnt[8][band tiles] u16
-constexpr int kEsWinShift = 10;
-static_assert((1 << kEsWinShift) == kEsWin, "window size must match its shift");
 // The per-tile arrays (bases, per-warp counters: 20 B per tile) never cover more than kEsBandTiles tiles: a frame with
 // more tiles is processed in BANDS of whole tile rows (1024^2: 4 bands of 16 rows x 64 tiles).  A CTA loads its
-// chunk's Gaussians once and runs count / publish / look-back / rank / scatter once per band on the rectangles clipped
-// to the band.  Round 1 sized the arrays for the whole frame instead: at 4096 tiles 115 KB per CTA (two CTAs per SM,
-// 28 KB of L1), 512-pair windows, rectangles walked three times — 15 issue slots per pair against 10 at 1024 tiles.
+// chunk's Gaussians once and runs compact / count / publish / look-back / rank / scatter once per band on the
+// rectangles clipped to the band.
 constexpr int kEsBandTiles = 1024;
 static inline int emit_scatter_band_rows(int gx, int gy) { return std::min(gy, std::max(1, kEsBandTiles / gx)); }
-// Up to 1024 tiles per band a CTA needs 65.6 KB: three CTAs take 195.3 KB, just inside the 196 KB shared-memory carve-out,
-// which leaves 60 KB of L1 for the record gathers.  ONE more KB per CTA selects the 228 KB carve-out (28 KB of L1) and
-// costs the kernel 25 % (measured: 0.336 -> 0.417 ms per 60 frames).  Anything added here must be paid for elsewhere.
-static inline size_t emit_scatter_smem(int band_tiles) {
+// dynamic shared memory: rec[kEsChunk + pad] uint2 | gidx, bx, by [kEsChunk] u32 | base[band tiles] u32 |
+// magic[gx + 1] u32 | wcnt[8][band tiles] u16.  41.3 KB at 1024 tiles: four CTAs per SM inside the 196 KB carve-out
+// (60 KB of L1 left for the record gathers — the kernel is sensitive to that).
+static inline size_t emit_scatter_smem(int band_tiles, int gx) {
     const int tp = (band_tiles + 1) & ~1;  // even row stride: the packed 16-bit counters are updated as 32-bit words
-    return sizeof(uint32_t) * (kEsWarps * kEsWin + 3 * kEsChunk + band_tiles) + sizeof(uint16_t) * kEsWarps * tp + 64;
+    return sizeof(uint2) * (kEsChunk + kEsRecPad) + sizeof(uint32_t) * (3 * kEsChunk + band_tiles + ((gx + 2) & ~1)) +
+           sizeof(uint16_t) * kEsWarps * tp + 64;
 }
 
-__global__ void __launch_bounds__(kEsThreads) emit_scatter_kernel(
+// The pairs of a (chunk, band) are numbered Gaussian-major in depth order, row-major inside a Gaussian's clipped
+// rectangle.  The Gaussians that own at least one pair are compacted into records {first pair | local index << 21,
+// first column | first row << 10 | width << 20}; first pairs increase strictly, so the 32 pairs [J, J + 32) of a
+// step find their owners with ONE probe of the 32 records behind the cursor `p` (the record that holds pair J or
+// ends just before it), one warp-wide OR of "record starts at pair J + r" bits, and a population count: every lane
+// produces one pair per step, whatever the rectangle sizes are.  (The first version let every thread walk its own
+// four rectangles into a shared-memory window: 19 % of the lanes busy at 4096 tiles, 27 instructions per pair visited,
+// a third of the kernel's instructions.)
+struct EsPair {
+    uint32_t tx, tyl, li;   // tile column, band-local tile row, local Gaussian index inside the chunk
+};
+__device__ __forceinline__ EsPair es_generate(const uint2* __restrict__ s_rec, const uint32_t* __restrict__ s_magic,
+                                              uint32_t J, uint32_t& p, int lane, uint32_t lanemask_le) {
+    const uint32_t rel = (s_rec[p + 1 + lane].x & kEsOffMask) - J;   // >= 0: records behind the cursor start at J or later
+    const uint32_t starts = __reduce_or_sync(0xffffffffu, rel < 32u ? (1u << rel) : 0u);
+    const uint2 rec = s_rec[p + __popc(starts & lanemask_le)];
+    p += __popc(starts);
+    const uint32_t k = J + (uint32_t)lane - (rec.x & kEsOffMask);    // my pair inside its Gaussian's rectangle
+    const uint32_t rw = rec.y >> 20;
+    const uint32_t cy = __umulhi(k + k, s_magic[rw]);                // k / rw, exact while k * rw < 2^31
+    EsPair r;
+    r.tx = (rec.y & 1023u) + (k - cy * rw);
+    r.tyl = ((rec.y >> 10) & 1023u) + cy;
+    r.li = rec.x >> kEsOffBits;
+    return r;
+}
+
+__global__ void __launch_bounds__(kEsThreads, OMFS_ES_CTAS) emit_scatter_kernel(
     int S, int N, int width, int height, int tiles, int band_rows, const uint32_t* __restrict__ perm_a,
     const uint32_t* __restrict__ perm_b, const uint32_t* __restrict__ perm_select,
     const uint32_t* __restrict__ tt, const float4* __restrict__ P0, const uint32_t* __restrict__ tile_start,
     const uint32_t* __restrict__ sort_count, uint32_t* __restrict__ chunk_counter,
     volatile uint32_t* __restrict__ status /*[chunks][tiles]*/, uint32_t* __restrict__ vals_out) {
     extern __shared__ __align__(16) unsigned char es_raw[];
-    constexpr int kWinShift = kEsWinShift;
-    constexpr int kWin = kEsWin;
     constexpr int TILE_BITS = 10;   // band-local tile ids < kEsBandTiles: one ballot per bit in the ranking
-    uint32_t* s_pair = reinterpret_cast<uint32_t*>(es_raw);            // [8][kWin]: band-local tile << 10 | local Gaussian
-    uint32_t* s_gidx = s_pair + kEsWarps * kWin;                       // [kEsChunk]
-    uint32_t* s_bx = s_gidx + kEsChunk;                                // [kEsChunk] 8x8-block columns the footprint reaches: min | max << 16
-    uint32_t* s_by = s_bx + kEsChunk;                                  // [kEsChunk] ... rows
     const int gx = (width + kTile - 1) / kTile, gy = (height + kTile - 1) / kTile;
     const int band_tiles = band_rows * gx;                             // <= kEsBandTiles (checked by the launcher)
+    uint2* s_rec = reinterpret_cast<uint2*>(es_raw);                   // [kEsChunk + kEsRecPad] compacted Gaussians of the band
+    uint32_t* s_gidx = reinterpret_cast<uint32_t*>(s_rec + kEsChunk + kEsRecPad);  // [kEsChunk]
+    uint32_t* s_bx = s_gidx + kEsChunk;                                // [kEsChunk] 8x8-block columns the footprint reaches: min | max << 16
+    uint32_t* s_by = s_bx + kEsChunk;                                  // [kEsChunk] ... rows
     uint32_t* s_base = s_by + kEsChunk;                                // [band_tiles]
-    uint16_t* s_wcnt = reinterpret_cast<uint16_t*>(s_base + band_tiles);  // [8][tp]
+    uint32_t* s_magic = s_base + band_tiles;                           // [gx + 1] 2^31 / width + 1
+    uint16_t* s_wcnt = reinterpret_cast<uint16_t*>(s_magic + ((gx + 2) & ~1));  // [8][tp]
     const int tp = (band_tiles + 1) & ~1;
     __shared__ uint32_t s_scan[8];
     __shared__ uint32_t s_chunk;
@@ -266,13 +297,12 @@ __global__ void __launch_bounds__(kEsThreads) emit_scatter_kernel(
     const int cps = (N + kEsChunk - 1) / kEsChunk;  // chunks per segment
     const uint32_t n_chunks = (uint32_t)cps * (uint32_t)S;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t lanemask_lt = (1u << lane) - 1u;
-    // t / gx for tile ids t < 2^18 as one multiply-high (exact while gx < 2^14)
-    const uint32_t gx_magic = 0xffffffffu / (uint32_t)gx + 1u;
+    const uint32_t lanemask_lt = (1u << lane) - 1u, lanemask_le = lanemask_lt | (1u << lane);
     // two bits: do blocks b0, b0 + 1 lie in [bmin, bmax]?  (an empty range is stored as min 0xffff, max 0)
     auto half_bits = [](uint32_t b0, uint32_t bmin, uint32_t bmax) -> uint32_t {
         return (uint32_t)(b0 >= bmin && b0 <= bmax) | ((uint32_t)(b0 + 1 >= bmin && b0 + 1 <= bmax) << 1);
     };
+    for (int r = threadIdx.x; r <= gx; r += kEsThreads) s_magic[r] = r ? 0x80000000u / (uint32_t)r + 1u : 0u;
 
     while (true) {
         // chunks are handed out in increasing order: every predecessor a chunk looks back at is owned
@@ -337,91 +367,59 @@ __global__ void __launch_bounds__(kEsThreads) emit_scatter_kernel(
         const int y1 = min(gy, y0 + band_rows);
         const int nt = (y1 - y0) * gx;             // tiles of this band
         const int tile_lo = y0 * gx;               // its first tile in the frame's numbering
-        int rminy[kEsGpt];                         // first row of the clipped rectangle, band-local
-        uint32_t cnt[kEsGpt];                      // pairs of the clipped rectangle
-        uint32_t acc = 0;
-#pragma unroll
-        for (int q = 0; q < kEsGpt; q++) {
-            const int cy0 = max(fminy[q], y0), cy1 = min(fmaxy[q], y1);
-            rminy[q] = cy0 - y0;
-            cnt[q] = cy1 > cy0 ? (uint32_t)((cy1 - cy0) * rw[q]) : 0u;
-            acc += cnt[q];
-        }
-        uint32_t total_pairs;
-        const uint32_t my_off = block_excl_scan_256(acc, s_scan, total_pairs);
-        // warp w owns the contiguous pair range [w*per_warp, (w+1)*per_warp) of the chunk, consumed in
-        // windows of kWin pairs; all warps step through their windows together
-        const uint32_t per_warp = (total_pairs + kEsWarps - 1) / kEsWarps;
-        const uint32_t n_win = (per_warp + kWin - 1) / kWin;
-        const uint32_t my_lo = min(total_pairs, (uint32_t)warp * per_warp);
-        const uint32_t my_n = min(total_pairs, (uint32_t)(warp + 1) * per_warp) - my_lo;
-
-        // expansion of the chunk's pairs IN ORDER into the owning warps' windows (window `win` of every warp)
-        auto expand = [&](uint32_t win) {
+        // ---- compact the Gaussians that own pairs in this band (one scan carries pair offsets and record slots)
+        uint32_t total_pairs, n_rec;
+        {
+            int rminy[kEsGpt];                     // first row of the clipped rectangle, band-local
+            uint32_t cnt[kEsGpt];                  // pairs of the clipped rectangle
+            uint32_t acc = 0;
 #pragma unroll
             for (int q = 0; q < kEsGpt; q++) {
-                if (cnt[q] == 0) continue;
-                uint32_t j = my_off;
+                const int cy0 = max(fminy[q], y0), cy1 = min(fmaxy[q], y1);
+                rminy[q] = cy0 - y0;
+                cnt[q] = cy1 > cy0 ? (uint32_t)((cy1 - cy0) * rw[q]) : 0u;
+                acc += (cnt[q] << 11) + (cnt[q] ? 1u : 0u);
+            }
+            uint32_t packed_total;
+            uint32_t run = block_excl_scan_256(acc, s_scan, packed_total);
+            total_pairs = packed_total >> 11;
+            n_rec = packed_total & 2047u;
 #pragma unroll
-                for (int qq = 0; qq < kEsGpt; qq++)
-                    if (qq < q) j += cnt[qq];
-                uint32_t owner = j / per_warp;
-                uint32_t wi = j - owner * per_warp;
-                int cx = 0, cy = 0;
-                const uint32_t li = (uint32_t)(threadIdx.x * kEsGpt + q);
-                for (uint32_t k = 0; k < cnt[q]; k++) {
-                    if ((wi >> kWinShift) == win) {
-                        const uint32_t tile = (uint32_t)((rminy[q] + cy) * gx + rminx[q] + cx);
-                        s_pair[owner * kWin + (wi & (kWin - 1))] = (tile << 10) | li;
-                    }
-                    if (++cx == rw[q]) {
-                        cx = 0;
-                        cy++;
-                    }
-                    if (++wi == per_warp) {
-                        wi = 0;
-                        owner++;
-                    }
+            for (int q = 0; q < kEsGpt; q++) {
+                if (cnt[q]) {
+                    const uint32_t li = (uint32_t)(threadIdx.x * kEsGpt + q);
+                    s_rec[run & 2047u] = make_uint2((run >> 11) | (li << kEsOffBits),
+                                                    (uint32_t)rminx[q] | ((uint32_t)rminy[q] << 10) | ((uint32_t)rw[q] << 20));
+                    run += (cnt[q] << 11) + 1u;
                 }
             }
-        };
-        // A chunk whose pairs fit ONE window per warp (the usual case up to 1024 tiles) is expanded once, up
-        // front, and every warp counts its own range straight from shared memory (lane-parallel, only its own
-        // counter row): the rectangles are walked once instead of twice.
-        const bool one_window = n_win <= 1;  // uniform over the CTA
-        if (one_window) {
-            expand(0);
+            if (threadIdx.x < kEsRecPad) s_rec[n_rec + threadIdx.x] = make_uint2(kEsOffMask, 0u);
             __syncthreads();
-            const uint32_t* wp = s_pair + warp * kWin;
+        }
+        // warp w owns the contiguous pair range [w*per_warp, (w+1)*per_warp) of the (chunk, band)
+        const uint32_t per_warp = (total_pairs + kEsWarps - 1) / kEsWarps;
+        const uint32_t my_lo = min(total_pairs, (uint32_t)warp * per_warp);
+        const uint32_t my_hi = min(total_pairs, (uint32_t)(warp + 1) * per_warp);
+        // cursor of my first pair: the last record that starts at or before it (32-ary search, two probes per lane;
+        // slots from the record count on hold sentinels, so a clamped probe reads "starts after every pair")
+        uint32_t p0 = 0;
+        if (my_hi > my_lo) {
+            uint32_t idx = min((uint32_t)lane * 32u, n_rec);
+            const uint32_t c1 = __ballot_sync(0xffffffffu, (s_rec[idx].x & kEsOffMask) <= my_lo);
+            const uint32_t b = (uint32_t)__popc(c1) - 1u;
+            idx = min(b * 32u + (uint32_t)lane, n_rec);
+            const uint32_t c2 = __ballot_sync(0xffffffffu, (s_rec[idx].x & kEsOffMask) <= my_lo);
+            p0 = b * 32u + (uint32_t)__popc(c2) - 1u;
+        }
+        // ---- count: every warp counts its own pairs per tile in its own counter row (order is irrelevant here)
+        {
             uint32_t* wrow = reinterpret_cast<uint32_t*>(s_wcnt + warp * tp);
-            for (uint32_t i = lane; i < my_n; i += 32) {
-                const uint32_t tile = wp[i] >> 10;
-                atomicAdd(wrow + (tile >> 1), 1u << (16 * (tile & 1u)));
-            }
-        } else {
-            // ---- pass A: per-warp, per-tile counts.  Order is irrelevant for counting, so every thread walks
-            // its own Gaussians' rectangles and bumps the counter of the warp that OWNS each pair.
-    #pragma unroll
-            for (int q = 0; q < kEsGpt; q++) {
-                if (cnt[q] == 0) continue;
-                uint32_t j = my_off;
-    #pragma unroll
-                for (int qq = 0; qq < kEsGpt; qq++)
-                    if (qq < q) j += cnt[qq];
-                uint32_t owner = j / per_warp;
-                uint32_t wi = j - owner * per_warp;
-                int cx = 0, cy = 0;
-                for (uint32_t k = 0; k < cnt[q]; k++) {
-                    const uint32_t tile = (uint32_t)((rminy[q] + cy) * gx + rminx[q] + cx);
-                    atomicAdd(reinterpret_cast<uint32_t*>(s_wcnt + owner * tp) + (tile >> 1), 1u << (16 * (tile & 1u)));
-                    if (++cx == rw[q]) {
-                        cx = 0;
-                        cy++;
-                    }
-                    if (++wi == per_warp) {
-                        wi = 0;
-                        owner++;
-                    }
+            uint32_t p = p0;
+            for (uint32_t J = my_lo; J < my_hi; J += 32) {
+                const EsPair g = es_generate(s_rec, s_magic, J, p, lane, lanemask_le);
+                if (J + (uint32_t)lane < my_hi) {
+                    const uint32_t t = g.tyl * (uint32_t)gx + g.tx;
+                    atomicAdd(wrow + (t >> 1), 1u << (16 * (t & 1u)));
                 }
             }
         }
@@ -485,29 +483,35 @@ __global__ void __launch_bounds__(kEsThreads) emit_scatter_kernel(
                 s_base[t] = __ldg(tile_start + (size_t)seg * tiles + tile_lo + t) + excl[g];
             }
         }
-        // ---- pass B: (expand the pairs IN ORDER into the owning warp's window,) rank, scatter
-        for (uint32_t win = 0; win < n_win; win++) {
-            __syncthreads();  // windows are free; for win 0 also: s_base / s_wcnt are final
-            if (!one_window) {
-                expand(win);
-                __syncthreads();
-            }
-            // my warp's window, 32 pairs per step, in pair order
-            const uint32_t w_lo = win * kWin;
-            const uint32_t w_n = (my_n > w_lo) ? min((uint32_t)kWin, my_n - w_lo) : 0u;
-            const uint32_t* wp = s_pair + warp * kWin;
+        __syncthreads();  // s_base / s_wcnt are final
+        // ---- rank + scatter: the same walk again, 32 pairs per step in pair order
+        {
             uint16_t* wc = s_wcnt + warp * tp;
-            for (uint32_t s0 = 0; s0 < w_n; s0 += 32) {
-                const bool valid = s0 + lane < w_n;
-                const uint32_t pr = valid ? wp[s0 + lane] : 0u;
-                const uint32_t t = pr >> 10;
-                uint32_t peers = __ballot_sync(0xffffffffu, valid);
+            uint32_t p = p0;
+            for (uint32_t J = my_lo; J < my_hi; J += 32) {
+                const EsPair g = es_generate(s_rec, s_magic, J, p, lane, lanemask_le);
+                const bool valid = J + (uint32_t)lane < my_hi;
+                const uint32_t t = g.tyl * (uint32_t)gx + g.tx;
+                // lanes of the step that hold my tile
+                uint32_t peers;
+#if OMFS_ES_MATCH == 1
+                peers = __match_any_sync(0xffffffffu, valid ? t : (0x80000000u | (uint32_t)lane));
+#else
+#if OMFS_ES_MATCH == 2
+                if ((J >> 5) & 1u) {
+                    peers = __match_any_sync(0xffffffffu, valid ? t : (0x80000000u | (uint32_t)lane));
+                } else
+#endif
+                {
+                    peers = __ballot_sync(0xffffffffu, valid);
 #pragma unroll
-                for (int b = 0; b < TILE_BITS; b++) {
-                    const bool bit = (t >> b) & 1u;
-                    const uint32_t bal = __ballot_sync(0xffffffffu, bit);
-                    peers &= bit ? bal : ~bal;
+                    for (int b = 0; b < TILE_BITS; b++) {
+                        const bool bit = (t >> b) & 1u;
+                        const uint32_t bal = __ballot_sync(0xffffffffu, bit);
+                        peers &= bit ? bal : ~bal;
+                    }
                 }
+#endif
                 const int leader = __ffs(peers) - 1;
                 uint32_t pre = 0;
                 if (valid && lane == leader) {
@@ -517,12 +521,11 @@ __global__ void __launch_bounds__(kEsThreads) emit_scatter_kernel(
                 pre = __shfl_sync(0xffffffffu, pre, leader & 31);
                 if (valid) {
                     // block hint of the pair: which halves of tile (tx, ty) the footprint's block range reaches
-                    const uint32_t li = pr & 1023u;
-                    const uint32_t tyl = __umulhi(t, gx_magic), tx = t - tyl * (uint32_t)gx, ty = tyl + (uint32_t)y0;
-                    const uint32_t rx = s_bx[li], ry = s_by[li];
-                    const uint32_t hx = half_bits(2u * tx, rx & 0xffffu, rx >> 16), hy = half_bits(2u * ty, ry & 0xffffu, ry >> 16);
+                    const uint32_t ty = g.tyl + (uint32_t)y0;
+                    const uint32_t rx = s_bx[g.li], ry = s_by[g.li];
+                    const uint32_t hx = half_bits(2u * g.tx, rx & 0xffffu, rx >> 16), hy = half_bits(2u * ty, ry & 0xffffu, ry >> 16);
                     const uint32_t hint = ((hy & 1u) ? hx : 0u) | ((hy & 2u) ? (hx << 2) : 0u);
-                    vals_out[s_base[t] + pre + __popc(peers & lanemask_lt)] = s_gidx[li] | (hint << kValIndexBits);
+                    vals_out[s_base[t] + pre + __popc(peers & lanemask_lt)] = s_gidx[g.li] | (hint << kValIndexBits);
                 }
                 __syncwarp();
             }
@@ -838,7 +841,7 @@ static int set_kernel_attrs(int tiles) {
     int rc;
     if ((rc = ensure_dyn_smem(rs_once, rs_onesweep_kernel, (int)sizeof(RsSmem)))) return rc;
     (void)tiles;
-    if ((rc = ensure_dyn_smem(es_once, emit_scatter_kernel, (int)emit_scatter_smem(kEsBandTiles)))) return rc;
+    if ((rc = ensure_dyn_smem(es_once, emit_scatter_kernel, (int)emit_scatter_smem(kEsBandTiles, kEsBandTiles)))) return rc;
     return OMFS_OK;
 }
 
@@ -927,7 +930,7 @@ int binning_emit_scatter(int S, int N, int width, int height, size_t capacity, c
         return OMFS_ERR_INVALID;
     }
     const int band_rows = emit_scatter_band_rows(gx, gy);
-    emit_scatter_kernel<<<kNumSMs * 4, kEsThreads, emit_scatter_smem(band_rows * gx), stream>>>(
+    emit_scatter_kernel<<<kNumSMs * OMFS_ES_CTAS, kEsThreads, emit_scatter_smem(band_rows * gx, gx), stream>>>(
         S, N, width, height, w.tiles, band_rows, w.perm[0], w.perm[1], w.counters + 6, d_tiles_touched,
         (const float4*)d_P0, w.tile_start, w.sort_count, w.counters + 4, w.status_emit, d_sorted_vals);
     count_launch();
