@@ -237,8 +237,9 @@ def main():
                     help="A/B: every step joins its compositing into the rendering stream before the next one starts")
     ap.add_argument("--no-weak", action="store_true", help="N > 1: skip the weak-scaling companion measurement")
     ap.add_argument("--no-gather", action="store_true", help="diagnosis only: skip the frame gather (flagged in config)")
-    ap.add_argument("--gather", default="p2p", choices=("p2p", "nccl"),
-                    help="frame exchange: copy-engine peer-to-peer pushes into rank 0 (default) or one NCCL gather")
+    ap.add_argument("--gather", default="p2p", choices=("p2p", "fused", "nccl"),
+                    help="frame exchange: copy-engine peer-to-peer pushes into rank 0 (default), the compositing kernel's "
+                         "own stores into rank 0's peer-mapped slot (fused: no local frame buffer, no copy), or one NCCL gather")
     args = ap.parse_args()
     wl = WORKLOADS[args.config]
     if args.units <= 0:
@@ -349,6 +350,7 @@ def main():
         ev_rendered = [torch.cuda.Event() for _ in frames_bufs]
         ev_gathered = [torch.cuda.Event() for _ in frames_bufs]
         step_no = [0]
+        local_only = [False]   # content check of the fused exchange: one step into the local buffer, nothing sent
         my_bytes = S_local * frame_bytes
 
         def step():
@@ -356,8 +358,15 @@ def main():
             step_no[0] += 1
             if world > 1:
                 stream.wait_event(ev_gathered[b])
+            fused = world > 1 and args.gather == "fused" and not args.no_gather and not local_only[0]
             if S_local:
-                sess.render_device(d_ptrs, T_local, nv, d_out_u8=frames_bufs[b].data_ptr(), stream=stream.cuda_stream)
+                # fused: the compositing kernel's uint8 stores ARE the exchange (rank 0's slot is mapped into this process)
+                sess.render_device(d_ptrs, T_local, nv, d_out_u8=peer.slot_ptr() if fused else frames_bufs[b].data_ptr(),
+                                   stream=stream.cuda_stream)
+            if fused:
+                return
+            if local_only[0]:
+                return
             if world > 1 and not args.no_gather:
                 # the only exchange of the path: finished frames to rank 0 over NVLink, on a second stream, which waits
                 # for the step's compositing (the rendering stream itself goes straight on to the next step)
@@ -422,6 +431,11 @@ def main():
             barrier()
             step()
             drain()
+            if args.gather == "fused":   # the same frames once more, into the local buffer, for the sums below
+                local_only[0] = True
+                step()
+                drain()
+                local_only[0] = False
             barrier()
             b = (step_no[0] - 1) % n_bufs
             mine = frame_sums(frames_bufs[b][:S_local], S_local)
@@ -698,7 +712,9 @@ def main():
                              "frame-invariant avatar streams (%.0f MB) stay L2-resident by design" % (
                                  48e-6 * main_res["batch"] * NG, 4e-6 * R * main_res["batch"], 240e-6 * NG),
                        "gather": ("none" if world == 1 else
-                                  ("copy-engine peer-to-peer pushes (CUDA IPC, NVLink)" if args.gather == "p2p" else "NCCL gather") +
+                                  ({"p2p": "copy-engine peer-to-peer pushes (CUDA IPC, NVLink)",
+                                    "fused": "compositing kernel stores straight into rank 0's peer-mapped slot (CUDA IPC, NVLink)",
+                                    "nccl": "NCCL gather"}[args.gather]) +
                                   " of every step's uint8 frames into rank 0 inside the timed region, on a second stream: "
                                   "step i's exchange overlaps step i+1's rendering; every rank waits for its last push "
                                   "before its end event and the time is the max over ranks"),

@@ -93,6 +93,9 @@ class PeerFrameGather:
     to hand the root's IPC handle to the peers.  `push(src_ptr, nbytes, stream)` enqueues this rank's
     copy on `stream` (ordered after the rendering by the caller's events); the data is complete on the
     root once every rank has synchronised that stream and the ranks have met at a barrier.
+    `slot_ptr()` is also a valid uint8 output pointer for `Session.render_device`: the compositing kernel then
+    stores its pixels straight into the root's slot over NVLink and no local frame buffer or copy exists
+    (`bench.py --gather fused`).
     """
 
     def __init__(self, slot_bytes: int, rank: int, world: int, exchange, dst: int = 0):
