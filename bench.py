@@ -51,7 +51,7 @@ WORKLOADS = {
             units=300, unit_name="frames", views=1, frames_per_unit=1, batch=75, pairs_per_seg=0,
             name="configs[2]: 512x512 x {units}-frame surgery video, 100k FLAME-bound Gaussians"),
     3: dict(metric="multi-view render images/s (1024^2, 16 views, 500k Gaussians)", width=1024, height=1024,
-            n_gauss=500_000, units=300, unit_name="frames", views=16, frames_per_unit=1, batch=32,
+            n_gauss=500_000, units=300, unit_name="frames", views=16, frames_per_unit=1, batch=128,
             pairs_per_seg=4_500_000,
             name="configs[3]: 1024x1024 x 16 camera views x {units} frames, 500k Gaussians (images = frames x views)"),
     4: dict(metric="plan-sweep images/s (512^2, 100k Gaussians, 120 frames per plan)", width=512, height=512,
