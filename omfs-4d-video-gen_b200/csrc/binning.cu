@@ -254,12 +254,15 @@ static inline size_t emit_scatter_smem(int band_tiles, int gx) {
 struct EsPair {
     uint32_t tx, tyl, li;   // tile column, band-local tile row, local Gaussian index inside the chunk
 };
-__device__ __forceinline__ EsPair es_generate(const uint2* __restrict__ s_rec, const uint32_t* __restrict__ s_magic,
-                                              uint32_t J, uint32_t& p, int lane, uint32_t lanemask_le) {
+// `starts` of a step: bit r set when a record's first pair is pair J + r (p = cursor before the step)
+__device__ __forceinline__ uint32_t es_starts(const uint2* __restrict__ s_rec, uint32_t J, uint32_t p, int lane) {
     const uint32_t rel = (s_rec[p + 1 + lane].x & kEsOffMask) - J;   // >= 0: records behind the cursor start at J or later
-    const uint32_t starts = __reduce_or_sync(0xffffffffu, rel < 32u ? (1u << rel) : 0u);
+    return __reduce_or_sync(0xffffffffu, rel < 32u ? (1u << rel) : 0u);
+}
+// the lane's pair of the step that starts at pair J (cursor p and `starts` of THAT step)
+__device__ __forceinline__ EsPair es_pair(const uint2* __restrict__ s_rec, const uint32_t* __restrict__ s_magic,
+                                          uint32_t J, uint32_t starts, uint32_t p, int lane, uint32_t lanemask_le) {
     const uint2 rec = s_rec[p + __popc(starts & lanemask_le)];
-    p += __popc(starts);
     const uint32_t k = J + (uint32_t)lane - (rec.x & kEsOffMask);    // my pair inside its Gaussian's rectangle
     const uint32_t rw = rec.y >> 20;
     const uint32_t cy = __umulhi(k + k, s_magic[rw]);                // k / rw, exact while k * rw < 2^31
@@ -269,6 +272,16 @@ __device__ __forceinline__ EsPair es_generate(const uint2* __restrict__ s_rec, c
     r.li = rec.x >> kEsOffBits;
     return r;
 }
+// The walk is software-pipelined: the cursor chain (probe -> warp-wide OR -> population count) of step i + 1 is issued
+// before the pairs of step i are decoded and used, so its shared-memory and reduction latency overlaps the ranking.
+#define OMFS_ES_WALK_BEGIN(J0)                                   \
+    uint32_t p = p0;                                             \
+    uint32_t starts_next = es_starts(s_rec, (J0), p, lane);
+#define OMFS_ES_WALK_STEP(J)                                     \
+    const uint32_t starts = starts_next, p_step = p;             \
+    p += __popc(starts);                                         \
+    starts_next = es_starts(s_rec, (J) + 32u, p, lane);          \
+    const EsPair g = es_pair(s_rec, s_magic, (J), starts, p_step, lane, lanemask_le);
 
 __global__ void __launch_bounds__(kEsThreads, OMFS_ES_CTAS) emit_scatter_kernel(
     int S, int N, int width, int height, int tiles, int band_rows, const uint32_t* __restrict__ perm_a,
@@ -414,9 +427,9 @@ __global__ void __launch_bounds__(kEsThreads, OMFS_ES_CTAS) emit_scatter_kernel(
         // ---- count: every warp counts its own pairs per tile in its own counter row (order is irrelevant here)
         {
             uint32_t* wrow = reinterpret_cast<uint32_t*>(s_wcnt + warp * tp);
-            uint32_t p = p0;
+            OMFS_ES_WALK_BEGIN(my_lo)
             for (uint32_t J = my_lo; J < my_hi; J += 32) {
-                const EsPair g = es_generate(s_rec, s_magic, J, p, lane, lanemask_le);
+                OMFS_ES_WALK_STEP(J)
                 if (J + (uint32_t)lane < my_hi) {
                     const uint32_t t = g.tyl * (uint32_t)gx + g.tx;
                     atomicAdd(wrow + (t >> 1), 1u << (16 * (t & 1u)));
@@ -487,9 +500,9 @@ __global__ void __launch_bounds__(kEsThreads, OMFS_ES_CTAS) emit_scatter_kernel(
         // ---- rank + scatter: the same walk again, 32 pairs per step in pair order
         {
             uint16_t* wc = s_wcnt + warp * tp;
-            uint32_t p = p0;
+            OMFS_ES_WALK_BEGIN(my_lo)
             for (uint32_t J = my_lo; J < my_hi; J += 32) {
-                const EsPair g = es_generate(s_rec, s_magic, J, p, lane, lanemask_le);
+                OMFS_ES_WALK_STEP(J)
                 const bool valid = J + (uint32_t)lane < my_hi;
                 const uint32_t t = g.tyl * (uint32_t)gx + g.tx;
                 // lanes of the step that hold my tile
