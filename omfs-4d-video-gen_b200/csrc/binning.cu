@@ -281,7 +281,7 @@ __device__ __forceinline__ EsPair es_pair(const uint2* __restrict__ s_rec, const
     const uint32_t starts = starts_next, p_step = p;             \
     p += __popc(starts);                                         \
     starts_next = es_starts(s_rec, (J) + 32u, p, lane);          \
-    const EsPair g = es_pair(s_rec, s_magic, (J), starts, p_step, lane, lanemask_le);
+    const EsPair g_step = es_pair(s_rec, s_magic, (J), starts, p_step, lane, lanemask_le);
 
 __global__ void __launch_bounds__(kEsThreads, OMFS_ES_CTAS) emit_scatter_kernel(
     int S, int N, int width, int height, int tiles, int band_rows, const uint32_t* __restrict__ perm_a,
@@ -431,7 +431,7 @@ __global__ void __launch_bounds__(kEsThreads, OMFS_ES_CTAS) emit_scatter_kernel(
             for (uint32_t J = my_lo; J < my_hi; J += 32) {
                 OMFS_ES_WALK_STEP(J)
                 if (J + (uint32_t)lane < my_hi) {
-                    const uint32_t t = g.tyl * (uint32_t)gx + g.tx;
+                    const uint32_t t = g_step.tyl * (uint32_t)gx + g_step.tx;
                     atomicAdd(wrow + (t >> 1), 1u << (16 * (t & 1u)));
                 }
             }
@@ -501,10 +501,31 @@ __global__ void __launch_bounds__(kEsThreads, OMFS_ES_CTAS) emit_scatter_kernel(
         {
             uint16_t* wc = s_wcnt + warp * tp;
             OMFS_ES_WALK_BEGIN(my_lo)
+            EsPair g;
+            {   // the first step's pairs
+                OMFS_ES_WALK_STEP(my_lo)
+                g = g_step;
+            }
             for (uint32_t J = my_lo; J < my_hi; J += 32) {
-                OMFS_ES_WALK_STEP(J)
+                // the NEXT step's pairs are decoded first (probing past the range's end reads sentinels: harmless), and
+                // everything that depends only on the pair — tile, block hint, list word — is formed before the ranking,
+                // so that the MATCH and the counter round trip overlap independent work
+                EsPair g_next;
+                {
+                    OMFS_ES_WALK_STEP(J + 32u)
+                    g_next = g_step;
+                }
                 const bool valid = J + (uint32_t)lane < my_hi;
                 const uint32_t t = g.tyl * (uint32_t)gx + g.tx;
+                uint32_t word;
+                {   // block hint of the pair: which halves of tile (tx, ty) the footprint's block range reaches
+                    const uint32_t ty = g.tyl + (uint32_t)y0;
+                    const uint32_t rx = s_bx[g.li], ry = s_by[g.li];
+                    const uint32_t hx = half_bits(2u * g.tx, rx & 0xffffu, rx >> 16), hy = half_bits(2u * ty, ry & 0xffffu, ry >> 16);
+                    const uint32_t hint = ((hy & 1u) ? hx : 0u) | ((hy & 2u) ? (hx << 2) : 0u);
+                    word = s_gidx[g.li] | (hint << kValIndexBits);
+                }
+                g = g_next;
                 // lanes of the step that hold my tile
                 uint32_t peers;
 #if OMFS_ES_MATCH == 1
@@ -532,14 +553,7 @@ __global__ void __launch_bounds__(kEsThreads, OMFS_ES_CTAS) emit_scatter_kernel(
                     wc[t] = (uint16_t)(pre + __popc(peers));
                 }
                 pre = __shfl_sync(0xffffffffu, pre, leader & 31);
-                if (valid) {
-                    // block hint of the pair: which halves of tile (tx, ty) the footprint's block range reaches
-                    const uint32_t ty = g.tyl + (uint32_t)y0;
-                    const uint32_t rx = s_bx[g.li], ry = s_by[g.li];
-                    const uint32_t hx = half_bits(2u * g.tx, rx & 0xffffu, rx >> 16), hy = half_bits(2u * ty, ry & 0xffffu, ry >> 16);
-                    const uint32_t hint = ((hy & 1u) ? hx : 0u) | ((hy & 2u) ? (hx << 2) : 0u);
-                    vals_out[s_base[t] + pre + __popc(peers & lanemask_lt)] = s_gidx[g.li] | (hint << kValIndexBits);
-                }
+                if (valid) vals_out[s_base[t] + pre + __popc(peers & lanemask_lt)] = word;
                 __syncwarp();
             }
         }
