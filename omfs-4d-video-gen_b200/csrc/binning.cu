@@ -12,11 +12,13 @@
 //      because the first pass starts from the identity permutation.
 //   2. TILE COUNTS: how many Gaussians touch each tile (shared-memory histograms), then ONE scan over
 //      the S*tiles counters — which is already the tile-range table (U9) and the pair count.
-//   3. EMIT + SCATTER, fused: chunks of 1024 depth-ordered Gaussians expand their pairs in shared
-//      memory, rank them per tile with warp ballots, resolve the chunk's offset inside every tile by
-//      decoupled look-back over the chunks before it, and write each Gaussian index straight to its
-//      FINAL position.  It is a one-pass onesweep with one bin per tile; inside a tile, emission order
-//      IS depth order, so the depth bits are never written and no pair is ever moved twice.
+//   3. EMIT + SCATTER, fused: a chunk of 1024 depth-ordered Gaussians compacts the ones that own pairs into
+//      records, every warp walks its share of the chunk's pair space 32 pairs per step (every lane produces one
+//      pair per step from the records: es_starts / es_pair), ranks the step's pairs per tile with one MATCH.ANY,
+//      resolves the chunk's offset inside every tile by decoupled look-back over the chunks before it, and
+//      writes each Gaussian index straight to its FINAL position.  It is a one-pass onesweep with one bin per
+//      tile; inside a tile, emission order IS depth order, so the depth bits are never written and no pair is
+//      ever moved twice.
 // Traffic per pair drops from (8 + 24*6) = 152 B to 4 B written once (L2 merges the 4-byte scatters of
 // neighbouring chunks: the whole value array of a batch fits in the 126 MB L2), plus 4 + 16*4 B per
 // Gaussian for the depth sort.  The 64-bit keys exist only on request (rebuild_keys_kernel) for the
