@@ -313,6 +313,35 @@ def test_wide_frame_in_ragged_tile_bands(rt):
     sess.close()
 
 
+@pytest.mark.parametrize("W,H,n_gauss", [(512, 512, 3000), (1040, 560, 1500)])
+def test_screen_filling_splats_long_pair_walks(rt, W, H, n_gauss):
+    """Rectangles of hundreds of tiles: a 1024-Gaussian chunk of emit_scatter owns several hundred thousand pairs
+    (pair offsets far past 2^16, tens of thousands of pairs per warp, most steps of the pair walk inside ONE
+    rectangle, a cursor that advances by zero or one record per step), once in a single band and once in ragged
+    bands.  Sorted keys, values and ranges against the oracle bit for bit; image on the shared vertices."""
+    import omfs_b200  # noqa: F401
+    import oracle
+    from omfs_b200 import avatar, synthetic
+    T = 1
+    model, params, av, cam = synthetic.make_scene(n_gauss=n_gauss, n_frames=T, width=W, height=H, n_verts=642)
+    av.scaling[:] = av.scaling + np.float32(3.0)             # 20x larger splats
+    av.opacity[:] = -np.abs(av.opacity) - np.float32(3.0)    # faint: the lists are walked to their ends
+    baked = avatar.bake(av)
+    sess, u8, img = run_session(rt, model, params, baked, [cam], W, H, max_batch=T)
+    verts = sess.tap_array("verts", (T, 642, 3), np.float32)
+    ref = oracle.render(model, params, baked, [cam.pack()] * T, W, H, verts=verts)
+    tiles = ((W + 15) // 16) * ((H + 15) // 16)
+    R = ref.binned.n_pairs
+    assert R == sess.dims()["pairs_last_batch"]
+    assert R / n_gauss > 100.0 and R > 250_000               # rectangles of hundreds of tiles
+    assert np.array_equal(sess.tap_array("keys", (R,), np.uint64), ref.binned.sorted_keys)
+    assert np.array_equal(rt.pair_indices(sess.tap_array("vals", (R,), np.uint32)), ref.binned.sorted_values)
+    assert np.array_equal(sess.tap_array("ranges", (T * tiles, 2), np.uint32), ref.binned.ranges)
+    assert np.abs(img - ref.image).max() <= 2e-4
+    assert (oracle.to_uint8(ref.image) != u8).mean() < 1e-4
+    sess.close()
+
+
 def test_needle_splats_take_the_guarded_loop(rt):
     """Long thin splats (one axis x150, the others /8): their conics are badly conditioned (D <= 1e-4 tr^2), which is
     when the compositing kernel may NOT drop ex_blend's `e <= lo` rejection — rounds that hold one run the guarded
