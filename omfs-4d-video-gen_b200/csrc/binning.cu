@@ -569,6 +569,9 @@ __global__ void __launch_bounds__(kEsThreads, OMFS_ES_CTAS) emit_scatter_kernel(
     }
 }
 
+#undef OMFS_ES_WALK_BEGIN
+#undef OMFS_ES_WALK_STEP
+
 // ---------------------------------------------------------------------------------- histograms
 // hist[seg][pass][256] from ONE read of the keys.  Digits listed in uniform_mask are almost always
 // identical across a warp's 32 consecutive keys (depth exponent byte, high tile byte): they are counted
