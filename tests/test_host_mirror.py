@@ -228,8 +228,24 @@ def test_frame_sink(tmp_path, monkeypatch):
     bad.write_text("#!/bin/sh\ncat > /dev/null\necho boom >&2\nexit 3\n")
     bad.chmod(0o755)
     monkeypatch.setattr(rs, "_get_ffmpeg_path", lambda: str(bad))
-    with pytest.raises(RuntimeError, match="ffmpeg failed"):
+    with pytest.raises(RuntimeError, match="(?s)ffmpeg failed.*boom"):
         rs.stitch_video_frames(frames, str(tmp_path / "v2.mp4"))
+    # an encoder that dies before it has read its input (the pipe breaks under the one blocking write of a clip far
+    # larger than a pipe buffer) and one that floods stderr while the frames are still being written: neither may
+    # hang the caller, both surface as the reference's RuntimeError with the encoder's own words
+    big = np.zeros((40, 128, 128, 3), np.uint8)   # 1.9 MB
+    early = tmp_path / "ffmpeg_early"
+    early.write_text("#!/bin/sh\necho no such codec >&2\nexit 1\n")
+    early.chmod(0o755)
+    monkeypatch.setattr(rs, "_get_ffmpeg_path", lambda: str(early))
+    with pytest.raises(RuntimeError, match="(?s)ffmpeg failed.*no such codec"):
+        rs.stitch_video_frames(big, str(tmp_path / "v4.mp4"))
+    chatty = tmp_path / "ffmpeg_chatty"
+    chatty.write_text("#!/bin/sh\nhead -c 300000 /dev/zero | tr '\\0' 'x' >&2\ncat > %s\n" % (tmp_path / "big.bin"))
+    chatty.chmod(0o755)
+    monkeypatch.setattr(rs, "_get_ffmpeg_path", lambda: str(chatty))
+    rs.stitch_video_frames(big, str(tmp_path / "v5.mp4"))
+    assert (tmp_path / "big.bin").stat().st_size == big.size
     with pytest.raises(FileNotFoundError):
         rs.stitch_video_frames(frames[:0], str(tmp_path / "v3.mp4"))
 
@@ -452,3 +468,30 @@ def test_read_npz_equals_numpy_load(tmp_path):
             assert got[k].shape == want[k].shape and np.array_equal(got[k], want[k]), (path, k)
             assert got[k].dtype.newbyteorder("=") == want[k].dtype.newbyteorder("="), (path, k)
     assert all(v.flags.writeable for v in flame_io.read_npz(p).values())
+    # the stored-archive walk (local file headers of one read, no zipfile) is what served the first file ...
+    direct = flame_io._read_stored_zip(p)
+    assert set(direct) == set(np.load(p).files) and all(np.array_equal(direct[k], np.load(p)[k]) for k in direct)
+    # ... it refuses what it does not cover (compressed members, a stored archive of odd members, a truncated file,
+    # no archive at all), and read_npz still answers through zipfile / np.load where an answer exists
+    with pytest.raises(ValueError):
+        flame_io._read_stored_zip(odd)
+    stored_odd = str(tmp_path / "stored_odd.npz")
+    np.savez(stored_odd, s=np.array("txt"), be=np.array([1, 2], dtype=">f4"), f=np.asfortranarray(np.ones((2, 3))))
+    with pytest.raises(ValueError):
+        flame_io._read_stored_zip(stored_odd)
+    got = flame_io.read_npz(stored_odd)
+    assert str(got["s"]) == "txt" and np.array_equal(got["be"], [1, 2]) and got["f"].shape == (2, 3)
+    cut = str(tmp_path / "cut.npz")
+    with open(p, "rb") as f:
+        blob = f.read()
+    with open(cut, "wb") as f:
+        f.write(blob[: len(blob) // 2])
+    with pytest.raises(ValueError):
+        flame_io._read_stored_zip(cut)
+    with pytest.raises(Exception):
+        flame_io.read_npz(cut)
+    # a large member (zip64 sizes in the extra field, as np.savez always writes them) and an empty archive member
+    big = str(tmp_path / "big.npz")
+    np.savez(big, a=np.arange(300_000, dtype=np.float32).reshape(1000, 300), e=np.zeros((0, 3), np.float32))
+    d = flame_io._read_stored_zip(big)
+    assert np.array_equal(d["a"], np.arange(300_000, dtype=np.float32).reshape(1000, 300)) and d["e"].shape == (0, 3)
