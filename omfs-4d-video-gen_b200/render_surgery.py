@@ -543,11 +543,16 @@ def stitch_video_frames(frames_u8: np.ndarray, output_path: str, fps: int = 30):
     with tempfile.TemporaryFile() as log:
         proc = subprocess.Popen(cmd, stdin=subprocess.PIPE, stdout=subprocess.DEVNULL, stderr=log)
         try:
-            proc.stdin.write(memoryview(frames_u8.reshape(-1)))
-            proc.stdin.close()
-        except BrokenPipeError:   # the encoder died early: its exit status and messages say why
-            pass
-        rc = proc.wait()
+            try:
+                proc.stdin.write(memoryview(frames_u8.reshape(-1)))
+                proc.stdin.close()
+            except BrokenPipeError:   # the encoder died early: its exit status and messages say why
+                pass
+            rc = proc.wait()
+        except BaseException:         # interrupted or failed while feeding it: never leave an encoder behind
+            proc.kill()
+            proc.wait()
+            raise
         if rc != 0:
             log.seek(0)
             raise RuntimeError(f"ffmpeg failed:\n{log.read().decode(errors='replace')}")
